@@ -1,0 +1,174 @@
+/*
+ * popcorn_b200 — C-ABI of the B200-native (sm_100a) POPCORN dense-prediction hot path.
+ *
+ * Drop-in boundary: the reference has no FFI — its "kernels" are the
+ * torch.nn calls inside model/popcorn.py and model/DDA_model/utils/networks.py.  Each entry
+ * point below names the reference code it replaces (paths relative to the reference root).
+ * The Python host (popcorn_b200/model/popcorn.py) binds these with ctypes; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - all tensor pointers are DEVICE pointers, fp32, planar NCHW unless stated; strides in elements
+ *   - every call enqueues on `stream` (a cudaStream_t) and returns immediately; no internal threads,
+ *     no allocation: scratch comes from the caller-provided workspace (torch's caching allocator)
+ *   - return value 0 = ok, otherwise a cudaError_t value or PC_ERR_*; pc_last_error() gives the text
+ *   - no exceptions cross the ABI; re-entrant per (workspace, stream)
+ */
+#ifndef POPCORN_B200_H
+#define POPCORN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* pc_stream_t; /* cudaStream_t */
+
+#define PC_ERR_INVALID 10001   /* bad argument */
+#define PC_ERR_WORKSPACE 10002 /* workspace too small */
+
+#define PC_DDA_FEATURES 0 /* DualStreamUNet(..., return_features=True): [B,F,H,W], F = 8 per present stream */
+#define PC_DDA_BUILTUP 1  /* sigmoid(logits) of create_building_score: [B,1,H,W] */
+
+/* Library version (major*100+minor) and last error text of the calling thread. */
+int pc_version(void);
+const char* pc_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Packed weights.  The host folds BatchNorm(eval) into each conv and lays the
+ * floats out in the order the kernels stage them: per stream (sar, optical) 12 layer blocks
+ *   conv block  : w[cin][ky*3+kx][cout], bias[cout]
+ *   convT block : w[cin][dy*2+dx][cout], bias[cout]
+ * in the order inc.0 inc.3 down1.0 down1.3 down2.0 down2.3 up2.up up2.0 up2.3 up1.up up1.0 up1.3,
+ * followed by fusion_out_conv (16 w + 1 b, padded to 20), sar_out_conv (8+1 -> 12), optical_out_conv
+ * (8+1 -> 12).  pc_dda_pack_floats() returns the total length; pc_dda_pack_offset(stream, layer)
+ * the offset of a block (layer 12 with stream 0/1/2 = fusion/sar/optical out conv).
+ * Replaces: the nn.Module parameter storage of model/DDA_model/utils/networks.py:154-181.
+ * --------------------------------------------------------------------------------------------- */
+int pc_dda_pack_floats(void);
+int pc_dda_pack_offset(int stream, int layer);
+
+/* Head pack: W1t[k=Cin][64], b1[64], W2t[64][64], b2[64], W3t[64][64], b3[64], w4[64] (row 0 of
+ * head.6.weight — only channel 0 is used, model/popcorn.py:162-164), b4 (+3 pad).  Cin = 16 or 8. */
+int pc_head_pack_floats(int head_in);
+
+/* ---------------------------------------------------------------------------------------------
+ * pc_dda_forward — one DualStreamUNet copy on a (reflect-padded) window.
+ * Replaces: POPCORN.add_padding + channel reorder + DualStreamUNet.forward (+ fusion_out_conv +
+ *           sigmoid + revert_padding)   model/popcorn.py:126-158 and 279-322,
+ *           model/DDA_model/utils/networks.py:121-151, 192-237, 253-330.
+ *   x          [B,C,H,W] view (C = 6: R,G,B,NIR,VV,VH | 2: VV,VH | 4: R,G,B,NIR), strides given
+ *   pad_*      reflect padding applied virtually by the loader (14/14/14/14 for the builtup pass,
+ *              the pad-to-64 amounts for the feature pass, 0 otherwise); nothing is materialised
+ *   mode       PC_DDA_FEATURES -> out[B,F,H,W] ; PC_DDA_BUILTUP -> out[B,1,H,W]; cropped back to HxW
+ * --------------------------------------------------------------------------------------------- */
+size_t pc_dda_workspace_bytes(int B, int C, int Hv, int Wv);
+int pc_dda_forward(const float* wpack, const float* x, int B, int C, int H, int W, long long x_bstride,
+                   long long x_cstride, int x_rstride, int pad_top, int pad_bottom, int pad_left, int pad_right,
+                   int mode, float* out, long long out_bstride, long long out_cstride, int out_rstride,
+                   void* workspace, size_t workspace_bytes, pc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * pc_head_dense_forward — fused occupancy head on every pixel.
+ * Replaces: self.head(headin)[:,0] -> relu -> * building_counts -> region sum
+ *           model/popcorn.py:164, 170, 178, 184-190 (and the per-region loop of
+ *           data/PopulationDataset.py:705-712 when `ids` is a full id raster).
+ *   feats [B,Cin,H,W] (strided), builtup [B,1,H,W] or NULL (occupancymodel=False: dens = relu(out))
+ *   dens, scale   [B,H,W] outputs (scale may be NULL)
+ *   ids           optional int32 [B,H,W] region ids; sums (double[B? no: R]) += dens where 0 <= id < R
+ *   census_idx    optional int32 [B]: if given, sums has B entries and pixel p of image b contributes to
+ *                 sums[b] iff ids[b,p] == census_idx[b]  (popcount of model/popcorn.py:186-187);
+ *                 with ids == NULL and sums != NULL: sums[b] += all pixels of image b (:190)
+ * --------------------------------------------------------------------------------------------- */
+int pc_head_dense_forward(const float* hpack, int head_in, const float* feats, long long f_bstride,
+                          long long f_cstride, int f_rstride, const float* builtup, long long bu_bstride,
+                          int bu_rstride, int B, int H, int W, float* dens, float* scale, long long o_bstride,
+                          int o_rstride, const int32_t* ids, long long id_bstride, int id_rstride,
+                          const int32_t* census_idx, double* sums, int R, pc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Sparse occupancy head (training path).
+ * pc_sparse_mask_compact — get_sparsity_mask live branch + row-major compaction.
+ * Replaces: model/popcorn.py:361-377 and the boolean-index gather of :214-226.
+ *   builtup [B,H,W], admin [B,H,W] fp32 ids (reference dtype) , census_idx int32 [B]
+ *   grid_rows uint8[H], grid_cols uint8[W]: the CPU-RNG 60x60 grid (host draws it, popcorn.py:367-368)
+ *   mask_out uint8 [B,H,W]; idx_out int32 [B*H*W] (first n valid, row-major (b,h,w) order);
+ *   n_out   int32 device scalar.  If the mask is empty the region mask is used (popcorn.py:374-375).
+ *   workspace: pc_compact_workspace_bytes(B*H*W)
+ * --------------------------------------------------------------------------------------------- */
+size_t pc_compact_workspace_bytes(long long npix);
+int pc_sparse_mask_compact(const float* builtup, const float* admin, const int32_t* census_idx,
+                           const uint8_t* grid_rows, const uint8_t* grid_cols, int use_builtup, int B, int H, int W,
+                           uint8_t* mask_out, int32_t* idx_out, int32_t* n_out, void* workspace,
+                           size_t workspace_bytes, pc_stream_t stream);
+
+/* pc_head_sparse_forward — gather + MLP + scatter (+ popcount) on the n compacted pixels.
+ * Replaces: sparse_module_forward + relu + *builtup + masked sum, model/popcorn.py:195-228, 170-187.
+ *   feats [B,Cin,H,W] contiguous per image (f_bstride, f_cstride); idx int32[n] flat (b*H*W + p)
+ *   n_dev: device int32 (n); n_max: upper bound used to size the grid (B*H*W is always valid)
+ *   dens [B*H*W] must be zero-filled by the caller (scatter target); scale_sel [n] = relu(out) row-major
+ *   popcount double[B] += dens over selected pixels of image b (mask is inside the region by construction)
+ */
+int pc_head_sparse_forward(const float* hpack, int head_in, const float* feats, long long f_bstride,
+                           long long f_cstride, const float* builtup, const int32_t* idx, const int32_t* n_dev,
+                           long long n_max, long long HW, float* dens, float* scale_sel, double* popcount,
+                           pc_stream_t stream);
+
+/* pc_head_sparse_backward — gradients of the head parameters for the census-supervised step.
+ * Replaces: autograd backward of model/popcorn.py:162-187 under unet_no_grad=True (run_train.py:201-230).
+ *   g_popcount float[B]  : dL/dpopcount[b]
+ *   g_scale_coef         : coefficient c of the scale regulariser, dL/dscale_sel[i] += c * sign(scale_sel[i])
+ *                          (utils/losses.py:74-76: lam * scale_regularization / n)
+ *   g_scale_sel float[n] or NULL : additional explicit dL/dscale_sel
+ *   grad_pack            : device float[pc_head_pack_floats(head_in)] gradient in hpack layout (w4/b4 slots =
+ *                          row 0 of head.6; row 1 has zero gradient), overwritten
+ *   workspace            : pc_head_bwd_workspace_bytes(head_in)
+ *  Deterministic: fixed grid, fixed tile->CTA assignment, two-stage fixed-order reduction, no float atomics.
+ */
+size_t pc_head_bwd_workspace_bytes(int head_in);
+int pc_head_sparse_backward(const float* hpack, int head_in, const float* feats, long long f_bstride,
+                            long long f_cstride, const float* builtup, const int32_t* idx, const int32_t* n_dev,
+                            long long n_max, long long HW, const float* g_popcount, float g_scale_coef,
+                            const float* g_scale_sel, float* grad_pack, void* workspace, size_t workspace_bytes,
+                            pc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Census aggregation.
+ * pc_region_sum — sums[id[p]] += dens[p] for 0 <= id < R (ids int32; id < 0 or >= R ignored).
+ * Replaces: the R-iteration crop/mask/sum loop of data/PopulationDataset.py:696-725 (and :842-846).
+ * pc_region_sum_backward — g_dens[p] = (0 <= id[p] < R) ? g_sums[id[p]] : 0   (autograd of the above).
+ * pc_region_scale — dens[p] *= factor[id[p]]  (adjust_map_to_census, data/PopulationDataset.py:846-850).
+ * --------------------------------------------------------------------------------------------- */
+int pc_region_sum(const float* dens, const int32_t* ids, long long npix, int R, double* sums, pc_stream_t stream);
+int pc_region_sum_backward(const float* g_sums, const int32_t* ids, long long npix, int R, float* g_dens,
+                           pc_stream_t stream);
+int pc_region_scale(float* dens, const int32_t* ids, long long npix, int R, const float* factor, pc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Country-map accumulation (run_eval.py:127-154).
+ * pc_accumulate_tile — map[y0+r, x0+c] += dens[r,c]; map_sq += dens^2; scale maps likewise; count += 1
+ *                      for the tile's centre window rows [r0,r1) x cols [c0,c1).
+ * pc_finalize_map    — where count > 1: mean = sum / count; std = sqrt((sumsq - mean^2*count)/(count-1)).
+ * --------------------------------------------------------------------------------------------- */
+int pc_accumulate_tile(const float* dens, const float* scale, int t_rstride, int r0, int r1, int c0, int c1,
+                       float* map, float* map_sq, float* smap, float* smap_sq, int16_t* count, int m_rstride,
+                       int y0, int x0, pc_stream_t stream);
+int pc_finalize_map(float* map, float* map_sq, float* smap, float* smap_sq, const int16_t* count, long long npix,
+                    pc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Unit-test hooks (tests/test_gpu_kernels.py): ONE fused conv3x3(+folded BN)+ReLU layer, optionally with a
+ * second concatenated source placed at an offset (Up block) and a fused 2x2 max-pool output, and ONE
+ * ConvTranspose2d(k2,s2) layer, on plain contiguous tensors.  w uses the packed block layouts above.
+ * Same kernels pc_dda_forward schedules; replaces networks.py:258-267 / :289 / :302 one layer at a time.
+ * --------------------------------------------------------------------------------------------- */
+int pc_test_conv3x3(const float* a, int cin_a, int a_H, int a_W, int a_oy, int a_ox, int a_reflect, const float* b,
+                    int cin_b, int b_H, int b_W, int b_oy, int b_ox, const float* w, int cout, int H, int W,
+                    float* out, float* pool, pc_stream_t stream);
+int pc_test_convt2x2(const float* in, int C, int Hl, int Wl, const float* w, float* out, pc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POPCORN_B200_H */

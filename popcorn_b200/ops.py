@@ -1,0 +1,188 @@
+"""Thin torch-tensor front ends over the C-ABI (pointers, strides, stream, workspace)."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+PC_DDA_FEATURES, PC_DDA_BUILTUP = 0, 1
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("popcorn_b200: tensors must live on a CUDA device (no CPU path exists)")
+
+
+class Workspace:
+    """Grow-only scratch buffer owned by torch's caching allocator."""
+
+    def __init__(self):
+        self.buf: Optional[torch.Tensor] = None
+
+    def get(self, nbytes: int, device) -> torch.Tensor:
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != torch.device(device):
+            self.buf = None
+            self.buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        return self.buf
+
+
+_ws = Workspace()
+
+
+def dda_forward(wpack: torch.Tensor, x: torch.Tensor, pads=(0, 0, 0, 0), mode: int = PC_DDA_FEATURES,
+                out: Optional[torch.Tensor] = None, workspace: Optional[Workspace] = None) -> torch.Tensor:
+    """x [B,C,H,W] fp32 (any strides with unit W stride) -> features [B,F,H,W] or builtup score [B,1,H,W]."""
+    _need_cuda(wpack, x)
+    L = _lib.lib()
+    if x.dim() != 4:
+        raise ValueError("Input tensor must have shape (batch_size, channels, height, width)")
+    if x.dtype != torch.float32 or x.stride(3) != 1:
+        x = x.float().contiguous()
+    B, Cc, H, W = x.shape
+    top, bot, left, right = pads
+    nf = 16 if Cc == 6 else 8
+    oc = nf if mode == PC_DDA_FEATURES else 1
+    if out is None:
+        out = torch.empty(B, oc, H, W, dtype=torch.float32, device=x.device)
+    ws = (workspace or _ws)
+    need = L.pc_dda_workspace_bytes(B, Cc, H + top + bot, W + left + right)
+    buf = ws.get(need, x.device)
+    _lib.check(L.pc_dda_forward(wpack.data_ptr(), x.data_ptr(), B, Cc, H, W, x.stride(0), x.stride(1), x.stride(2),
+                                top, bot, left, right, mode, out.data_ptr(), out.stride(0), out.stride(1),
+                                out.stride(2), buf.data_ptr(), buf.numel(), _stream()), "pc_dda_forward")
+    return out
+
+
+def head_dense_forward(hpack, feats, builtup, ids=None, census_idx=None, sums=None, want_scale=True):
+    """feats [B,Cin,H,W], builtup [B,1,H,W]|None -> (dens [B,H,W], scale [B,H,W]|None); sums (float64) updated in place."""
+    _need_cuda(hpack, feats, builtup, ids, census_idx, sums)
+    L = _lib.lib()
+    B, Cin, H, W = feats.shape
+    assert feats.stride(3) == 1 and feats.dtype == torch.float32
+    dens = torch.empty(B, H, W, dtype=torch.float32, device=feats.device)
+    scale = torch.empty_like(dens) if want_scale else None
+    if builtup is not None:
+        assert builtup.stride(-1) == 1 and builtup.dtype == torch.float32
+    if ids is not None:
+        assert ids.dtype == torch.int32 and ids.stride(-1) == 1 and ids.dim() == 3
+    if census_idx is not None:
+        assert census_idx.dtype == torch.int32
+    R = 0 if sums is None else sums.numel()
+    if sums is not None:
+        assert sums.dtype == torch.float64 and sums.is_contiguous()
+    _lib.check(L.pc_head_dense_forward(
+        hpack.data_ptr(), Cin, feats.data_ptr(), feats.stride(0), feats.stride(1), feats.stride(2),
+        _ptr(builtup), 0 if builtup is None else builtup.stride(0), 0 if builtup is None else builtup.stride(-2),
+        B, H, W, dens.data_ptr(), _ptr(scale), dens.stride(0), dens.stride(1),
+        _ptr(ids), 0 if ids is None else ids.stride(0), 0 if ids is None else ids.stride(1),
+        _ptr(census_idx), _ptr(sums), R, _stream()), "pc_head_dense_forward")
+    return dens, scale
+
+
+def sparse_mask_compact(builtup, admin, census_idx, grid_rows, grid_cols, use_builtup=True):
+    """-> (mask uint8 [B,H,W], idx int32 [B*H*W] (first n valid), n int32[1] device)."""
+    _need_cuda(builtup, admin, census_idx, grid_rows, grid_cols)
+    L = _lib.lib()
+    B, H, W = admin.shape
+    admin = admin.float().contiguous()
+    bu = None if builtup is None else builtup.float().contiguous()
+    dev = admin.device
+    mask = torch.empty(B, H, W, dtype=torch.uint8, device=dev)
+    idx = torch.empty(B * H * W, dtype=torch.int32, device=dev)
+    n = torch.zeros(1, dtype=torch.int32, device=dev)
+    need = L.pc_compact_workspace_bytes(B * H * W)
+    buf = _ws.get(need, dev)
+    _lib.check(L.pc_sparse_mask_compact(_ptr(bu), admin.data_ptr(), census_idx.data_ptr(), grid_rows.data_ptr(),
+                                        grid_cols.data_ptr(), 1 if use_builtup else 0, B, H, W, mask.data_ptr(),
+                                        idx.data_ptr(), n.data_ptr(), buf.data_ptr(), buf.numel(), _stream()),
+               "pc_sparse_mask_compact")
+    return mask, idx, n
+
+
+def head_sparse_forward(hpack, feats, builtup, idx, n_dev, n_max):
+    """-> (dens [B,H,W] scattered, scale_sel [n_max] (first n valid), popcount float64 [B])."""
+    _need_cuda(hpack, feats, builtup, idx, n_dev)
+    L = _lib.lib()
+    B, Cin, H, W = feats.shape
+    assert feats.is_contiguous() and feats.dtype == torch.float32
+    bu = None if builtup is None else builtup.float().contiguous()
+    dens = torch.zeros(B, H, W, dtype=torch.float32, device=feats.device)
+    scale_sel = torch.empty(max(int(n_max), 1), dtype=torch.float32, device=feats.device)
+    pop = torch.zeros(B, dtype=torch.float64, device=feats.device)
+    _lib.check(L.pc_head_sparse_forward(hpack.data_ptr(), Cin, feats.data_ptr(), feats.stride(0), feats.stride(1),
+                                        _ptr(bu), idx.data_ptr(), n_dev.data_ptr(), int(n_max), H * W, dens.data_ptr(),
+                                        scale_sel.data_ptr(), pop.data_ptr(), _stream()), "pc_head_sparse_forward")
+    return dens, scale_sel, pop
+
+
+def head_sparse_backward(hpack, feats, builtup, idx, n_dev, n_max, g_pop, g_coef, g_sel=None):
+    """-> gradient buffer in hpack layout (fp32)."""
+    _need_cuda(hpack, feats, builtup, idx, n_dev, g_pop, g_sel)
+    L = _lib.lib()
+    B, Cin, H, W = feats.shape
+    bu = None if builtup is None else builtup.float().contiguous()
+    grad = torch.empty_like(hpack)
+    need = L.pc_head_bwd_workspace_bytes(Cin)
+    buf = _ws.get(need, feats.device)
+    g_pop = g_pop.float().contiguous()
+    if g_sel is not None:
+        g_sel = g_sel.float().contiguous()
+    _lib.check(L.pc_head_sparse_backward(hpack.data_ptr(), Cin, feats.data_ptr(), feats.stride(0), feats.stride(1),
+                                         _ptr(bu), idx.data_ptr(), n_dev.data_ptr(), int(n_max), H * W,
+                                         g_pop.data_ptr(), float(g_coef), _ptr(g_sel), grad.data_ptr(),
+                                         buf.data_ptr(), buf.numel(), _stream()), "pc_head_sparse_backward")
+    return grad
+
+
+def region_sum(dens: torch.Tensor, ids: torch.Tensor, R: int, sums: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """sums[id] += dens (float64 [R]); ids int32, same shape as dens, both contiguous."""
+    _need_cuda(dens, ids)
+    assert dens.is_contiguous() and ids.is_contiguous() and ids.dtype == torch.int32 and dens.dtype == torch.float32
+    assert dens.numel() == ids.numel()
+    if sums is None:
+        sums = torch.zeros(R, dtype=torch.float64, device=dens.device)
+    _lib.check(_lib.lib().pc_region_sum(dens.data_ptr(), ids.data_ptr(), dens.numel(), R, sums.data_ptr(), _stream()),
+               "pc_region_sum")
+    return sums
+
+
+def region_sum_backward(g_sums: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
+    _need_cuda(g_sums, ids)
+    g = g_sums.float().contiguous()
+    out = torch.empty(ids.shape, dtype=torch.float32, device=ids.device)
+    _lib.check(_lib.lib().pc_region_sum_backward(g.data_ptr(), ids.data_ptr(), ids.numel(), g.numel(), out.data_ptr(),
+                                                 _stream()), "pc_region_sum_backward")
+    return out
+
+
+def region_scale_(dens: torch.Tensor, ids: torch.Tensor, factor: torch.Tensor) -> torch.Tensor:
+    _need_cuda(dens, ids, factor)
+    assert dens.is_contiguous() and ids.is_contiguous() and factor.dtype == torch.float32
+    _lib.check(_lib.lib().pc_region_scale(dens.data_ptr(), ids.data_ptr(), dens.numel(), factor.numel(),
+                                          factor.data_ptr(), _stream()), "pc_region_scale")
+    return dens
+
+
+def accumulate_tile(dens, scale, rows, cols, maps, y0, x0):
+    """maps = (map, map_sq, smap, smap_sq, count) full-raster tensors (any may be None except map)."""
+    m, msq, sm, ssq, cnt = maps
+    _lib.check(_lib.lib().pc_accumulate_tile(dens.data_ptr(), _ptr(scale), dens.stride(-2), rows[0], rows[1], cols[0],
+                                             cols[1], m.data_ptr(), _ptr(msq), _ptr(sm), _ptr(ssq), _ptr(cnt),
+                                             m.stride(0), y0, x0, _stream()), "pc_accumulate_tile")
+
+
+def finalize_map(maps):
+    m, msq, sm, ssq, cnt = maps
+    _lib.check(_lib.lib().pc_finalize_map(m.data_ptr(), _ptr(msq), _ptr(sm), _ptr(ssq), cnt.data_ptr(), m.numel(),
+                                          _stream()), "pc_finalize_map")

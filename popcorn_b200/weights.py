@@ -1,0 +1,91 @@
+"""Weight packing for the sm_100a kernels: BatchNorm(eval) folding, channel-order folding and layout.
+
+Layout contract: include/popcorn_b200.h ("Packed weights").  BN is always in eval mode on this path
+(model/popcorn.py:128, 288-289), so  W' = W * g / sqrt(var + eps),  b' = (b - mean) * g / sqrt(var + eps) + beta
+(SURVEY.md Appendix A); the fold is done in float64 and rounded once to fp32.
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+import torch
+
+BN_EPS = 1e-5
+
+# (prefix inside a stream, first slot) for the ten 3x3 convs and the two transposed convs, in pack order
+_LAYERS = [
+    ("conv", "inc.conv.conv", 0), ("conv", "inc.conv.conv", 3),
+    ("conv", "down_seq.down1.mpconv.1.conv", 0), ("conv", "down_seq.down1.mpconv.1.conv", 3),
+    ("conv", "down_seq.down2.mpconv.1.conv", 0), ("conv", "down_seq.down2.mpconv.1.conv", 3),
+    ("convt", "up_seq.up2.up", None),
+    ("conv", "up_seq.up2.conv.conv", 0), ("conv", "up_seq.up2.conv.conv", 3),
+    ("convt", "up_seq.up1.up", None),
+    ("conv", "up_seq.up1.conv.conv", 0), ("conv", "up_seq.up1.conv.conv", 3),
+]
+
+
+def _fold_conv(sd: Dict[str, torch.Tensor], pfx: str, slot: int) -> torch.Tensor:
+    w = sd[f"{pfx}.{slot}.weight"].detach().double().cpu()          # [Cout, Cin, 3, 3]
+    b = sd[f"{pfx}.{slot}.bias"].detach().double().cpu()
+    g = sd[f"{pfx}.{slot + 1}.weight"].detach().double().cpu()
+    beta = sd[f"{pfx}.{slot + 1}.bias"].detach().double().cpu()
+    mean = sd[f"{pfx}.{slot + 1}.running_mean"].detach().double().cpu()
+    var = sd[f"{pfx}.{slot + 1}.running_var"].detach().double().cpu()
+    s = g / torch.sqrt(var + BN_EPS)
+    wf = (w * s.view(-1, 1, 1, 1)).permute(1, 2, 3, 0).reshape(-1)   # [Cin][ky][kx][Cout]
+    bf = (b - mean) * s + beta
+    return torch.cat([wf, bf])
+
+
+def _pack_convt(sd, pfx: str) -> torch.Tensor:
+    w = sd[f"{pfx}.weight"].detach().double().cpu()                  # [Cin, Cout, 2, 2]
+    b = sd[f"{pfx}.bias"].detach().double().cpu()
+    return torch.cat([w.permute(0, 2, 3, 1).reshape(-1), b])          # [Cin][dy][dx][Cout]
+
+
+def _pad4(t: torch.Tensor) -> torch.Tensor:
+    r = (-t.numel()) % 4
+    return torch.cat([t, torch.zeros(r, dtype=t.dtype)]) if r else t
+
+
+def pack_dda(sd: Dict[str, torch.Tensor], copy: str) -> torch.Tensor:
+    """One DualStreamUNet copy ('unetmodel' | 'building_extractor') -> flat fp32 CPU tensor."""
+    parts = []
+    for stream in ("sar_stream", "optical_stream"):
+        for kind, pfx, slot in _LAYERS:
+            full = f"{copy}.{stream}.{pfx}"
+            parts.append(_fold_conv(sd, full, slot) if kind == "conv" else _pack_convt(sd, full))
+    for oc in ("fusion_out_conv", "sar_out_conv", "optical_out_conv"):
+        parts.append(_pad4(torch.cat([sd[f"{copy}.{oc}.conv.weight"].detach().double().cpu().reshape(-1),
+                                      sd[f"{copy}.{oc}.conv.bias"].detach().double().cpu().reshape(-1)])))
+    return torch.cat(parts).float().contiguous()
+
+
+def pack_head(sd: Dict[str, torch.Tensor]) -> torch.Tensor:
+    """head.{0,2,4,6} -> W1t[k][n], b1, W2t, b2, W3t, b3, w4 (row 0 of head.6), b4 (+3 pad).  Differentiable:
+    built with torch ops on the live parameters so it can be re-packed each step."""
+    w = lambda i: sd[f"head.{i}.weight"].flatten(1)
+    b = lambda i: sd[f"head.{i}.bias"]
+    parts = []
+    for i in (0, 2, 4):
+        parts += [w(i).t().reshape(-1), b(i)]
+    parts += [w(6)[0], b(6)[0:1], torch.zeros(3, dtype=w(6).dtype, device=w(6).device)]
+    return torch.cat([p.float() for p in parts]).contiguous()
+
+
+def unpack_head_grad(gpack: torch.Tensor, head_in: int) -> Dict[str, torch.Tensor]:
+    """Inverse of pack_head for a gradient buffer in pack layout -> per-parameter gradients."""
+    out, o = {}, 0
+    dims = [(head_in, 64), (64, 64), (64, 64)]
+    for i, (k, n) in zip((0, 2, 4), dims):
+        out[f"head.{i}.weight"] = gpack[o:o + k * n].view(k, n).t().reshape(n, k, 1, 1).contiguous()
+        o += k * n
+        out[f"head.{i}.bias"] = gpack[o:o + n].clone()
+        o += n
+    w6 = torch.zeros(2, 64, 1, 1, dtype=gpack.dtype, device=gpack.device)
+    w6[0, :, 0, 0] = gpack[o:o + 64]
+    o += 64
+    b6 = torch.zeros(2, dtype=gpack.dtype, device=gpack.device)
+    b6[0] = gpack[o]
+    out["head.6.weight"], out["head.6.bias"] = w6, b6
+    return out

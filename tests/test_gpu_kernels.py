@@ -1,0 +1,170 @@
+"""GPU: per-kernel unit tests of the sm_100a kernels against plain torch fp32 ops / the oracle."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from popcorn_b200 import _lib, ops
+from oracle import popcorn_oracle as po
+
+pytestmark = pytest.mark.gpu
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _pack_conv(w, b):
+    return torch.cat([w.permute(1, 2, 3, 0).reshape(-1), b]).contiguous()
+
+
+@pytest.mark.parametrize("cin,cout", [(2, 8), (4, 8), (8, 8), (8, 16), (16, 16)])
+@pytest.mark.parametrize("H,W", [(64, 64), (37, 53), (32, 100)])
+def test_conv3x3_bias_relu(cin, cout, H, W):
+    g = torch.Generator().manual_seed(cin * 100 + cout + H)
+    x = torch.randn(cin, H, W, generator=g).cuda()
+    w = (torch.randn(cout, cin, 3, 3, generator=g) * 0.3).cuda()
+    b = torch.randn(cout, generator=g).cuda()
+    out = torch.full((cout, H, W), float("nan"), device="cuda")
+    _lib.check(_lib.lib().pc_test_conv3x3(x.data_ptr(), cin, H, W, 0, 0, 0, None, 0, 0, 0, 0, 0,
+                                          _pack_conv(w, b).data_ptr(), cout, H, W, out.data_ptr(), None, _st()))
+    ref = F.relu(F.conv2d(x[None].cpu(), w.cpu(), b.cpu(), padding=1))[0]
+    assert torch.allclose(out.cpu(), ref, rtol=1e-4, atol=1e-4), float((out.cpu() - ref).abs().max())
+
+
+@pytest.mark.parametrize("c", [8, 16])
+@pytest.mark.parametrize("H,W", [(64, 64), (37, 52), (50, 36)])
+def test_conv3x3_fused_maxpool(c, H, W):
+    g = torch.Generator().manual_seed(c + H)
+    x = torch.randn(c, H, W, generator=g).cuda()
+    w = (torch.randn(c, c, 3, 3, generator=g) * 0.3).cuda()
+    b = torch.randn(c, generator=g).cuda()
+    out = torch.empty(c, H, W, device="cuda")
+    pool = torch.full((c, H // 2, W // 2), float("nan"), device="cuda")
+    _lib.check(_lib.lib().pc_test_conv3x3(x.data_ptr(), c, H, W, 0, 0, 0, None, 0, 0, 0, 0, 0,
+                                          _pack_conv(w, b).data_ptr(), c, H, W, out.data_ptr(), pool.data_ptr(), _st()))
+    ref = F.relu(F.conv2d(x[None].cpu(), w.cpu(), b.cpu(), padding=1))
+    assert torch.allclose(out.cpu(), ref[0], rtol=1e-4, atol=1e-4)
+    assert torch.allclose(pool.cpu(), F.max_pool2d(ref, 2)[0], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("ca,cb,cout", [(16, 16, 8), (8, 8, 8)])
+@pytest.mark.parametrize("H,W", [(64, 64), (37, 53)])
+def test_conv3x3_concat_with_offset_zero_pad(ca, cb, cout, H, W):
+    """Up block: cat[skip, F.pad(upsampled)] -> conv (networks.py:309-319) without materialising either."""
+    g = torch.Generator().manual_seed(ca + H)
+    a = torch.randn(ca, H, W, generator=g).cuda()
+    bH, bW = 2 * (H // 2), 2 * (W // 2)
+    bsrc = torch.randn(cb, bH, bW, generator=g).cuda()
+    w = (torch.randn(cout, ca + cb, 3, 3, generator=g) * 0.2).cuda()
+    bias = torch.randn(cout, generator=g).cuda()
+    dy, dx = H - bH, W - bW
+    out = torch.empty(cout, H, W, device="cuda")
+    _lib.check(_lib.lib().pc_test_conv3x3(a.data_ptr(), ca, H, W, 0, 0, 0, bsrc.data_ptr(), cb, bH, bW, dy // 2, dx // 2,
+                                          _pack_conv(w, bias).data_ptr(), cout, H, W, out.data_ptr(), None, _st()))
+    bp = F.pad(bsrc.cpu(), (dx // 2, dx - dx // 2, dy // 2, dy - dy // 2))
+    ref = F.relu(F.conv2d(torch.cat([a.cpu(), bp])[None], w.cpu(), bias.cpu(), padding=1))[0]
+    assert torch.allclose(out.cpu(), ref, rtol=1e-4, atol=1e-4), float((out.cpu() - ref).abs().max())
+
+
+@pytest.mark.parametrize("pad", [(14, 14), (5, 0), (0, 9)])
+def test_conv3x3_virtual_reflect_padding(pad):
+    """Reflect padding folded into the loader (popcorn.py:244, 292): conv over the virtually padded image."""
+    g = torch.Generator().manual_seed(3)
+    H, W, cin, cout = 45, 61, 4, 8
+    py, px = pad
+    x = torch.randn(cin, H, W, generator=g).cuda()
+    w = (torch.randn(cout, cin, 3, 3, generator=g) * 0.3).cuda()
+    b = torch.randn(cout, generator=g).cuda()
+    Hv, Wv = H + 2 * py, W + 2 * px
+    out = torch.empty(cout, Hv, Wv, device="cuda")
+    _lib.check(_lib.lib().pc_test_conv3x3(x.data_ptr(), cin, H, W, py, px, 1, None, 0, 0, 0, 0, 0,
+                                          _pack_conv(w, b).data_ptr(), cout, Hv, Wv, out.data_ptr(), None, _st()))
+    xp = F.pad(x[None].cpu(), (px, px, py, py), mode="reflect")
+    ref = F.relu(F.conv2d(xp, w.cpu(), b.cpu(), padding=1))[0]
+    assert torch.allclose(out.cpu(), ref, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("c", [8, 16])
+def test_conv_transpose_2x2(c):
+    g = torch.Generator().manual_seed(c)
+    Hl, Wl = 19, 45
+    x = torch.randn(c, Hl, Wl, generator=g).cuda()
+    w = (torch.randn(c, c, 2, 2, generator=g) * 0.3).cuda()
+    b = torch.randn(c, generator=g).cuda()
+    pack = torch.cat([w.permute(0, 2, 3, 1).reshape(-1), b]).contiguous()
+    out = torch.empty(c, 2 * Hl, 2 * Wl, device="cuda")
+    _lib.check(_lib.lib().pc_test_convt2x2(x.data_ptr(), c, Hl, Wl, pack.data_ptr(), out.data_ptr(), _st()))
+    ref = F.conv_transpose2d(x[None].cpu(), w.cpu(), b.cpu(), stride=2)[0]
+    assert torch.allclose(out.cpu(), ref, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("npix,R", [(1000, 7), (128 * 1024 + 37, 400), (3_000_001, 72976), (0, 3)])
+def test_region_sum_and_backward(npix, R):
+    g = torch.Generator().manual_seed(npix % 1000 + R)
+    dens = torch.rand(npix, generator=g)
+    # spatially coherent runs plus a noisy stretch, background 0 and out-of-range ids (-1, R) that must be ignored
+    run = torch.randint(1, 5000, (max(1, npix // 700 + 2),), generator=g)
+    ids = torch.repeat_interleave(torch.randint(-1, R + 1, (len(run),), generator=g), run)[:npix].to(torch.int32)
+    if npix > 5000:
+        ids[1000:3000] = torch.randint(0, R, (2000,), generator=g).to(torch.int32)
+    sums = ops.region_sum(dens.cuda(), ids.cuda(), R).cpu()
+    valid = (ids >= 0) & (ids < R)
+    ref = torch.zeros(R, dtype=torch.float64).index_add_(0, ids[valid].long(), dens[valid].double())
+    assert torch.allclose(sums, ref, rtol=1e-5, atol=1e-6)
+    if npix:
+        gs = torch.randn(R, generator=g)
+        gd = ops.region_sum_backward(gs.cuda(), ids.cuda()).cpu()
+        refg = torch.where(valid, gs[ids.clamp(0, R - 1).long()], torch.zeros(()))
+        assert torch.equal(gd, refg)
+        fac = torch.rand(R, generator=g) + 0.5
+        d2 = ops.region_scale_(dens.clone().cuda(), ids.cuda(), fac.cuda()).cpu()
+        assert torch.equal(d2, torch.where(valid, dens * fac[ids.clamp(0, R - 1).long()], dens))
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 72, 88), (1, 300, 517), (3, 33, 41)])
+@pytest.mark.parametrize("empty", [False, True])
+def test_sparsity_mask_compaction_is_bit_exact(B, H, W, empty):
+    g = torch.Generator().manual_seed(B * H + W)
+    builtup = torch.rand(B, 1, H, W, generator=g)
+    builtup[:, :, ::3] = 0.0                                    # exercise the (builtup > 0) term
+    admin = torch.randint(0, 4, (B, H, W), generator=g).float()
+    admin[:, :, -5:] = -1.0
+    cidx = torch.tensor([2, 3, 1][:B])
+    if empty:
+        admin[admin == cidx.view(-1, 1, 1).float()] = 0.0       # no pixel of the region -> fallback branch (:374-375)
+    torch.manual_seed(11)
+    grid = po.sparsity_grid(H, W)
+    ref = po.sparsity_mask(builtup, admin, cidx, True, grid)
+    rows = torch.zeros(H, dtype=torch.uint8); rows[grid[0]] = 1
+    cols = torch.zeros(W, dtype=torch.uint8); cols[grid[1]] = 1
+    mask, idx, n = ops.sparse_mask_compact(builtup[:, 0].cuda(), admin.cuda(), cidx.int().cuda(), rows.cuda(), cols.cuda())
+    n = int(n.item())
+    assert torch.equal(mask.bool().cpu(), ref)                                   # index set bit-exact
+    assert torch.equal(idx[:n].long().cpu(), ref.reshape(-1).nonzero()[:, 0])    # row-major (b,h,w) order
+
+
+def test_accumulate_and_finalize_match_run_eval_arithmetic():
+    H, W, ps, ov = 200, 236, 96, 16
+    g = torch.Generator().manual_seed(1)
+    maps = [torch.zeros(H, W, device="cuda") for _ in range(4)] + [torch.zeros(H, W, dtype=torch.int16, device="cuda")]
+    ref = [torch.zeros(H, W) for _ in range(4)] + [torch.zeros(H, W, dtype=torch.int16)]
+    m = po.centre_mask(ps, ps, ov)
+    for xl, yl in po.get_patch_indices(H, W, ps, ov).tolist():
+        d = torch.rand(ps, ps, generator=g)
+        s = torch.rand(ps, ps, generator=g)
+        ops.accumulate_tile(d.cuda(), s.cuda(), (ov, ps - ov), (ov, ps - ov), maps, xl, yl)
+        for t, v in zip(ref[:4], (d, d * d, s, s * s)):
+            t[xl:xl + ps, yl:yl + ps][m] += v[m]
+        ref[4][xl:xl + ps, yl:yl + ps][m] += 1
+    ops.finalize_map(maps)
+    div = ref[4] > 1
+    cf = ref[4][div].float()
+    ref[0][div] = ref[0][div] / cf
+    ref[1][div] = torch.sqrt((ref[1][div] - ref[0][div] ** 2 * cf) / (cf - 1))
+    ref[2][div] = ref[2][div] / cf
+    ref[3][div] = torch.sqrt((ref[3][div] - ref[2][div] ** 2 * cf) / (cf - 1))
+    assert torch.equal(maps[4].cpu(), ref[4]) and int(div.sum()) > 0
+    for a, b in zip(maps[:4], ref[:4]):
+        assert torch.allclose(a.cpu(), b, rtol=1e-5, atol=1e-5, equal_nan=True)

@@ -1,0 +1,138 @@
+"""CPU: host-side logic and the C-ABI surface (no compute calls: there is no GPU here)."""
+import ctypes
+import os
+import re
+import warnings
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import popcorn_b200 as pb
+from popcorn_b200 import _lib, weights
+from popcorn_b200.model import dda
+from oracle import popcorn_oracle as po
+from util import golden_state_dict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def sd():
+    return golden_state_dict()
+
+
+def _model(**kw):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return pb.POPCORN(device="cpu", **kw)
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "popcorn_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(pc_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/popcorn_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert _lib.lib().pc_version() >= 100
+
+
+def test_state_dict_grammar_matches_reference(sd):
+    m = _model(input_channels=6, occupancymodel=True, pretrained=False, biasinit=0.9407, sentinelbuildings=True)
+    mine = m.state_dict()
+    assert list(mine.keys()) == list(sd.keys())            # 324 keys, reference order
+    for k in sd:
+        assert tuple(mine[k].shape) == tuple(sd[k].shape) and mine[k].dtype == sd[k].dtype, k
+    m.load_state_dict(sd, strict=True)
+    assert m.num_params == 39799                            # notebook: SAR 15041 + OPT 15185 + out convs 35 + head 9538
+    assert sum(p.numel() for p in m.unetmodel.sar_stream.parameters()) == 15041
+    assert sum(p.numel() for p in m.unetmodel.optical_stream.parameters()) == 15185
+    assert sum(p.numel() for p in m.head.parameters()) == 9538
+    assert torch.equal(m.head[6].bias.detach(), sd["head.6.bias"])
+    # optimizer grouping by name (run_train.py:82-85) must find these
+    names = [n for n, _ in m.named_parameters()]
+    assert "head.6.weight" in names and "head.6.bias" in names and any(n.startswith("unetmodel.") for n in names)
+
+
+def test_checkpoint_roundtrip(tmp_path, sd):
+    m = _model(input_channels=6, occupancymodel=True)
+    m.load_state_dict(sd)
+    path = tmp_path / "last_model.pth"
+    torch.save({"model": m.state_dict(), "epoch": 3, "iter": 7}, path)       # run_train.py:450-456
+    m2 = _model(input_channels=6, occupancymodel=True)
+    m2.load_state_dict(torch.load(path)["model"])                            # run_eval.py:252-253
+    for k, v in m2.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+    # DDA .pt layout {'step','network','optimizer'} (networks.py:22-29)
+    net = dda.DualStreamUNetParams()
+    dpath = tmp_path / "dda.pt"
+    torch.save({"step": 11, "network": net.state_dict(), "optimizer": {}}, dpath)
+    net2, _, step = dda.load_checkpoint(device="cpu", path=str(dpath), strict_file=True)
+    assert step == 11 and all(torch.equal(a, b) for a, b in zip(net.state_dict().values(), net2.state_dict().values()))
+
+
+def test_get_model_surface():
+    from popcorn_b200.model.get_model import Args, calculate_input_channels, get_model_kwargs, model_dict
+    a = Args(Sentinel1=True, NIR=True, Sentinel2=True, feature_extractor="DDA", occupancymodel=True, pretrained=False,
+             biasinit=0.9407, sentinelbuildings=True)
+    assert calculate_input_channels(a) == 6
+    kw = get_model_kwargs(a, "POPCORN")
+    assert kw == dict(input_channels=6, feature_extractor="DDA", occupancymodel=True, pretrained=False, biasinit=0.9407,
+                      sentinelbuildings=True)
+    assert model_dict["POPCORN"] is pb.POPCORN
+    with pytest.raises(ValueError):
+        get_model_kwargs(a, "nope")
+    assert calculate_input_channels(a._replace(Sentinel2=False, NIR=False)) == 2
+    assert calculate_input_channels(a._replace(Sentinel1=False)) == 4
+
+
+def test_pack_sizes_agree_with_library(sd):
+    L = _lib.lib()
+    p = weights.pack_dda(sd, "unetmodel")
+    assert p.numel() == L.pc_dda_pack_floats() and p.dtype == torch.float32
+    assert weights.pack_head(sd).numel() == L.pc_head_pack_floats(16)
+    assert L.pc_head_pack_floats(8) == 8 * 64 + 64 + 2 * (64 * 64 + 64) + 64 + 4
+    assert L.pc_dda_pack_offset(0, 0) == 0 and L.pc_dda_pack_offset(0, 1) == 2 * 9 * 8 + 8
+    assert L.pc_dda_pack_offset(2, 12) + 12 == L.pc_dda_pack_floats()
+
+
+def test_bn_fold_is_exact_to_fp32_rounding(sd):
+    """Folded conv == conv -> BN(eval), layer inc.conv.0 of the optical stream."""
+    L = _lib.lib()
+    pack = weights.pack_dda(sd, "building_extractor")
+    off = L.pc_dda_pack_offset(1, 0)
+    wf = pack[off:off + 4 * 9 * 8].view(4, 3, 3, 8).permute(3, 0, 1, 2).contiguous()
+    bf = pack[off + 4 * 9 * 8: off + 4 * 9 * 8 + 8]
+    x = torch.randn(1, 4, 20, 24)
+    ref = po._conv_bn_relu(sd, "building_extractor.optical_stream.inc.conv.conv", 0, x)
+    got = F.relu(F.conv2d(x, wf, bf, padding=1))
+    assert torch.allclose(got, ref, rtol=1e-5, atol=1e-5)
+
+
+def test_head_pack_and_grad_unpack_roundtrip(sd):
+    hp = weights.pack_head(sd)
+    g = weights.unpack_head_grad(hp, 16)
+    for i in (0, 2, 4):
+        assert torch.equal(g[f"head.{i}.weight"], sd[f"head.{i}.weight"])
+        assert torch.equal(g[f"head.{i}.bias"], sd[f"head.{i}.bias"])
+    assert torch.equal(g["head.6.weight"][0], sd["head.6.weight"][0]) and float(g["head.6.weight"][1].abs().sum()) == 0
+    assert float(g["head.6.bias"][0]) == float(sd["head.6.bias"][0])
+
+
+def test_feature_padding_matches_reference_rule():
+    m = _model(input_channels=6, occupancymodel=True)
+    for H, W in ((2048, 2048), (75, 101), (1577, 1635), (64, 96), (33, 32)):
+        assert m.feature_padding(H, W, False) == po.feature_padding(H, W, False)
+    assert m.feature_padding(50, 50, True) == (14, 14, 14, 14)
+
+
+def test_cpu_tensors_are_rejected_loudly(sd):
+    m = _model(input_channels=6, occupancymodel=True)
+    m.load_state_dict(sd)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m({"input": torch.zeros(1, 6, 32, 32)}, padding=False)
+    with pytest.raises(ValueError):
+        m({"input": torch.zeros(6, 32, 32)}, padding=False)

@@ -1,0 +1,426 @@
+#!/usr/bin/env python
+"""bench.py — POPCORN country inference throughput on B200 (contract: see the task statement / DESIGN.md §measurement).
+
+    python bench.py --gpus 1 --steps 5 --warmup 3                       # this repo's CUDA path
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...                                # the reference algorithm on host cores
+
+One step = one full pass of the hot path over a synthetic country raster: tiled DDA builtup + feature passes,
+occupancy head, centre-masked accumulation, finalisation, census region sums, all-reduce of the R sums.
+N=1 : Rwanda-shaped 15104 x 17216 (BASELINE.json configs[1]).   N>1 : Uganda-shaped columns (47952) with
+50048*N/8 rows, i.e. configs[3] at N=8 and the same per-GPU slab at N=2,4 (weak scaling, rows sharded).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+import warnings
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "10m_pixels_per_sec_country_inference"
+UNIT = "pixels/s"
+R_REGIONS = 400
+FLOP_PER_PX_HEAD = 18688          # 9 344 MAC per pixel, dense head
+BYTES_PER_PX_HEAD = 64 + 4 + 8    # 16 feature planes + builtup in, dens + scale out
+
+
+def workload(n_gpus: int):
+    if n_gpus <= 1:
+        return 15104, 17216, "rwanda_shaped_15104x17216_tiled_inference_dense_head_region_sums_R400"
+    H = 50048 * n_gpus // 8
+    return H, 47952, f"uganda_shaped_{H}x47952_rows_sharded_over_{n_gpus}_gpus_R400"
+
+
+# ---------------------------------------------------------------------------------------------------
+# synthetic data, generated on the device slab by slab
+# ---------------------------------------------------------------------------------------------------
+def synth_raster_slab(rows: int, W: int, row0: int, device, seed: int = 1610) -> torch.Tensor:
+    """[6, rows, W] normalised fp32, channel order [R,G,B,NIR,VV,VH]; low-frequency structure + noise."""
+    g = torch.Generator(device=device).manual_seed(seed + row0)
+    out = torch.empty(6, rows, W, dtype=torch.float32, device=device)
+    for c in range(6):
+        coarse = torch.randn(1, 1, rows // 64 + 2, W // 64 + 2, generator=g, device=device)
+        low = torch.nn.functional.interpolate(coarse, size=(rows, W), mode="bilinear", align_corners=True)[0, 0]
+        out[c] = 0.6 * low + 0.8 * torch.randn(rows, W, generator=g, device=device)
+        del low
+    return out
+
+
+def synth_ids_slab(H: int, W: int, R: int, lo: int, hi: int, device, seed: int = 7) -> torch.Tensor:
+    """int32 [hi-lo, W]: 0 = background frame, 1..R Voronoi cells of R seeded centres over the whole raster."""
+    g = torch.Generator().manual_seed(seed)
+    cy = (torch.rand(R, generator=g) * H).to(device)
+    cx = (torch.rand(R, generator=g) * W).to(device)
+    step = 16
+    ys = torch.arange(lo // step * step, hi + step, step, device=device, dtype=torch.float32)
+    xs = torch.arange(0, W + step, step, device=device, dtype=torch.float32)
+    best = torch.full((len(ys), len(xs)), float("inf"), device=device)
+    ids = torch.zeros(len(ys), len(xs), dtype=torch.int32, device=device)
+    for r in range(R):
+        d = (ys[:, None] - cy[r]) ** 2 + (xs[None, :] - cx[r]) ** 2
+        upd = d < best
+        best = torch.where(upd, d, best)
+        ids[upd] = r + 1
+    full = ids.repeat_interleave(step, 0).repeat_interleave(step, 1)
+    off = lo - lo // step * step
+    full = full[off: off + (hi - lo), :W].contiguous()
+    m = 128
+    if lo < m:
+        full[: m - lo] = 0
+    if hi > H - m:
+        full[max(0, H - m - lo):] = 0
+    full[:, :m] = 0
+    full[:, W - m:] = 0
+    return full
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        res = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return res
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [t.strip() for t in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            sm.sort()
+            res = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return res
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU baseline = the oracle port of the reference algorithm on the host cores (bounded sample)
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_tiles(n_tiles: int, sd=None):
+    """Runs n_tiles reference-sized (2048^2) tiles through the oracle + census sums; returns (seconds, unique px)."""
+    from oracle import popcorn_oracle as po
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = sd or po.random_state_dict(seed=1600)
+    ids = po.synthetic_regions(2048, 2048, 40)
+    xs = [po.synthetic_input(2048, 2048, seed=1610 + i) for i in range(n_tiles)]   # untimed: data generation
+    t0 = time.perf_counter()
+    for x in xs:
+        with torch.no_grad():
+            out = po.forward(sd, {"input": x}, padding=False)
+        centre = out["popdensemap"][0][128:-128, 128:-128]
+        po.region_sums(centre, ids[128:-128, 128:-128], 41)
+    dt = time.perf_counter() - t0
+    return dt, n_tiles * 1792 * 1792
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    H, W, name = workload(args.gpus)
+    from oracle import popcorn_oracle as po
+    sd = po.random_state_dict(seed=1600)
+    torch.set_num_threads(os.cpu_count() or 1)
+    # warm-up is bounded to one tile: every further warm-up tile costs seconds of host time and changes nothing
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_tiles(1, sd)
+    times = []
+    px = 0
+    for _ in range(args.steps):
+        dt, p = cpu_reference_tiles(1, sd)
+        times.append(dt)
+        px += p
+    total = sum(times)
+    value = px / total
+    cores = torch.get_num_threads()
+    sample = "per step: one 2048x2048 reference tile (oracle port of POPCORN.forward, fp32) + census sums; unique px = centre 1792^2"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": name, "sampled": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+def train_step_ms(model, device, iters: int = 5):
+    """BASELINE config 3: census-supervised step B=2, 896x960, sparse head, log-L1 loss, clip 0.01, Adam (run_train.py)."""
+    from oracle import popcorn_oracle as po
+    B, H, W = 2, 896, 960
+    x = synth_raster_slab(B * H, W, 12345, device).view(6, B, H, W).permute(1, 0, 2, 3).contiguous()
+    yy, xx = torch.meshgrid(torch.arange(H, device=device), torch.arange(W, device=device), indexing="ij")
+    admin = torch.zeros(B, H, W, device=device)
+    admin[0][((yy - 448) / 400.0) ** 2 + ((xx - 480) / 420.0) ** 2 < 1] = 17.0
+    admin[1][((yy - 430) / 380.0) ** 2 + ((xx - 500) / 400.0) ** 2 < 1] = 5.0
+    cidx = torch.tensor([17, 5], device=device)
+    y = torch.tensor([3500.0, 12000.0], device=device)
+    model.train()
+    params = [p for n, p in model.named_parameters() if n.startswith("head.")]
+    opt = torch.optim.Adam(params, lr=1e-4)
+    times = []
+    n_sel = 0
+    for it in range(iters + 2):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        inp = {"input": x, "admin_mask": admin, "census_idx": cidx}
+        out = model(inp, train=True, padding=False, encoder_no_grad=True, unet_no_grad=True, sparse=True)
+        loss = po.train_loss(out, y)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(params, 0.01)
+        opt.step()
+        opt.zero_grad()
+        torch.cuda.synchronize()
+        if it >= 2:
+            times.append(1e3 * (time.perf_counter() - t0))
+        n_sel = int(out["scale"].numel())
+    model.eval()
+    times.sort()
+    return {"ms": times[len(times) // 2], "config": f"B=2 x 896x960, sparse head on {n_sel} px, unet_no_grad, log-L1 + scale reg, clip 0.01, Adam",
+            "includes": "2 frozen DDA passes + mask compaction + sparse head fwd + loss + head bwd + clip + Adam"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="popcorn_b200", choices=["popcorn_b200", "reference"])
+    ap.add_argument("--rows-per-strip", type=int, default=2)
+    ap.add_argument("--no-merge", action="store_true", help="run the reference's 2048^2 tile grid tile by tile")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-train", action="store_true")
+    ap.add_argument("--height", type=int, default=0, help="override raster rows (debug)")
+    ap.add_argument("--width", type=int, default=0, help="override raster cols (debug)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: popcorn_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import popcorn_b200 as pb
+    from popcorn_b200 import country as ct
+    from popcorn_b200 import ops
+    from oracle import popcorn_oracle as po   # only for the synthetic state_dict + the cpu_baseline leg
+
+    H, W, name = workload(world)
+    if args.height and args.width:
+        H, W, name = args.height, args.width, f"debug_{args.height}x{args.width}"
+    sd = po.random_state_dict(seed=1600)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = pb.POPCORN(6, occupancymodel=True, pretrained=False, biasinit=0.9407, sentinelbuildings=True, device=dev)
+    model.load_state_dict(sd)
+    model.eval()
+
+    eng = ct.CountryEngine([model], H, W, merge=not args.no_merge, rows_per_strip=args.rows_per_strip, rank=rank, world=world)
+    i0, i1 = eng.in_rows
+    lo, hi = eng.out_rows
+    raster = synth_raster_slab(i1 - i0, W, i0, dev)
+    ids = synth_ids_slab(H, W, R_REGIONS, lo, hi, dev)
+    R = R_REGIONS + 1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        with torch.no_grad():
+            return eng.run(raster, ids, R, row_offset=i0)
+
+    # phase events inside the timed region (cheap): per-call durations of the dominant kernel (the head launch)
+    prof = {"head": [], "head_px": 0}
+    orig_head = ops.head_dense_forward
+
+    def timed_head(*a, **k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = orig_head(*a, **k)
+        e1.record()
+        f = a[1]
+        prof["head"].append((e0, e1, f.shape[0] * f.shape[2] * f.shape[3]))
+        return r
+
+    for _ in range(args.warmup):
+        out = step_device()
+    barrier()
+    ops.launch_count(reset=True)
+    ops.head_dense_forward = timed_head
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        out = step_device()
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ops.head_dense_forward = orig_head
+    launches = ops.launch_count(reset=True)
+    ms_total = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = H * W / (ms_step * 1e-3)
+    sums_check = float(out["sums"].sum().item())
+    map_total = float(out["map"].double().sum().item())
+
+    head_ms = sum(a.elapsed_time(b) for a, b, _ in prof["head"])
+    head_px = sum(n for _, _, n in prof["head"])
+    head_calls = len(prof["head"])
+    hbm_peak, bf16_peak, bf16_sust, peak_src = measured_peaks()
+    head_tflops = FLOP_PER_PX_HEAD * head_px / (head_ms * 1e-3) / 1e12 if head_ms else 0.0
+    roofline = {"kernel": "head_forward_kernel<16,dense>", "bound": "tensor", "achieved": head_tflops,
+                "peak": bf16_sust, "unit": "TFLOP/s", "frac": head_tflops / bf16_sust, "traffic": None,
+                "peak_source": f"{peak_src} bf16 cuBLAS sustained (MEASURED_PEAKS.json); the kernel computes in fp32 "
+                               "(3xTF32-equivalent work, see DESIGN.md) so its practical ceiling is far below this",
+                "launches": head_calls, "avg_launch_ms": head_ms / max(head_calls, 1),
+                "share_of_step": head_ms / (ms_total if ms_total else 1.0),
+                "algorithmic": {"flop_per_px": FLOP_PER_PX_HEAD, "bytes_per_px": BYTES_PER_PX_HEAD,
+                                "hbm_gbs": BYTES_PER_PX_HEAD * head_px / (head_ms * 1e-3) / 1e9 if head_ms else 0.0}}
+
+    # ---- end-to-end: pinned host raster in, pinned host map + sums out, copies inside the timed region ----
+    e2e = None
+    if not args.skip_e2e:
+        host_raster = torch.empty(raster.shape, dtype=torch.float32, pin_memory=True)
+        host_raster.copy_(raster)
+        host_map = torch.empty(hi - lo, W, dtype=torch.float32, pin_memory=True)
+        del raster
+        torch.cuda.empty_cache()
+
+        def step_e2e():
+            with torch.no_grad():
+                o = eng.run(host_raster, ids, R, row_offset=i0)
+                ops.copy_d2h(host_map, o["map"])
+                s = o["sums"].cpu()
+            torch.cuda.synchronize()
+            return s
+
+        step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        k_e2e = max(2, min(args.steps, 3))
+        for _ in range(k_e2e):
+            s_host = step_e2e()
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        h2d = torch.tensor([float(getattr(eng, "h2d_bytes", 0))], dtype=torch.float64, device=dev)
+        d2h = torch.tensor([float(host_map.numel() * 4 + R * 8)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(h2d); dist.all_reduce(d2h)
+        e2e = {"value": H * W / (float(tt.item()) / k_e2e), "unit": UNIT, "h2d_bytes_per_step": int(h2d.item()),
+               "d2h_bytes_per_step": int(d2h.item()), "steps": k_e2e,
+               "api": "popcorn_b200.country.CountryEngine.run(pinned host raster) + copy_d2h(map) + sums.cpu()"}
+
+    train = None
+    cpu_base = None
+    fp32 = None
+    if rank == 0:
+        if not args.skip_train:
+            try:
+                train = train_step_ms(model, dev)
+            except Exception as ex:   # the headline metric must still be printed
+                train = {"error": repr(ex)[:200]}
+        # measured FP32 SIMT ceiling (packed FFMA2), the practical bound of the stencil + SIMT head kernels
+        from popcorn_b200 import _lib
+        o = torch.zeros(4, device=dev)
+        st = torch.cuda.current_stream().cuda_stream
+        iters = 4096
+        for _ in range(2):
+            nthr = _lib.lib().pc_test_fma_peak(1, iters, 8, o.data_ptr(), st)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        nthr = _lib.lib().pc_test_fma_peak(1, iters, 8, o.data_ptr(), st)
+        b.record()
+        torch.cuda.synchronize()
+        fp32_peak = 2 * 32 * iters * nthr / (a.elapsed_time(b) * 1e-3) / 1e12
+        fp32 = {"peak_tflops_measured_ffma2": fp32_peak, "head_frac": head_tflops / fp32_peak if fp32_peak else None}
+        if world == 1 and not args.skip_cpu_baseline:
+            dt, px = cpu_reference_tiles(2)
+            cpu_base = {"value": px / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                        "sample": "2 reference tiles of 2048x2048 (oracle port of POPCORN.forward, fp32, all host threads) "
+                                  "+ census sums; unique px = centre 1792^2 per tile"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": name, "H": H, "W": W, "regions": R_REGIONS, "patch": 2048, "overlap": 128,
+                           "windows": "merged_row_strips" if not args.no_merge else "reference_tiles",
+                           "rows_per_strip": args.rows_per_strip, "ensemble": 1, "head": "dense",
+                           "l2": "inputs (>=6 GB per GPU) far larger than the 126 MB L2; no flush needed",
+                           "weights": "random-init DDA x2 + head (oracle.random_state_dict seed 1600)"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "fp32_simt": fp32,
+                "cpu_baseline": cpu_base, "train_step": train,
+                "check": {"sum_of_region_sums": sums_check, "map_total": map_total}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -34,6 +34,14 @@ typedef void* pc_stream_t; /* cudaStream_t */
 /* Library version (major*100+minor) and last error text of the calling thread. */
 int pc_version(void);
 const char* pc_last_error(void);
+/* Number of kernels this library has launched in this process (all threads); reset != 0 zeroes it after reading.
+ * bench.py reports it as "gpu_launches". */
+long long pc_launch_count(int reset);
+/* Strided window copy between a (pinned) host raster and device memory on `stream` (cudaMemcpy2DAsync);
+ * kind 1 = host->device, 2 = device->host.  Replaces to_cuda_inplace (utils/utils.py:22) / the per-tile .cpu()
+ * of run_eval.py:127-135 for row/column windows that are not contiguous in the raster. */
+int pc_memcpy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes, size_t rows,
+                      int kind, pc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Packed weights.  The host folds BatchNorm(eval) into each conv and lays the
@@ -76,7 +84,7 @@ int pc_dda_forward(const float* wpack, const float* x, int B, int C, int H, int 
  *           data/PopulationDataset.py:705-712 when `ids` is a full id raster).
  *   feats [B,Cin,H,W] (strided), builtup [B,1,H,W] or NULL (occupancymodel=False: dens = relu(out))
  *   dens, scale   [B,H,W] outputs (scale may be NULL)
- *   ids           optional int32 [B,H,W] region ids; sums (double[B? no: R]) += dens where 0 <= id < R
+ *   ids           optional int32 [B,H,W] region ids; sums (double[R]) += dens where 0 <= id < R
  *   census_idx    optional int32 [B]: if given, sums has B entries and pixel p of image b contributes to
  *                 sums[b] iff ids[b,p] == census_idx[b]  (popcount of model/popcorn.py:186-187);
  *                 with ids == NULL and sums != NULL: sums[b] += all pixels of image b (:190)
@@ -167,6 +175,10 @@ int pc_test_conv3x3(const float* a, int cin_a, int a_H, int a_W, int a_oy, int a
                     int cin_b, int b_H, int b_W, int b_oy, int b_ox, const float* w, int cout, int H, int W,
                     float* out, float* pool, pc_stream_t stream);
 int pc_test_convt2x2(const float* in, int C, int Hl, int Wl, const float* w, float* out, pc_stream_t stream);
+/* FP32 SIMT ceiling probe: every thread runs 32*iters dependent-chain FMAs (scalar, or packed fma.rn.f32x2);
+ * returns the number of threads launched (negative = error is impossible: errors are > 0 codes <= 10002, thread
+ * counts are >= 37888).  Measured denominator for the stencil kernels' FP32 roofline. */
+int pc_test_fma_peak(int use_x2, int iters, int blocks_per_sm, float* out, pc_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -21,6 +21,8 @@ _vp, _i, _ll, _sz, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_size_t, C.c_float
 SIGNATURES = {
     "pc_version": (_i, []),
     "pc_last_error": (C.c_char_p, []),
+    "pc_launch_count": (_ll, [_i]),
+    "pc_memcpy2d_async": (_i, [_vp, _sz, _vp, _sz, _sz, _sz, _i, _vp]),
     "pc_dda_pack_floats": (_i, []),
     "pc_dda_pack_offset": (_i, [_i, _i]),
     "pc_head_pack_floats": (_i, [_i]),
@@ -40,6 +42,7 @@ SIGNATURES = {
     "pc_finalize_map": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _vp]),
     "pc_test_conv3x3": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "pc_test_convt2x2": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
+    "pc_test_fma_peak": (_i, [_i, _i, _i, _vp, _vp]),
 }
 
 

@@ -14,6 +14,9 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+static long long g_launches = 0;
+void count_launch() { __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED); }
+
 int num_sms() {
     static int cached[64] = {0};
     int dev = 0;
@@ -29,4 +32,60 @@ int num_sms() {
 }  // namespace pc
 
 extern "C" int pc_version(void) { return 100; }
+extern "C" long long pc_launch_count(int reset) {
+    const long long v = __atomic_load_n(&pc::g_launches, __ATOMIC_RELAXED);
+    if (reset) __atomic_store_n(&pc::g_launches, 0, __ATOMIC_RELAXED);
+    return v;
+}
+extern "C" int pc_memcpy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes,
+                                 size_t rows, int kind, pc_stream_t stream) {
+    PC_CHECK_ARG(dst && src, "null pointer");
+    PC_CHECK_ARG(kind == 1 || kind == 2, "kind must be 1 (host->device) or 2 (device->host)");
+    if (rows == 0 || width_bytes == 0) return 0;
+    PC_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, rows,
+                              kind == 1 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return 0;
+}
 extern "C" const char* pc_last_error(void) { return pc::g_err; }
+
+// ---------------------------------------------------------------------------------------------------
+// FP32 SIMT ceiling probe (tools/kernel_bench.py): a register-resident FMA loop, scalar or packed x2.
+// 2 * 32 * iters FLOP per thread.  Used as the measured "fp32" roofline denominator for the stencils.
+// ---------------------------------------------------------------------------------------------------
+template <bool X2>
+__global__ void __launch_bounds__(256) fma_peak_kernel(int iters, float* out) {
+    float a[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) a[i] = threadIdx.x * 1e-3f + i;
+    const float m = 1.0000001f, c = 1e-7f;
+    if (X2) {
+        unsigned long long v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = pc::pack2(a[2 * i], a[2 * i + 1]);
+        const unsigned long long mm = pc::pack2(m, m), cc = pc::pack2(c, c);
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(v[i]) : "l"(mm), "l"(cc));
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pc::unpack2(v[i], a[2 * i], a[2 * i + 1]);
+    } else {
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) a[i] = fmaf(a[i], m, c);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) s += a[i];
+    if (s == 12345.678f) out[0] = s;
+}
+
+extern "C" int pc_test_fma_peak(int use_x2, int iters, int blocks_per_sm, float* out, pc_stream_t stream) {
+    PC_CHECK_ARG(out && iters > 0 && blocks_per_sm > 0, "bad argument");
+    const int grid = pc::num_sms() * blocks_per_sm;
+    if (use_x2) fma_peak_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(iters, out);
+    else fma_peak_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(iters, out);
+    PC_LAUNCH_CHECK();
+    return grid * 256;
+}

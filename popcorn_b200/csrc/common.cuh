@@ -9,6 +9,7 @@
 namespace pc {
 
 void set_error(const char* fmt, ...);
+void count_launch();
 
 #define PC_CHECK_ARG(cond, msg)                           \
     do {                                                  \
@@ -29,6 +30,7 @@ void set_error(const char* fmt, ...);
 
 #define PC_LAUNCH_CHECK()                                                                     \
     do {                                                                                      \
+        pc::count_launch();                                                                   \
         cudaError_t _e = cudaGetLastError();                                                  \
         if (_e != cudaSuccess) {                                                              \
             pc::set_error("%s: kernel launch failed: %s", __func__, cudaGetErrorString(_e));  \

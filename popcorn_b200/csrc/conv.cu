@@ -42,21 +42,37 @@ struct ConvParams {
     ConvJob jobs[MAX_JOBS];
 };
 
+template <int CIN>
+__host__ __device__ constexpr int conv_cc() { return CIN < 4 ? CIN : 4; }       // channels per staged chunk
+
 template <int CIN, int COUT, int EPI>
 constexpr int conv_smem_floats() {
-    constexpr int CC = CIN < 8 ? CIN : 8;
-    return CIN * 9 * COUT + COUT + CC * SROWS * SPITCH;
+    constexpr int CC = conv_cc<CIN>();
+    constexpr int NBUF = (CIN / CC) > 1 ? 2 : 1;
+    return CIN * 9 * COUT + COUT + NBUF * CC * SROWS * SPITCH;
 }
+
+// 4-byte async copy global -> shared with zero fill when !ok (src-size 0 reads nothing)
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc, bool ok) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int n = ok ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int CIN_A, int CIN_B, int COUT, int EPI, bool F32X2>
 __global__ void __launch_bounds__(128 * (COUT / 8), (COUT == 8) ? 4 : 2)
 conv3x3_kernel(const __grid_constant__ ConvParams p) {
     constexpr int CIN = CIN_A + CIN_B;
-    constexpr int CC = CIN < 8 ? CIN : 8;
+    constexpr int CC = conv_cc<CIN>();
     constexpr int NCHUNK = CIN / CC;
+    constexpr int NBUF = NCHUNK > 1 ? 2 : 1;
     constexpr int NT = 128 * (COUT / 8);
     constexpr int NWARP = NT / 32;
     constexpr int WFLOATS = CIN * 9 * COUT + COUT;
+    constexpr int XBUF = CC * SROWS * SPITCH;
     static_assert(CIN % CC == 0 && (CIN_A % CC == 0 || CIN_B == 0), "chunks must not straddle sources");
 
     extern __shared__ __align__(16) float smem[];
@@ -70,6 +86,50 @@ conv3x3_kernel(const __grid_constant__ ConvParams p) {
     const int x0 = blockIdx.x * TILE, y0 = blockIdx.y * TILE;
     const int H = p.H, W = p.W;
 
+    // ---- stage CC channels of the (virtual) input tile with a 1-px halo: all copies are issued
+    //      back-to-back as cp.async (no register staging, no branches), zero-filled outside ----
+    auto stage = [&](int chunk, float* dst) {
+        const bool fromA = (chunk * CC) < CIN_A;
+        const float* sp; long long cs; int rs, sH, sW, oy, ox, refl, ch0;
+        if (fromA) { sp = job.a; cs = job.a_cs; rs = job.a_rs; sH = job.a_H; sW = job.a_W; oy = job.a_oy; ox = job.a_ox; refl = job.a_reflect; ch0 = chunk * CC; }
+        else       { sp = job.b; cs = job.b_cs; rs = job.b_rs; sH = job.b_H; sW = job.b_W; oy = job.b_oy; ox = job.b_ox; refl = 0; ch0 = chunk * CC - CIN_A; }
+        int sxv[2]; bool okv[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int c = lane + 32 * k;
+            const int vx = x0 - 1 + c;
+            bool ok = (c < SROWS) && vx >= 0 && vx < W;
+            int sx = vx - ox;
+            if (refl) { sx = sx < 0 ? -sx : sx; sx = sx >= sW ? 2 * (sW - 1) - sx : sx; }
+            else ok = ok && sx >= 0 && sx < sW;
+            sxv[k] = ok ? sx : 0; okv[k] = ok;
+        }
+        const float* planes[CC];
+#pragma unroll
+        for (int c = 0; c < CC; ++c) {
+            int plane = ch0 + c;
+            if (CIN_A <= 4 && fromA) plane = (job.a_chmap >> (8 * plane)) & 0xff;
+            planes[c] = sp + plane * cs;
+        }
+#pragma unroll 3
+        for (int r = warp; r < SROWS; r += NWARP) {
+            const int vy = y0 - 1 + r;
+            bool rok = vy >= 0 && vy < H;
+            int sy = vy - oy;
+            if (refl) { sy = sy < 0 ? -sy : sy; sy = sy >= sH ? 2 * (sH - 1) - sy : sy; }
+            else rok = rok && sy >= 0 && sy < sH;
+            const long long roff = rok ? (long long)sy * rs : 0;
+#pragma unroll
+            for (int c = 0; c < CC; ++c) {
+                float* d = dst + (c * SROWS + r) * SPITCH + lane;
+                cp_async4(d, planes[c] + roff + sxv[0], rok && okv[0]);
+                if (lane < SROWS - 32) cp_async4(d + 32, planes[c] + roff + sxv[1], rok && okv[1]);
+            }
+        }
+    };
+
+    stage(0, xs);
+    cp_async_commit();
     for (int i = tid; i < WFLOATS / 4; i += NT)
         reinterpret_cast<float4*>(ws)[i] = __ldg(reinterpret_cast<const float4*>(job.w) + i);
 
@@ -87,48 +147,17 @@ conv3x3_kernel(const __grid_constant__ ConvParams p) {
 
 #pragma unroll 1
     for (int chunk = 0; chunk < NCHUNK; ++chunk) {
-        __syncthreads();  // previous chunk fully consumed
-        // ---------------- stage CC channels of the (virtual) input tile, 1-px halo, zero outside ----------------
-        {
-            const bool fromA = (chunk * CC) < CIN_A;
-            const float* sp; long long cs; int rs, sH, sW, oy, ox, refl, ch0;
-            if (fromA) { sp = job.a; cs = job.a_cs; rs = job.a_rs; sH = job.a_H; sW = job.a_W; oy = job.a_oy; ox = job.a_ox; refl = job.a_reflect; ch0 = chunk * CC; }
-            else       { sp = job.b; cs = job.b_cs; rs = job.b_rs; sH = job.b_H; sW = job.b_W; oy = job.b_oy; ox = job.b_ox; refl = 0; ch0 = chunk * CC - CIN_A; }
-            int sxv[2]; bool okv[2];
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const int c = lane + 32 * k;
-                const int vx = x0 - 1 + c;
-                bool ok = (c < SROWS) && vx >= 0 && vx < W;
-                int sx = vx - ox;
-                if (refl) { sx = sx < 0 ? -sx : sx; sx = sx >= sW ? 2 * (sW - 1) - sx : sx; }
-                else ok = ok && sx >= 0 && sx < sW;
-                sxv[k] = sx; okv[k] = ok;
-            }
-            for (int r = warp; r < SROWS; r += NWARP) {
-                const int vy = y0 - 1 + r;
-                bool rok = vy >= 0 && vy < H;
-                int sy = vy - oy;
-                if (refl) { sy = sy < 0 ? -sy : sy; sy = sy >= sH ? 2 * (sH - 1) - sy : sy; }
-                else rok = rok && sy >= 0 && sy < sH;
-                const float* rowp = sp + (long long)sy * rs;
-#pragma unroll
-                for (int c = 0; c < CC; ++c) {
-                    int plane = ch0 + c;
-                    if (CIN_A <= 4 && fromA) plane = (job.a_chmap >> (8 * plane)) & 0xff;
-                    const float* pp = rowp + plane * cs;
-                    float v0 = (rok && okv[0]) ? __ldg(pp + sxv[0]) : 0.f;
-                    xs[(c * SROWS + r) * SPITCH + lane] = v0;
-                    if (lane < SROWS - 32) {
-                        float v1 = (rok && okv[1]) ? __ldg(pp + sxv[1]) : 0.f;
-                        xs[(c * SROWS + r) * SPITCH + 32 + lane] = v1;
-                    }
-                }
-            }
+        float* cur = xs + (chunk & (NBUF - 1)) * XBUF;
+        if (chunk + 1 < NCHUNK) {           // prefetch the next chunk into the other buffer
+            stage(chunk + 1, xs + ((chunk + 1) & (NBUF - 1)) * XBUF);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
         }
         __syncthreads();
         // ---------------- register-tiled stencil: 2x4 pixels x 8 output channels per thread ----------------
-        const float* xt = xs + (2 * ty) * SPITCH + 4 * tx;
+        const float* xt = cur + (2 * ty) * SPITCH + 4 * tx;
 #pragma unroll 1
         for (int c = 0; c < CC; ++c) {
             float xin[4][8];
@@ -178,6 +207,7 @@ conv3x3_kernel(const __grid_constant__ ConvParams p) {
                     }
                 }
         }
+        if (NBUF > 1) __syncthreads();  // `cur` is refilled by the prefetch issued at the top of the next-but-one chunk
     }
 
     // ---------------- epilogue: bias + ReLU, then store / pool / logit dot ----------------
@@ -373,7 +403,7 @@ template <int CIN_A, int CIN_B, int COUT, int EPI>
 static int launch_conv(const ConvParams& p, int njobs, cudaStream_t st) {
     static const bool use_x2 = [] {
         const char* e = getenv("POPCORN_CONV_F32X2");
-        return e ? atoi(e) != 0 : false;
+        return e ? atoi(e) != 0 : true;   // packed fma.rn.f32x2 (FFMA2) is ~13% faster on B200
     }();
     constexpr int smem = conv_smem_floats<CIN_A + CIN_B, COUT, EPI>() * 4;
     dim3 grid(cdiv(p.W, TILE), cdiv(p.H, TILE), njobs), block(8, 16, COUT / 8);

@@ -24,48 +24,56 @@ __global__ void __launch_bounds__(256) region_sum_kernel(const float* __restrict
     int cur = -1;        // warp-uniform id of the open run
     float run = 0.f;     // this lane's private partial of the open run
     const bool vec_ok = ((((uintptr_t)dens) | ((uintptr_t)ids)) & 15) == 0;
-    for (long long g = beg; g < end; g += 128) {
-        const long long p = g + 4 * lane;
-        float v[4]; int id[4];
-        if (vec_ok && p + 3 < end) {
-            const float4 fv = ld_stream4(dens + p);
-            const int4 iv = ld_stream4i(ids + p);
-            v[0] = fv.x; v[1] = fv.y; v[2] = fv.z; v[3] = fv.w;
-            id[0] = iv.x; id[1] = iv.y; id[2] = iv.z; id[3] = iv.w;
-        } else {
+    constexpr int U = 4;   // independent 128-px groups in flight per warp (8 x 16 B loads per lane)
+    for (long long g0 = beg; g0 < end; g0 += 128 * U) {
+        float v[U][4]; int id[U][4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const bool ok = p + k < end;
-                v[k] = ok ? dens[p + k] : 0.f;
-                id[k] = ok ? ids[p + k] : -1;
+        for (int u = 0; u < U; ++u) {
+            const long long p = g0 + 128 * u + 4 * lane;
+            if (vec_ok && p + 3 < end) {
+                const float4 fv = ld_stream4(dens + p);
+                const int4 iv = ld_stream4i(ids + p);
+                v[u][0] = fv.x; v[u][1] = fv.y; v[u][2] = fv.z; v[u][3] = fv.w;
+                id[u][0] = iv.x; id[u][1] = iv.y; id[u][2] = iv.z; id[u][3] = iv.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const bool ok = p + k < end;
+                    v[u][k] = ok ? dens[p + k] : 0.f;
+                    id[u][k] = ok ? ids[p + k] : -1;
+                }
             }
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (id[k] < 0 || id[k] >= R) { id[k] = -1; v[k] = 0.f; }
-        const bool mine_uniform = (id[0] == id[1]) && (id[1] == id[2]) && (id[2] == id[3]);
-        int all_same;
-        __match_all_sync(0xffffffffu, mine_uniform ? id[0] : -2 - lane, &all_same);
-        if (all_same) {
-            if (id[0] != cur) {           // warp-uniform branch
-                const float s = warp_sum(run);
-                if (lane == 0 && cur >= 0) atomicAdd(sums + cur, (double)s);
-                cur = id[0];
-                run = 0.f;
-            }
-            run += (v[0] + v[1]) + (v[2] + v[3]);
-        } else {
-            // mixed group: merge equal neighbours privately, then one atomic per private run
-            float s = v[0]; int c = id[0];
+        for (int u = 0; u < U; ++u) {
+            if (g0 + 128 * u >= end) break;   // warp-uniform
 #pragma unroll
-            for (int k = 1; k < 4; ++k) {
-                if (id[k] == c) s += v[k];
-                else {
-                    if (c >= 0) atomicAdd(sums + c, (double)s);
-                    c = id[k]; s = v[k];
+            for (int k = 0; k < 4; ++k)
+                if (id[u][k] < 0 || id[u][k] >= R) { id[u][k] = -1; v[u][k] = 0.f; }
+            const bool mine_uniform = (id[u][0] == id[u][1]) && (id[u][1] == id[u][2]) && (id[u][2] == id[u][3]);
+            int all_same;
+            __match_all_sync(0xffffffffu, mine_uniform ? id[u][0] : -2 - lane, &all_same);
+            if (all_same) {
+                if (id[u][0] != cur) {           // warp-uniform branch
+                    const float s = warp_sum(run);
+                    if (lane == 0 && cur >= 0) atomicAdd(sums + cur, (double)s);
+                    cur = id[u][0];
+                    run = 0.f;
                 }
+                run += (v[u][0] + v[u][1]) + (v[u][2] + v[u][3]);
+            } else {
+                // mixed group: merge equal neighbours privately, then one atomic per private run
+                float s = v[u][0]; int c = id[u][0];
+#pragma unroll
+                for (int k = 1; k < 4; ++k) {
+                    if (id[u][k] == c) s += v[u][k];
+                    else {
+                        if (c >= 0) atomicAdd(sums + c, (double)s);
+                        c = id[u][k]; s = v[u][k];
+                    }
+                }
+                if (c >= 0) atomicAdd(sums + c, (double)s);
             }
-            if (c >= 0) atomicAdd(sums + c, (double)s);
         }
     }
     const float s = warp_sum(run);
@@ -230,13 +238,14 @@ __global__ void __launch_bounds__(256) accumulate_kernel(const float* __restrict
     if (c >= c1 || r >= r1) return;
     const long long t = (long long)r * t_rs + c;
     const long long m = (long long)(y0 + r) * m_rs + (x0 + c);
+    // separately rounded mul / add (no FMA contraction): the reference squares, then adds (run_eval.py:111,128)
     const float d = dens[t];
     map[m] += d;
-    if (map_sq) map_sq[m] += d * d;
+    if (map_sq) map_sq[m] = __fadd_rn(map_sq[m], __fmul_rn(d, d));
     if (scale) {
         const float s = scale[t];
         if (smap) smap[m] += s;
-        if (smap_sq) smap_sq[m] += s * s;
+        if (smap_sq) smap_sq[m] = __fadd_rn(smap_sq[m], __fmul_rn(s, s));
     }
     if (count) count[m] += 1;
 }
@@ -248,13 +257,17 @@ __global__ void __launch_bounds__(256) finalize_kernel(float* map, float* map_sq
         const int n = count[p];
         if (n <= 1) continue;                                   // run_eval.py:140 (div_mask = count > 1)
         const float nf = (float)n;
-        const float mean = map[p] / nf;
+        // op-by-op IEEE arithmetic in the reference's order (run_eval.py:143-154): the variance formula cancels
+        // catastrophically where tile results nearly coincide, so FMA contraction would change NaN / 0 outcomes
+        const float mean = __fdiv_rn(map[p], nf);
         map[p] = mean;
-        if (map_sq) map_sq[p] = sqrtf((map_sq[p] - mean * mean * nf) / (nf - 1.f));   // run_eval.py:146
+        if (map_sq)
+            map_sq[p] = __fsqrt_rn(__fdiv_rn(__fsub_rn(map_sq[p], __fmul_rn(__fmul_rn(mean, mean), nf)), nf - 1.f));
         if (smap) {
-            const float sm = smap[p] / nf;
+            const float sm = __fdiv_rn(smap[p], nf);
             smap[p] = sm;
-            if (smap_sq) smap_sq[p] = sqrtf((smap_sq[p] - sm * sm * nf) / (nf - 1.f));
+            if (smap_sq)
+                smap_sq[p] = __fsqrt_rn(__fdiv_rn(__fsub_rn(smap_sq[p], __fmul_rn(__fmul_rn(sm, sm), nf)), nf - 1.f));
         }
     }
 }
@@ -265,13 +278,13 @@ using namespace pc;
 
 extern "C" int pc_region_sum(const float* dens, const int32_t* ids, long long npix, int R, double* sums,
                              pc_stream_t stream) {
-    PC_CHECK_ARG(dens && ids && sums, "null pointer");
     PC_CHECK_ARG(npix >= 0 && R >= 1, "bad shape");
     if (npix == 0) return 0;
+    PC_CHECK_ARG(dens && ids && sums, "null pointer");
     // ~16 warps per SM resident x 4 waves of spans; each span a multiple of 128 px
     const long long want_warps = (long long)num_sms() * 16 * 4;
-    long long span = round_up(cdiv(npix, want_warps), 128);
-    if (span < 1024) span = 1024;
+    long long span = round_up(cdiv(npix, want_warps), 512);
+    if (span < 2048) span = 2048;
     const long long nwarps = cdiv(npix, span);
     const int grid = cdiv(nwarps * 32, 256);
     region_sum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dens, ids, npix, R, sums, span);
@@ -281,9 +294,9 @@ extern "C" int pc_region_sum(const float* dens, const int32_t* ids, long long np
 
 extern "C" int pc_region_sum_backward(const float* g_sums, const int32_t* ids, long long npix, int R, float* g_dens,
                                       pc_stream_t stream) {
-    PC_CHECK_ARG(g_sums && ids && g_dens, "null pointer");
     PC_CHECK_ARG(npix >= 0 && R >= 1, "bad shape");
     if (npix == 0) return 0;
+    PC_CHECK_ARG(g_sums && ids && g_dens, "null pointer");
     const int grid = (int)(cdiv(npix, 256) < num_sms() * 16 ? cdiv(npix, 256) : num_sms() * 16);
     region_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g_sums, ids, npix, R, g_dens, 0);
     PC_LAUNCH_CHECK();
@@ -292,9 +305,9 @@ extern "C" int pc_region_sum_backward(const float* g_sums, const int32_t* ids, l
 
 extern "C" int pc_region_scale(float* dens, const int32_t* ids, long long npix, int R, const float* factor,
                                pc_stream_t stream) {
-    PC_CHECK_ARG(dens && ids && factor, "null pointer");
     PC_CHECK_ARG(npix >= 0 && R >= 1, "bad shape");
     if (npix == 0) return 0;
+    PC_CHECK_ARG(dens && ids && factor, "null pointer");
     const int grid = (int)(cdiv(npix, 256) < num_sms() * 16 ? cdiv(npix, 256) : num_sms() * 16);
     region_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(factor, ids, npix, R, dens, 1);
     PC_LAUNCH_CHECK();

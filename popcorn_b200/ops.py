@@ -186,3 +186,29 @@ def finalize_map(maps):
     m, msq, sm, ssq, cnt = maps
     _lib.check(_lib.lib().pc_finalize_map(m.data_ptr(), _ptr(msq), _ptr(sm), _ptr(ssq), cnt.data_ptr(), m.numel(),
                                           _stream()), "pc_finalize_map")
+
+
+def launch_count(reset: bool = False) -> int:
+    """Kernels launched by libpopcorn_b200 so far in this process."""
+    return int(_lib.lib().pc_launch_count(1 if reset else 0))
+
+
+def copy_window_h2d(dst: torch.Tensor, src: torch.Tensor, stream: Optional[int] = None) -> None:
+    """dst [C,h,w] device (contiguous rows) <- src [C,h,w] view of a pinned host raster (unit column stride)."""
+    assert dst.is_cuda and not src.is_cuda and src.stride(2) == 1 and dst.stride(2) == 1 and dst.shape == src.shape
+    L = _lib.lib()
+    st = _stream() if stream is None else stream
+    C, h, w = src.shape
+    es = src.element_size()
+    for c in range(C):
+        _lib.check(L.pc_memcpy2d_async(dst[c].data_ptr(), dst.stride(1) * es, src[c].data_ptr(), src.stride(1) * es,
+                                       w * es, h, 1, st), "pc_memcpy2d_async")
+
+
+def copy_d2h(dst: torch.Tensor, src: torch.Tensor, stream: Optional[int] = None) -> None:
+    """dst pinned host [h,w] <- src device [h,w] (both unit column stride)."""
+    assert src.is_cuda and not dst.is_cuda and dst.shape == src.shape and src.dim() == 2
+    es = src.element_size()
+    _lib.check(_lib.lib().pc_memcpy2d_async(dst.data_ptr(), dst.stride(0) * es, src.data_ptr(), src.stride(0) * es,
+                                            src.shape[1] * es, src.shape[0], 2, _stream() if stream is None else stream),
+               "pc_memcpy2d_async")

@@ -1,0 +1,120 @@
+"""CPU: window planning / sharding logic of the country driver and the N>1 combine step (gloo, world_size 2)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from popcorn_b200 import country as ct
+from oracle import popcorn_oracle as po
+
+
+def _count_from_windows(wins, H, W, ov):
+    c = torch.zeros(H, W, dtype=torch.int16)
+    for w in wins:
+        c[w.y0 + ov: w.y0 + w.h - ov, w.x0 + ov: w.x0 + w.w - ov] += 1
+    return c
+
+
+def _count_reference(H, W, ps, ov):
+    c = torch.zeros(H, W, dtype=torch.int16)
+    m = po.centre_mask(ps, ps, ov)
+    for xl, yl in po.get_patch_indices(H, W, ps, ov).tolist():
+        c[xl:xl + ps, yl:yl + ps][m] += 1
+    return c
+
+
+@pytest.mark.parametrize("H,W,ps,ov", [(200, 236, 96, 16), (300, 97, 96, 16), (97, 400, 96, 16), (1000, 1100, 256, 32),
+                                       (15104 // 8, 17216 // 8, 256, 16)])
+@pytest.mark.parametrize("merge,rps", [(False, 1), (True, 1), (True, 2), (True, 3)])
+def test_windows_cover_exactly_like_the_reference_tile_grid(H, W, ps, ov, merge, rps):
+    wins = ct.plan_windows(H, W, ps, ov, merge, rps)
+    assert torch.equal(_count_from_windows(wins, H, W, ov), _count_reference(H, W, ps, ov))
+    assert sum(w.ntiles for w in wins) == len(po.get_patch_indices(H, W, ps, ov))
+    stride = ps - 2 * ov
+    for w in wins:   # merged windows keep every tile's pool phase: origins on the reference grid, size = k*stride + 2*ov
+        assert (w.h - 2 * ov) % stride == 0 and (w.w - 2 * ov) % stride == 0
+        assert w.y0 % stride == 0 or w.y0 == H - ps
+        assert w.x0 % stride == 0 or w.x0 == W - ps
+
+
+def test_unmerged_plan_is_the_reference_index_list():
+    H, W, ps, ov = 200, 236, 96, 16
+    mine = sorted((w.y0, w.x0) for w in ct.plan_windows(H, W, ps, ov, merge=False))
+    assert mine == sorted(map(tuple, po.get_patch_indices(H, W, ps, ov).tolist()))
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+@pytest.mark.parametrize("rps", [1, 2])
+def test_sharding_partitions_windows_and_keeps_contributors_together(world, rps):
+    H, W, ps, ov = 1900, 700, 256, 32
+    wins = ct.plan_windows(H, W, ps, ov, True, rps)
+    n_rows = len(ct.grid_origins(H, ps, ov))
+    parts = [ct.shard_windows(wins, n_rows, r, world, rps) for r in range(world)]
+    assert sorted(sum(parts, []), key=lambda w: (w.y0, w.x0)) == sorted(wins, key=lambda w: (w.y0, w.x0))
+    owner = torch.full((H, W), -1, dtype=torch.int16)
+    for r, part in enumerate(parts):
+        for w in part:
+            reg = owner[w.y0 + ov: w.y0 + w.h - ov, w.x0 + ov: w.x0 + w.w - ov]
+            assert bool(((reg == -1) | (reg == r)).all()), "a pixel would be accumulated on two ranks"
+            reg.fill_(r)
+        lo, hi = ct.owned_rows(part, H, ov)
+        if part:
+            assert all(lo <= w.y0 + ov and w.y0 + w.h - ov <= hi for w in part)
+    # row ownership ranges of different ranks do not overlap
+    ranges = sorted(ct.owned_rows(p, H, ov) for p in parts if p)
+    assert all(a[1] <= b[0] for a, b in zip(ranges, ranges[1:]))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, H, W, R, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ps, ov = 96, 16
+        g = torch.Generator().manual_seed(5)
+        full_map = torch.rand(H, W, generator=g)
+        ids = po.synthetic_regions(H, W, R, seed=2)
+        wins = ct.plan_windows(H, W, ps, ov, True, 1)
+        mine = ct.shard_windows(wins, len(ct.grid_origins(H, ps, ov)), rank, world, 1)
+        lo, hi = ct.owned_rows(mine, H, ov)
+        # each rank "computes" only the pixels its windows write; partial census sums over its own rows
+        local = torch.zeros(H, W)
+        for w in mine:
+            ys, xs = slice(w.y0 + ov, w.y0 + w.h - ov), slice(w.x0 + ov, w.x0 + w.w - ov)
+            local[ys, xs] = full_map[ys, xs]
+        part = po.region_sums(local[lo:hi], ids[lo:hi], R + 1)
+        total = ct.allreduce_sums(part.clone())
+        q.put((rank, total))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_partial_sums_allreduce_gloo():
+    H, W, R = 500, 236, 9
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, H, W, R, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = torch.Generator().manual_seed(5)
+    full_map = torch.rand(H, W, generator=g)
+    ids = po.synthetic_regions(H, W, R, seed=2)
+    covered = _count_reference(H, W, 96, 16) > 0
+    ref = po.region_sums(full_map * covered, ids, R + 1)
+    assert torch.allclose(res[0], ref, rtol=1e-12) and torch.equal(res[0], res[1])

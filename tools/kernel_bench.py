@@ -51,6 +51,15 @@ def main():
     ms = timeit(lambda: ops.region_sum(d, big_ids, 401))
     res["region_sum_ms"] = ms
     res["region_sum_gbs"] = 8 * n / ms / 1e6
+    from popcorn_b200 import _lib
+    o = torch.zeros(4, device="cuda")
+    for x2 in (0, 1):
+        iters = 4096
+        nthr = [0]
+        def run():
+            nthr[0] = _lib.lib().pc_test_fma_peak(x2, iters, 8, o.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        ms = timeit(run)
+        res[f"fma_peak_x2_{x2}_tflops"] = 2 * 32 * iters * nthr[0] / ms / 1e9
     print(json.dumps(res))
 
 

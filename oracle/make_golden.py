@@ -97,7 +97,7 @@ def main():
                         **{"grad." + k: v.numpy() for k, v in grads.items()})
 
     # ---- tiled eval (restated run_eval loop around the reference forward), small patch size ----------------
-    Hh, Ww, ps, ov = 200, 236, 96, 16
+    Hh, Ww, ps, ov = 266, 301, 128, 32   # edge tiles at 138 / 173: off the 4-px pool phase of the main grid
     raster = po.synthetic_input(Hh, Ww, seed=99)[0]
     with torch.no_grad():
         ref_map, ref_std, ref_scale, ref_cnt = po.tiled_eval(

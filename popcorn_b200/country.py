@@ -26,6 +26,13 @@ from . import ops
 
 PATCH = 2048      # utils/constants.py:12
 OVERLAP = 128     # utils/constants.py:13
+RF_RADIUS = 24    # receptive-field radius of the DDA UNet is 23 px -> 24 keeps the 4-px phase
+
+
+def can_merge(patch: int, overlap: int) -> bool:
+    """Merged windows equal per-tile execution on the written centre only if the discarded frame (overlap) covers the
+    receptive field of the tile border (zero / reflect padding artefacts) and the tile stride keeps the pool phase."""
+    return overlap >= RF_RADIUS and (patch - 2 * overlap) % 4 == 0 and patch % 4 == 0
 
 
 @dataclass(frozen=True)
@@ -120,6 +127,8 @@ class CountryEngine:
         self.H, self.W, self.patch, self.overlap = H, W, patch, overlap
         self.rank, self.world = rank, world
         self.want_scale, self.want_std = want_scale, want_std
+        merge = merge and can_merge(patch, overlap)      # otherwise fall back to the reference tile grid
+        self.merged = merge
         all_w = plan_windows(H, W, patch, overlap, merge, rows_per_strip if merge else 1)
         n_rows = len(grid_origins(H, patch, overlap))
         self.windows = shard_windows(all_w, n_rows, rank, world, rows_per_strip if merge else 1) if world > 1 else all_w

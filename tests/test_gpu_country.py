@@ -25,12 +25,15 @@ def test_tiled_eval_vs_reference_golden(model, merge, rps, streamed):
     _, H, W = raster.shape
     R = int(g["ids"].max()) + 1
     eng = ct.CountryEngine([model], H, W, ps, ov, merge=merge, rows_per_strip=rps)
+    assert eng.merged == merge
+    lo, hi = eng.out_rows                         # the outer `overlap` frame of the raster is never written (stays 0)
+    assert (lo, hi) == (ov, H - ov) and float(g["map"][:lo].abs().sum() + g["map"][hi:].abs().sum()) == 0.0
     src = raster.pin_memory() if streamed else raster.cuda()
     with torch.no_grad():
-        out = eng.run(src, g["ids"].cuda().contiguous(), R)
-    assert torch.equal(out["count"].cpu(), g["count"])
-    assert max_rel(out["map"], g["map"]) < TOL_PIXEL
-    assert max_rel(out["scale_map"], g["scale_map"]) < TOL_PIXEL
+        out = eng.run(src, g["ids"][lo:hi].cuda().contiguous(), R)
+    assert torch.equal(out["count"].cpu(), g["count"][lo:hi])
+    assert max_rel(out["map"], g["map"][lo:hi]) < TOL_PIXEL
+    assert max_rel(out["scale_map"], g["scale_map"][lo:hi]) < TOL_PIXEL
     valid = g["census"] > -1
     assert max_rel(out["sums"][1:].float().cpu()[valid], g["census"][valid], floor_frac=1.0) < TOL_REGION
 
@@ -43,8 +46,9 @@ def test_merged_strips_are_bit_identical_to_reference_tiles(model):
     outs = []
     for merge, rps in ((False, 1), (True, 1), (True, 3)):
         eng = ct.CountryEngine([model], H, W, ps, ov, merge=merge, rows_per_strip=rps)
+        lo, hi = eng.out_rows
         with torch.no_grad():
-            outs.append(eng.run(raster, ids, 31))
+            outs.append(eng.run(raster, ids[lo:hi].contiguous(), 31))
     for o in outs[1:]:
         assert torch.equal(o["map"], outs[0]["map"])
         assert torch.equal(o["count"], outs[0]["count"])
@@ -57,16 +61,18 @@ def test_rank_sharded_partials_sum_to_the_single_gpu_result(model):
     raster = po.synthetic_input(H, W, seed=22)[0].cuda()
     ids = po.synthetic_regions(H, W, 20).cuda()
     with torch.no_grad():
-        full = ct.CountryEngine([model], H, W, ps, ov, merge=True, rows_per_strip=1).run(raster, ids, 21)
+        e0 = ct.CountryEngine([model], H, W, ps, ov, merge=True, rows_per_strip=1)
+        flo, fhi = e0.out_rows
+        full = e0.run(raster, ids[flo:fhi].contiguous(), 21)
         total = torch.zeros_like(full["sums"])
         for r in range(3):
             eng = ct.CountryEngine([model], H, W, ps, ov, merge=True, rows_per_strip=1, rank=r, world=3)
             lo, hi = eng.out_rows
             i0, i1 = eng.in_rows
             o = eng.run(raster[:, i0:i1].contiguous(), ids[lo:hi].contiguous(), 21, row_offset=i0)
-            assert torch.equal(o["map"], full["map"][lo:hi])
+            assert torch.equal(o["map"], full["map"][lo - flo:hi - flo])
             total += o["sums"]
-    assert max_rel(total, full["sums"], floor_frac=1.0) < 1e-9
+    assert max_rel(total, full["sums"], floor_frac=1.0) < 1e-6   # fp32 warp partials regroup across shards
 
 
 def test_ensemble_mean_std_and_dasymetric_adjust(model):
@@ -81,19 +87,26 @@ def test_ensemble_mean_std_and_dasymetric_adjust(model):
     ids = po.synthetic_regions(H, W, 6)
     eng = ct.CountryEngine([model, m2], H, W, ps, ov, merge=True)
     assert eng._bext_shared
+    lo, hi = eng.out_rows
+    ids_own = ids[lo:hi].cuda().contiguous()
     with torch.no_grad():
-        out = eng.run(raster.cuda(), ids.cuda(), 7)
+        out = eng.run(raster.cuda(), ids_own, 7)
         ref_map, ref_std, ref_scale, ref_cnt = po.tiled_eval([gsd, sd2], raster, ps, ov)
-    assert torch.equal(out["count"].cpu(), ref_cnt)
-    assert max_rel(out["map"], ref_map) < TOL_PIXEL
-    covered = ref_cnt > 0
-    assert max_rel(out["std"].cpu()[covered], ref_std[covered], floor_frac=1e-2) < 5e-2
+    assert torch.equal(out["count"].cpu(), ref_cnt[lo:hi])
+    assert max_rel(out["map"], ref_map[lo:hi]) < TOL_PIXEL
+    covered = ref_cnt[lo:hi] > 0
+    assert max_rel(out["std"].cpu()[covered], ref_std[lo:hi][covered], floor_frac=1e-2) < 5e-2
     # dasymetric adjustment: afterwards every region with a non-zero prediction sums to its census count
     pop = torch.arange(7, dtype=torch.float32) * 1000 + 500
-    adj = ct.adjust_map_to_census(out["map"].clone(), ids.cuda(), out["sums"], pop)
-    sums2 = ops.region_sum(adj, ids.cuda(), 7).cpu()
+    adj = ct.adjust_map_to_census(out["map"].clone(), ids_own, out["sums"], pop)
+    sums2 = ops.region_sum(adj, ids_own, 7).cpu()
     nz = out["sums"].cpu() > 0
     assert torch.allclose(sums2[nz].float(), pop[nz], rtol=1e-4)
-    ref_adj = po.adjust_map_to_census(ref_map, ids.float(), list(range(7)), po.region_bboxes(ids, 7)[:0] or
-                                      [(0, H, 0, W)] * 7, pop)
-    assert max_rel(adj, ref_adj) < TOL_PIXEL
+    ref_adj = po.adjust_map_to_census(ref_map, ids.float(), list(range(7)), [(0, H, 0, W)] * 7, pop)
+    assert max_rel(adj, ref_adj[lo:hi]) < TOL_PIXEL
+
+
+def test_merging_is_refused_below_the_receptive_field(model):
+    """overlap 16 < 24: tile-border padding artefacts reach the written centre, so windows must not be merged."""
+    eng = ct.CountryEngine([model], 200, 236, 96, 16, merge=True)
+    assert not eng.merged and all(w.h == 96 and w.w == 96 for w in eng.windows)

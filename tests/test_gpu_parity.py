@@ -51,7 +51,8 @@ def test_dda_forward_vs_oracle(sd, copy, mode, H, W):
         ref = po.building_score(sd, x)
     got = ops.dda_forward(pack, x.cuda(), pads, mode)
     assert got.shape == ref.shape
-    assert max_rel(got, ref) < 1e-4
+    assert max_rel(got, ref, floor_frac=1.0) < 2e-5          # fp32 rounding relative to the largest activation
+    assert max_rel(got, ref) < 5e-3                            # per element, floor 1e-3 * max
 
 
 @pytest.mark.parametrize("C", [2, 4])

@@ -95,6 +95,21 @@ int pc_head_dense_forward(const float* hpack, int head_in, const float* feats, l
                           int o_rstride, const int32_t* ids, long long id_bstride, int id_rstride,
                           const int32_t* census_idx, double* sums, int R, pc_stream_t stream);
 
+/* Tensor-core variants of the two head forwards (tcgen05.mma kind::tf32 with 3xTF32 operand splitting, activations
+ * as the A operand in TMEM; csrc/head_tc.cu).  Same contract and arguments as pc_head_dense_forward /
+ * pc_head_sparse_forward, except that `tcpack` is the pc_head_tc_pack_bytes()-byte weight image built by
+ * popcorn_b200.weights.pack_head_tc (hi/lo split, K-major SWIZZLE_128B). */
+int pc_head_tc_pack_bytes(void);
+int pc_head_dense_forward_tc(const void* tcpack, int head_in, const float* feats, long long f_bstride,
+                             long long f_cstride, int f_rstride, const float* builtup, long long bu_bstride,
+                             int bu_rstride, int B, int H, int W, float* dens, float* scale, long long o_bstride,
+                             int o_rstride, const int32_t* ids, long long id_bstride, int id_rstride,
+                             const int32_t* census_idx, double* sums, int R, pc_stream_t stream);
+int pc_head_sparse_forward_tc(const void* tcpack, int head_in, const float* feats, long long f_bstride,
+                              long long f_cstride, const float* builtup, const int32_t* idx, const int32_t* n_dev,
+                              long long n_max, long long HW, float* dens, float* scale_sel, double* popcount,
+                              pc_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Sparse occupancy head (training path).
  * pc_sparse_mask_compact — get_sparsity_mask live branch + row-major compaction.

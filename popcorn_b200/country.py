@@ -23,6 +23,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import ops
+from .model import popcorn as popcorn_mod
 
 PATCH = 2048      # utils/constants.py:12
 OVERLAP = 128     # utils/constants.py:13
@@ -161,8 +162,9 @@ class CountryEngine:
                 builtup = ops.dda_forward(m._dda_pack("building_extractor"), x, m.p2d, ops.PC_DDA_BUILTUP)
             feats = ops.dda_forward(m._dda_pack("unetmodel"), x, (0, 0, 0, 0), ops.PC_DDA_FEATURES)
             bu = builtup if m.occupancymodel else None
-            dens, scale = ops.head_dense_forward(m._head_pack(), feats, bu, None, None, None,
-                                                 want_scale=self.want_scale and m.occupancymodel)
+            tc = popcorn_mod.USE_TENSOR_CORE_HEAD
+            dens, scale = ops.head_dense_forward(m._head_pack(tc=tc), feats, bu, None, None, None,
+                                                 want_scale=self.want_scale and m.occupancymodel, tc=tc)
             ops.accumulate_tile(dens[0], None if scale is None else scale[0], (ov, win.h - ov), (ov, win.w - ov),
                                 self._maps, win.y0 - lo, win.x0)
             del feats, dens, scale

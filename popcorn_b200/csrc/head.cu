@@ -2,27 +2,9 @@
 // activations held in shared memory, ReLU, x builtup, store / scatter, census partial sums.
 // Replaces model/popcorn.py:79-88 (head), :160-190 (relu, x building_counts, region sum) and
 // :195-228 (sparse_module_forward gather / scatter).
-#include "common.cuh"
+#include "head_common.cuh"
 
 namespace pc {
-
-constexpr int HM = 256;   // pixels per CTA tile
-constexpr int HN = 64;    // hidden width
-
-__host__ __device__ constexpr int head_pack_floats(int K1) { return K1 * HN + HN + 2 * (HN * HN + HN) + HN + 4; }
-
-struct HeadArgs {
-    const float* pack;
-    const float* feats; long long f_bs, f_cs; int f_rs;
-    const float* builtup; long long bu_bs; int bu_rs;
-    int B, H, W;
-    float* dens; float* scale; long long o_bs; int o_rs;
-    const int32_t* ids; long long id_bs; int id_rs;
-    const int32_t* census_idx;
-    double* sums; int R;
-    // sparse
-    const int32_t* idx; const int32_t* n_dev; long long HW; float* scale_sel;
-};
 
 // one dense layer on the CTA's tile: act[k][m] (k < K) -> act[n][m] (n < 64), in place.
 // thread (lane, warp): pixels {4*lane..+3} and {128+4*lane..+3}, outputs n = 8*warp..+7.
@@ -58,18 +40,6 @@ __device__ __forceinline__ void mlp_layer(float* act, const float* Wt, const flo
             make_float4(fmaxf(acc[4][j], 0.f), fmaxf(acc[5][j], 0.f), fmaxf(acc[6][j], 0.f), fmaxf(acc[7][j], 0.f));
     }
     __syncthreads();
-}
-
-// warp-aggregated census partial sum: one fp64 atomic per warp when the whole warp shares a bin
-__device__ __forceinline__ void bin_add(double* sums, int bin, float v) {
-    int same;
-    __match_all_sync(0xffffffffu, bin, &same);
-    if (same) {
-        const float s = warp_sum(v);
-        if ((threadIdx.x & 31) == 0 && bin >= 0) atomicAdd(sums + bin, (double)s);
-    } else if (bin >= 0) {
-        atomicAdd(sums + bin, (double)v);
-    }
 }
 
 template <int K1, bool SPARSE>

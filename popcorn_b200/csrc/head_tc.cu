@@ -1,0 +1,293 @@
+// Occupancy head on the 5th-gen tensor cores (tcgen05 + TMEM), error-compensated 3xTF32.
+//
+// Per 128-pixel tile (UMMA M = 128, N = 64, cta_group::1):
+//   * the 128 threads each own one pixel = one TMEM lane;
+//   * activations are the A operand and LIVE IN TMEM: the epilogue reads the fp32 accumulator D with
+//     tcgen05.ld, applies bias + ReLU, splits x = hi + lo (hi = top 19 bits, exactly a TF32 number) and
+//     writes both halves back with tcgen05.st — they never touch shared or global memory;
+//   * weights are the B operand in shared memory, pre-split (hi/lo) and pre-swizzled on the host into the
+//     canonical K-major SWIZZLE_128B layout, copied in verbatim once per CTA;
+//   * every 8-wide k-step issues three tcgen05.mma.kind::tf32 (hi*hi + lo*hi + hi*lo) into the same fp32
+//     accumulator: ~21-bit operands, which is what the per-pixel 1e-2 bar needs;
+//   * the 64->1 output layer, ReLU, x builtup, stores and the census partial sums run in the last epilogue.
+// Two CTAs per SM (256 TMEM columns, 84 KB smem each) overlap one tile's epilogue with the other's MMAs.
+// Replaces model/popcorn.py:79-88, 160-190, 195-228 (same contract as head.cu's SIMT kernel).
+#include "head_common.cuh"
+
+namespace pc {
+
+constexpr int TM = 128;
+// instruction descriptor, kind::tf32: D=f32 (bits 4-5 = 1), A=B=tf32 (bits 7-9, 10-12 = 2), K-major A and B,
+// N>>3 at bits 17-22, M>>4 at bits 24-28   (cute/arch/mma_sm100_desc.hpp InstrDescriptor)
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+
+// byte offsets inside the packed TC weight image (host: weights.pack_head_tc)
+constexpr int OFF_W1HI = 0, OFF_W1LO = 8192, OFF_W2HI = 16384, OFF_W2LO = 32768, OFF_W3HI = 49152, OFF_W3LO = 65536;
+constexpr int OFF_VEC = 81920;                 // b1[64] b2[64] b3[64] w4[64] b4[4]
+constexpr int TC_PACK_BYTES = OFF_VEC + 260 * 4;
+constexpr int OFF_MBAR = TC_PACK_BYTES;        // 8-byte mbarrier
+constexpr int OFF_TMEM = OFF_MBAR + 8;         // 4-byte TMEM base address slot
+constexpr int TC_SMEM_BYTES = OFF_TMEM + 8 + 1024;   // + slack to align the base to 1024 B
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+// start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major, 1) | SBO>>4 [32,46) = 1024 B between 8-row groups |
+// version 1 [46,48) | layout SWIZZLE_128B = 2 [61,64)
+__device__ __forceinline__ uint64_t make_bdesc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}\n"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(IDESC), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t mbar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                   "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+
+// bounded spin on an mbarrier phase: a descriptor mistake must trap, never hang the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    for (uint32_t spin = 0;; ++spin) {
+        uint32_t done;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(mbar), "r"(parity)
+                     : "memory");
+        if (done) return;
+        if (spin > (1u << 26)) __trap();
+    }
+}
+
+// x = hi + lo with hi exactly representable in TF32 (low 13 mantissa bits cleared)
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(x) & 0xFFFFE000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+// one hidden layer's UMMAs: D[128x64] = A[128xK] * W[64xK]^T, K in steps of 8, three split terms per step
+template <int K>
+__device__ __forceinline__ void issue_layer(uint32_t tD, uint32_t tAhi, uint32_t tAlo, uint32_t sWhi, uint32_t sWlo,
+                                            uint32_t mbar) {
+#pragma unroll
+    for (int j = 0; j < K / 8; ++j) {
+        const uint32_t koff = (uint32_t)((j >> 2) * 8192 + (j & 3) * 32);   // 32-float swizzle atoms along K
+        const uint64_t bhi = make_bdesc(sWhi + koff), blo = make_bdesc(sWlo + koff);
+        umma_tf32_ts(tD, tAhi + 8 * j, bhi, j > 0 ? 1u : 0u);
+        umma_tf32_ts(tD, tAlo + 8 * j, bhi, 1u);
+        umma_tf32_ts(tD, tAhi + 8 * j, blo, 1u);
+    }
+    umma_commit(mbar);
+}
+
+// hidden-layer epilogue: D -> relu(D + bias) -> (hi, lo) -> A operand of the next layer (all in TMEM)
+__device__ __forceinline__ void epilogue_hidden(uint32_t tD, uint32_t tAhi, uint32_t tAlo, const float* bias) {
+#pragma unroll 1
+    for (int c = 0; c < HN; c += 16) {
+        uint32_t v[16], hi[16], lo[16];
+        tmem_ld16(tD + c, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) split_tf32(fmaxf(__uint_as_float(v[i]) + bias[c + i], 0.f), hi[i], lo[i]);
+        tmem_st16(tAhi + c, hi);
+        tmem_st16(tAlo + c, lo);
+    }
+}
+
+template <int K1, bool SPARSE>
+__global__ void __launch_bounds__(TM, 2) head_tc_kernel(const __grid_constant__ HeadArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const float* vec = reinterpret_cast<const float*>(sm + OFF_VEC);
+    const float* b1 = vec, *b2 = vec + 64, *b3 = vec + 128, *w4 = vec + 192, *b4 = vec + 256;
+    const uint32_t mbar = smem_u32(sm + OFF_MBAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + OFF_TMEM);
+    const int tid = threadIdx.x, warp = tid >> 5;
+
+    for (int i = tid; i < TC_PACK_BYTES / 16; i += TM)
+        reinterpret_cast<int4*>(sm)[i] = __ldg(reinterpret_cast<const int4*>(a.pack) + i);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // weight image (generic stores) -> visible to UMMA
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;          // this warp's 32 TMEM lanes
+    const uint32_t tD = tbase, tAhi = tbase + 64, tAlo = tbase + 128;  // column offsets inside the 256-col block
+    const uint32_t sW = smem_u32(sm);
+    uint32_t phase = 0;
+
+    const long long HW = SPARSE ? a.HW : (long long)a.H * a.W;
+    const long long total = SPARSE ? (long long)__ldg(a.n_dev) : HW * a.B;
+
+    for (long long base = (long long)blockIdx.x * TM; base < total; base += (long long)gridDim.x * TM) {
+        const long long i = base + tid;
+        const bool valid = i < total;
+        long long p = 0; int b = 0; long long foff = 0, boff = 0, ooff = 0, ioff = 0;
+        if (valid) {
+            p = SPARSE ? (long long)__ldg(a.idx + i) : i;
+            b = (int)(p / HW);
+            const long long q = p - (long long)b * HW;
+            if (SPARSE) {
+                foff = b * a.f_bs + q; boff = p; ooff = p;
+            } else {
+                const int y = (int)(q / a.W), x = (int)(q - (long long)y * a.W);
+                foff = b * a.f_bs + (long long)y * a.f_rs + x;
+                boff = b * a.bu_bs + (long long)y * a.bu_rs + x;
+                ooff = b * a.o_bs + (long long)y * a.o_rs + x;
+                ioff = b * a.id_bs + (long long)y * a.id_rs + x;
+            }
+        }
+        // ---- layer-1 A operand: this pixel's K1 features, split, into TMEM ----
+#pragma unroll
+        for (int c0 = 0; c0 < K1; c0 += 8) {
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float f = valid ? __ldg(a.feats + foff + (long long)(c0 + c) * a.f_cs) : 0.f;
+                split_tf32(f, hi[c], lo[c]);
+            }
+            tmem_st8(tAhi + lane_off + c0, hi);
+            tmem_st8(tAlo + lane_off + c0, lo);
+        }
+        tc_wait_st();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) { tc_fence_after(); issue_layer<K1>(tD, tAhi, tAlo, sW + OFF_W1HI, sW + OFF_W1LO, mbar); }
+        mbar_wait(mbar, phase); phase ^= 1;
+        tc_fence_after();
+        epilogue_hidden(tD + lane_off, tAhi + lane_off, tAlo + lane_off, b1);
+        tc_wait_st();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) { tc_fence_after(); issue_layer<HN>(tD, tAhi, tAlo, sW + OFF_W2HI, sW + OFF_W2LO, mbar); }
+        mbar_wait(mbar, phase); phase ^= 1;
+        tc_fence_after();
+        epilogue_hidden(tD + lane_off, tAhi + lane_off, tAlo + lane_off, b2);
+        tc_wait_st();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) { tc_fence_after(); issue_layer<HN>(tD, tAhi, tAlo, sW + OFF_W3HI, sW + OFF_W3LO, mbar); }
+        mbar_wait(mbar, phase); phase ^= 1;
+        tc_fence_after();
+        // ---- output layer on the CUDA cores: o = b4 + sum_n relu(D3[n] + b3[n]) * w4[n] ----
+        float o = b4[0];
+#pragma unroll 1
+        for (int c = 0; c < HN; c += 16) {
+            uint32_t v[16];
+            tmem_ld16(tD + lane_off + c, v);
+            tc_wait_ld();
+#pragma unroll
+            for (int k = 0; k < 16; ++k) o = fmaf(fmaxf(__uint_as_float(v[k]) + b3[c + k], 0.f), w4[c + k], o);
+        }
+        tc_fence_before();   // D is overwritten by the next tile's first UMMA after the next __syncthreads
+        const float s = fmaxf(o, 0.f);
+        float d = 0.f; int bin = -1;
+        if (valid) {
+            d = a.builtup ? s * __ldg(a.builtup + boff) : s;
+            a.dens[ooff] = d;
+            if (SPARSE) { if (a.scale_sel) a.scale_sel[i] = s; }
+            else if (a.scale) a.scale[ooff] = s;
+            if (a.sums) {
+                if (SPARSE) bin = b;
+                else if (a.census_idx) bin = (a.ids == nullptr || __ldg(a.ids + ioff) == __ldg(a.census_idx + b)) ? b : -1;
+                else if (a.ids) { const int id = __ldg(a.ids + ioff); bin = (id >= 0 && id < a.R) ? id : -1; }
+                else bin = b;
+            }
+        }
+        if (a.sums) bin_add(a.sums, bin, d);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(256) : "memory");
+}
+
+template <int K1, bool SPARSE>
+static int launch_head_tc(const HeadArgs& a, long long total_bound, cudaStream_t st) {
+    auto k = head_tc_kernel<K1, SPARSE>;
+    PC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    long long tiles = (total_bound + TM - 1) / TM;
+    const int maxg = num_sms() * 2;          // persistent: 2 CTAs per SM, each walks tiles grid-stride
+    int grid = (int)(tiles < maxg ? tiles : maxg);
+    if (grid < 1) grid = 1;
+    k<<<grid, TM, TC_SMEM_BYTES, st>>>(a);
+    PC_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace pc
+
+using namespace pc;
+
+extern "C" int pc_head_tc_pack_bytes(void) { return TC_PACK_BYTES; }
+
+extern "C" int pc_head_dense_forward_tc(const void* tcpack, int head_in, const float* feats, long long f_bstride,
+                                        long long f_cstride, int f_rstride, const float* builtup, long long bu_bstride,
+                                        int bu_rstride, int B, int H, int W, float* dens, float* scale,
+                                        long long o_bstride, int o_rstride, const int32_t* ids, long long id_bstride,
+                                        int id_rstride, const int32_t* census_idx, double* sums, int R,
+                                        pc_stream_t stream) {
+    PC_CHECK_ARG(tcpack && feats && dens, "null pointer");
+    PC_CHECK_ARG((((uintptr_t)tcpack) & 15) == 0, "tc pack must be 16-byte aligned");
+    PC_CHECK_ARG(head_in == 16 || head_in == 8, "head_in must be 16 or 8");
+    PC_CHECK_ARG(B >= 1 && H >= 1 && W >= 1, "bad shape");
+    PC_CHECK_ARG(!(ids && !census_idx && sums) || R >= 1, "R must be >= 1 with an id raster");
+    HeadArgs a{};
+    a.pack = reinterpret_cast<const float*>(tcpack); a.feats = feats; a.f_bs = f_bstride; a.f_cs = f_cstride; a.f_rs = f_rstride;
+    a.builtup = builtup; a.bu_bs = bu_bstride; a.bu_rs = bu_rstride; a.B = B; a.H = H; a.W = W;
+    a.dens = dens; a.scale = scale; a.o_bs = o_bstride; a.o_rs = o_rstride;
+    a.ids = ids; a.id_bs = id_bstride; a.id_rs = id_rstride; a.census_idx = census_idx; a.sums = sums; a.R = R;
+    const long long total = (long long)B * H * W;
+    return head_in == 16 ? launch_head_tc<16, false>(a, total, (cudaStream_t)stream)
+                         : launch_head_tc<8, false>(a, total, (cudaStream_t)stream);
+}
+
+extern "C" int pc_head_sparse_forward_tc(const void* tcpack, int head_in, const float* feats, long long f_bstride,
+                                         long long f_cstride, const float* builtup, const int32_t* idx,
+                                         const int32_t* n_dev, long long n_max, long long HW, float* dens,
+                                         float* scale_sel, double* popcount, pc_stream_t stream) {
+    PC_CHECK_ARG(tcpack && feats && idx && n_dev && dens, "null pointer");
+    PC_CHECK_ARG((((uintptr_t)tcpack) & 15) == 0, "tc pack must be 16-byte aligned");
+    PC_CHECK_ARG(head_in == 16 || head_in == 8, "head_in must be 16 or 8");
+    PC_CHECK_ARG(HW >= 1 && n_max >= 0, "bad shape");
+    HeadArgs a{};
+    a.pack = reinterpret_cast<const float*>(tcpack); a.feats = feats; a.f_bs = f_bstride; a.f_cs = f_cstride; a.builtup = builtup;
+    a.dens = dens; a.scale_sel = scale_sel; a.sums = popcount; a.idx = idx; a.n_dev = n_dev; a.HW = HW;
+    a.B = 1; a.H = 1; a.W = 1;
+    return head_in == 16 ? launch_head_tc<16, true>(a, n_max, (cudaStream_t)stream)
+                         : launch_head_tc<8, true>(a, n_max, (cudaStream_t)stream);
+}

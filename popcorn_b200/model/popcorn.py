@@ -8,6 +8,7 @@ memory, streams and autograd bookkeeping.  There is no CPU path: CPU tensors rai
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import torch
@@ -15,6 +16,9 @@ import torch.nn as nn
 
 from .. import ops, weights
 from .dda import STAGE1_FEATS, load_checkpoint
+
+# forward head on tcgen05 (3xTF32, csrc/head_tc.cu) unless POPCORN_HEAD_TC=0 selects the fp32 SIMT kernel (csrc/head.cu)
+USE_TENSOR_CORE_HEAD = os.environ.get("POPCORN_HEAD_TC", "1") != "0"
 
 
 class _SparseHeadFn(torch.autograd.Function):
@@ -25,8 +29,11 @@ class _SparseHeadFn(torch.autograd.Function):
     def forward(ctx, feats, builtup, idx, n_dev, n, head_in, *params):
         sd = {f"head.{i}.{t}": p for (i, t), p in zip(((0, "weight"), (0, "bias"), (2, "weight"), (2, "bias"),
                                                       (4, "weight"), (4, "bias"), (6, "weight"), (6, "bias")), params)}
-        hpack = weights.pack_head(sd)
-        dens, scale_sel, pop = ops.head_sparse_forward(hpack, feats, builtup, idx, n_dev, n)
+        hpack = weights.pack_head(sd)                      # fp32 pack: used by the backward's recompute
+        if USE_TENSOR_CORE_HEAD:
+            dens, scale_sel, pop = ops.head_sparse_forward(weights.pack_head_tc(sd), feats, builtup, idx, n_dev, n, tc=True)
+        else:
+            dens, scale_sel, pop = ops.head_sparse_forward(hpack, feats, builtup, idx, n_dev, n)
         ctx.save_for_backward(hpack, feats, builtup if builtup is not None else torch.empty(0, device=feats.device),
                               idx, n_dev)
         ctx.n, ctx.head_in, ctx.has_bu = n, head_in, builtup is not None
@@ -130,15 +137,17 @@ class POPCORN(nn.Module):
     def _head_params(self):
         return tuple(getattr(self.head[i], t) for i in (0, 2, 4, 6) for t in ("weight", "bias"))
 
-    def _head_pack(self) -> torch.Tensor:
+    def _head_pack(self, tc: bool = False) -> torch.Tensor:
         ps = self._head_params()
         sig = tuple((t.data_ptr(), t._version) for t in ps)
-        hit = self._pack_cache.get("head")
+        key = "head_tc" if tc else "head"
+        hit = self._pack_cache.get(key)
         if hit is not None and hit[0] == sig:
             return hit[1]
         with torch.no_grad():
-            pack = weights.pack_head({f"head.{i}.{t}": getattr(self.head[i], t) for i in (0, 2, 4, 6) for t in ("weight", "bias")})
-        self._pack_cache["head"] = (sig, pack)
+            sd = {f"head.{i}.{t}": getattr(self.head[i], t) for i in (0, 2, 4, 6) for t in ("weight", "bias")}
+            pack = weights.pack_head_tc(sd) if tc else weights.pack_head(sd)
+        self._pack_cache[key] = (sig, pack)
         return pack
 
     # ------------------------------------------------------------------------------------------
@@ -253,7 +262,7 @@ class POPCORN(nn.Module):
             else:
                 popcount = pop_sel
         else:
-            hpack = self._head_pack()
+            hpack = self._head_pack(tc=USE_TENSOR_CORE_HEAD)
             sums = torch.zeros(B, dtype=torch.float64, device=X.device)
             ids = cidx = None
             if has_admin:
@@ -261,7 +270,8 @@ class POPCORN(nn.Module):
                 cidx = inputs["census_idx"].to(device=X.device, dtype=torch.int32).contiguous()
             else:
                 cidx = torch.zeros(B, dtype=torch.int32, device=X.device)   # bin = batch index, all pixels
-            dens, scale = ops.head_dense_forward(hpack, feats, bu, ids, cidx, sums, want_scale=self.occupancymodel)
+            dens, scale = ops.head_dense_forward(hpack, feats, bu, ids, cidx, sums, want_scale=self.occupancymodel,
+                                                 tc=USE_TENSOR_CORE_HEAD)
             popdensemap = dens
             aux["scale"] = scale if self.occupancymodel else None
             popcount = sums.float()

@@ -64,10 +64,12 @@ def dda_forward(wpack: torch.Tensor, x: torch.Tensor, pads=(0, 0, 0, 0), mode: i
     return out
 
 
-def head_dense_forward(hpack, feats, builtup, ids=None, census_idx=None, sums=None, want_scale=True):
-    """feats [B,Cin,H,W], builtup [B,1,H,W]|None -> (dens [B,H,W], scale [B,H,W]|None); sums (float64) updated in place."""
+def head_dense_forward(hpack, feats, builtup, ids=None, census_idx=None, sums=None, want_scale=True, tc=False):
+    """feats [B,Cin,H,W], builtup [B,1,H,W]|None -> (dens [B,H,W], scale [B,H,W]|None); sums (float64) updated in place.
+    tc=True: `hpack` is the tcgen05 weight image (weights.pack_head_tc) and the tensor-core kernel runs."""
     _need_cuda(hpack, feats, builtup, ids, census_idx, sums)
     L = _lib.lib()
+    fn = L.pc_head_dense_forward_tc if tc else L.pc_head_dense_forward
     B, Cin, H, W = feats.shape
     assert feats.stride(3) == 1 and feats.dtype == torch.float32
     dens = torch.empty(B, H, W, dtype=torch.float32, device=feats.device)
@@ -81,7 +83,7 @@ def head_dense_forward(hpack, feats, builtup, ids=None, census_idx=None, sums=No
     R = 0 if sums is None else sums.numel()
     if sums is not None:
         assert sums.dtype == torch.float64 and sums.is_contiguous()
-    _lib.check(L.pc_head_dense_forward(
+    _lib.check(fn(
         hpack.data_ptr(), Cin, feats.data_ptr(), feats.stride(0), feats.stride(1), feats.stride(2),
         _ptr(builtup), 0 if builtup is None else builtup.stride(0), 0 if builtup is None else builtup.stride(-2),
         B, H, W, dens.data_ptr(), _ptr(scale), dens.stride(0), dens.stride(1),
@@ -110,17 +112,18 @@ def sparse_mask_compact(builtup, admin, census_idx, grid_rows, grid_cols, use_bu
     return mask, idx, n
 
 
-def head_sparse_forward(hpack, feats, builtup, idx, n_dev, n_max):
+def head_sparse_forward(hpack, feats, builtup, idx, n_dev, n_max, tc=False):
     """-> (dens [B,H,W] scattered, scale_sel [n_max] (first n valid), popcount float64 [B])."""
     _need_cuda(hpack, feats, builtup, idx, n_dev)
     L = _lib.lib()
+    fn = L.pc_head_sparse_forward_tc if tc else L.pc_head_sparse_forward
     B, Cin, H, W = feats.shape
     assert feats.is_contiguous() and feats.dtype == torch.float32
     bu = None if builtup is None else builtup.float().contiguous()
     dens = torch.zeros(B, H, W, dtype=torch.float32, device=feats.device)
     scale_sel = torch.empty(max(int(n_max), 1), dtype=torch.float32, device=feats.device)
     pop = torch.zeros(B, dtype=torch.float64, device=feats.device)
-    _lib.check(L.pc_head_sparse_forward(hpack.data_ptr(), Cin, feats.data_ptr(), feats.stride(0), feats.stride(1),
+    _lib.check(fn(hpack.data_ptr(), Cin, feats.data_ptr(), feats.stride(0), feats.stride(1),
                                         _ptr(bu), idx.data_ptr(), n_dev.data_ptr(), int(n_max), H * W, dens.data_ptr(),
                                         scale_sel.data_ptr(), pop.data_ptr(), _stream()), "pc_head_sparse_forward")
     return dens, scale_sel, pop

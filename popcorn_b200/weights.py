@@ -89,3 +89,46 @@ def unpack_head_grad(gpack: torch.Tensor, head_in: int) -> Dict[str, torch.Tenso
     b6[0] = gpack[o]
     out["head.6.weight"], out["head.6.bias"] = w6, b6
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# tcgen05 head: weights pre-split (3xTF32) and pre-swizzled into the UMMA K-major SWIZZLE_128B layout
+# ---------------------------------------------------------------------------------------------------
+def _split_tf32(w: torch.Tensor):
+    """w = hi + lo, hi exactly representable in TF32 (low 13 mantissa bits cleared), lo = w - hi (exact in fp32)."""
+    hi = (w.contiguous().view(torch.int32) & -8192).view(torch.float32)     # -8192 == 0xFFFFE000
+    return hi, w - hi
+
+
+def _swizzle_k_major_128b(w: torch.Tensor) -> torch.Tensor:
+    """[N=64, K] fp32 -> flat image [ceil(K/32)][64 rows][32 floats]: row n of a 32-float K-atom is 128 B, its eight
+    16-byte chunks XOR-swizzled with (n % 8) (Swizzle<3,4,3>); 8-row groups are 1024 B apart (the descriptor's SBO)."""
+    N, K = w.shape
+    assert N == 64
+    katoms = (K + 31) // 32
+    wp = torch.zeros(N, katoms * 32, dtype=w.dtype, device=w.device)
+    wp[:, :K] = w
+    n = torch.arange(N, device=w.device).view(N, 1)
+    k = torch.arange(katoms * 32, device=w.device).view(1, -1)
+    kk = k % 32
+    pos = (((kk // 4) ^ (n % 8)) * 4 + kk % 4)
+    dst = (k // 32) * (N * 32) + n * 32 + pos
+    out = torch.zeros(katoms * N * 32, dtype=w.dtype, device=w.device)
+    out[dst.reshape(-1)] = wp.reshape(-1)
+    return out
+
+
+def pack_head_tc(sd: Dict[str, torch.Tensor]) -> torch.Tensor:
+    """Weight image of csrc/head_tc.cu (byte offsets OFF_* there): W1hi W1lo (8 KB each, K padded to 32), W2hi W2lo
+    W3hi W3lo (16 KB each), then b1 b2 b3 w4 (64 floats each) and b4 (+3 pad).  float32 tensor of 20 740 elements."""
+    parts = []
+    for i in (0, 2, 4):
+        w = sd[f"head.{i}.weight"].detach().float().flatten(1)             # [64 out, K in]  == UMMA B operand, K-major
+        hi, lo = _split_tf32(w)
+        parts += [_swizzle_k_major_128b(hi), _swizzle_k_major_128b(lo)]
+    parts += [sd[f"head.{i}.bias"].detach().float() for i in (0, 2, 4)]
+    parts += [sd["head.6.weight"].detach().float().flatten(1)[0], sd["head.6.bias"].detach().float()[0:1],
+              torch.zeros(3, dtype=torch.float32, device=parts[0].device)]
+    out = torch.cat(parts).contiguous()
+    assert out.numel() * 4 == 82960, out.numel()
+    return out

@@ -52,7 +52,7 @@ def test_merged_strips_are_bit_identical_to_reference_tiles(model):
     for o in outs[1:]:
         assert torch.equal(o["map"], outs[0]["map"])
         assert torch.equal(o["count"], outs[0]["count"])
-        assert torch.allclose(o["sums"], outs[0]["sums"], rtol=1e-9)
+        assert torch.allclose(o["sums"], outs[0]["sums"], rtol=1e-6)   # per-CTA fp32 bins: atomic order varies
 
 
 def test_rank_sharded_partials_sum_to_the_single_gpu_result(model):

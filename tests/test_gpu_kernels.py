@@ -168,3 +168,31 @@ def test_accumulate_and_finalize_match_run_eval_arithmetic():
     assert torch.equal(maps[4].cpu(), ref[4]) and int(div.sum()) > 0
     for a, b in zip(maps[:4], ref[:4]):
         assert torch.allclose(a.cpu(), b, rtol=1e-5, atol=1e-5, equal_nan=True)
+
+
+@pytest.mark.parametrize("head_in", [16, 8])
+@pytest.mark.parametrize("B,H,W", [(1, 64, 96), (2, 37, 53), (1, 300, 517)])
+def test_head_tensor_core_matches_simt_and_oracle(head_in, B, H, W):
+    """tcgen05 3xTF32 head (activations in TMEM) vs the fp32 SIMT head and the torch fp32 MLP."""
+    from popcorn_b200 import weights
+    g = torch.Generator().manual_seed(H + head_in)
+    sd = po.random_state_dict(seed=3, head_in=head_in)
+    feats = (torch.randn(B, head_in, H, W, generator=g) * 3.0)
+    bu = torch.rand(B, 1, H, W, generator=g)
+    ids = torch.randint(0, 5, (B, H, W), generator=g).to(torch.int32)
+    ref_out = po.head_mlp(sd, feats.permute(0, 2, 3, 1).reshape(-1, head_in)).view(B, H, W, 2)[..., 0]
+    ref_scale = F.relu(ref_out)
+    ref_dens = ref_scale * bu[:, 0]
+    outs = {}
+    for tc in (False, True):
+        pack = (weights.pack_head_tc(sd) if tc else weights.pack_head(sd)).cuda()
+        sums = torch.zeros(5, dtype=torch.float64, device="cuda")
+        dens, scale = ops.head_dense_forward(pack, feats.cuda(), bu.cuda(), ids.cuda(), None, sums, tc=tc)
+        torch.cuda.synchronize()
+        outs[tc] = (dens.cpu(), scale.cpu(), sums.cpu())
+        err = ((scale.cpu() - ref_scale).abs() / ref_scale.abs().clamp(min=1e-3 * float(ref_scale.abs().max()))).max()
+        assert float(err) < 1e-4, (tc, float(err))
+        assert torch.allclose(dens.cpu(), ref_dens, rtol=1e-4, atol=1e-4 * float(ref_dens.abs().max()))
+        ref_sums = torch.zeros(5, dtype=torch.float64).index_add_(0, ids.reshape(-1).long(), ref_dens.reshape(-1).double())
+        assert torch.allclose(sums.cpu(), ref_sums, rtol=1e-5)
+    assert torch.allclose(outs[True][0], outs[False][0], rtol=1e-4, atol=1e-4 * float(ref_dens.abs().max()))

@@ -45,6 +45,11 @@ def main():
     res["head_dense_ms"] = ms
     res["head_dense_tflops"] = 18688 * H * W / ms / 1e9
     res["head_dense_gbs"] = 80 * H * W / ms / 1e6
+    hp_tc = weights.pack_head_tc(sd).cuda()
+    ms = timeit(lambda: ops.head_dense_forward(hp_tc, feats, bu, ids, None, sums, tc=True))
+    res["head_tc_ms"] = ms
+    res["head_tc_tflops"] = 18688 * H * W / ms / 1e9
+    res["head_tc_gbs"] = 80 * H * W / ms / 1e6
     n = 1 << 28
     d = torch.rand(n, device="cuda")
     big_ids = po.synthetic_regions(16384, 16384, 400).cuda().reshape(-1).contiguous()

@@ -83,6 +83,61 @@ def synth_ids_slab(H: int, W: int, R: int, lo: int, hi: int, device, seed: int =
     return full
 
 
+
+# per-kernel algorithmic work: FLOP and HBM bytes per processed pixel of that launch
+def _conv_work(name):
+    ca, cb, co, epi = name[len("conv3x3<"):-1].split(",")
+    cin, co = int(ca) + int(cb), int(co)
+    flop = 2 * 9 * cin * co
+    out_b = {"store": co * 4, "pool": co * 4 + co, "dot": 4 + 4}[epi]
+    return flop, cin * 4 + out_b
+
+
+# dram bytes per processed pixel measured by `ncu --set full` (profiles/r1_hot_kernels.md); None = not captured
+NCU_TRAFFIC_PER_PX = {"conv3x3<8,8,8,store>": 94.3, "conv3x3<8,0,8,pool>": 69.1, "conv3x3<8,0,8,store>": 61.5,
+                      "conv3x3<16,0,16,pool>": 133.0, "conv3x3<16,16,8,store>": 156.7, "head_simt": 14.9}
+
+
+def kernel_table(prof, ms_total, hbm_peak, tensor_peak):
+    rows = []
+    for name, (ms, n, units) in prof.items():
+        if ms <= 0:
+            continue
+        if name.startswith("conv3x3<"):
+            flop, byts = _conv_work(name)
+            bound, note = "hbm" if flop / byts < 11 else "tensor", "fp32 FFMA2 stencil (no tensor cores: N<=16, see DESIGN.md §3); " \
+                "compare `tflops` with fp32_simt.peak_tflops_measured_ffma2"
+        elif name.startswith("convt2x2<"):
+            c = int(name[len("convt2x2<"):-1])
+            flop, byts, bound, note = 8 * c * c, 5 * c * 4, "hbm", "units = low-res pixels"
+        elif name.startswith("head_tc"):
+            flop, byts, bound = FLOP_PER_PX_HEAD, BYTES_PER_PX_HEAD, "tensor"
+            note = "tcgen05 kind::tf32 with 3xTF32 splitting: 3 MMAs per algorithmic MAC at half the bf16 rate -> ceiling = peak/6"
+        elif name.startswith("head_forward_simt"):
+            flop, byts, bound, note = FLOP_PER_PX_HEAD, BYTES_PER_PX_HEAD, "tensor", "fp32 SIMT head"
+        elif name == "region_sum":
+            flop, byts, bound, note = 1, 8, "hbm", "dens + id read once"
+        elif name == "accumulate":
+            flop, byts, bound, note = 4, 8 + 4 * 8 + 4, "hbm", "tile dens+scale read, 4 maps + count read-modify-write"
+        elif name == "finalize":
+            flop, byts, bound, note = 10, 4 * 8 + 2, "hbm", "4 maps read+write, count read"
+        else:
+            flop, byts, bound, note = 0, 0, "hbm", ""
+        sec = ms * 1e-3
+        tfl = flop * units / sec / 1e12
+        gbs = byts * units / sec / 1e9
+        if bound == "hbm":
+            ach, peak, unit = gbs, hbm_peak, "GB/s"
+        else:
+            ach, peak, unit = tfl, tensor_peak, "TFLOP/s"
+        tpp = NCU_TRAFFIC_PER_PX.get(name)
+        rows.append({"kernel": name, "ms": ms, "launches": n, "pixels": units, "share_of_step": ms / ms_total if ms_total else None,
+                     "tflops": tfl, "gbs": gbs, "bound": bound, "achieved": ach, "peak": peak, "unit": unit,
+                     "frac": ach / peak if peak else None,
+                     "traffic": None if tpp is None else tpp * units / n, "note": note})
+    rows.sort(key=lambda r: -r["ms"])
+    return rows
+
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -288,24 +343,11 @@ def main():
         with torch.no_grad():
             return eng.run(raster, ids, R, row_offset=i0)
 
-    # phase events inside the timed region (cheap): per-call durations of the dominant kernel (the head launch)
-    prof = {"head": [], "head_px": 0}
-    orig_head = ops.head_dense_forward
-
-    def timed_head(*a, **k):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        r = orig_head(*a, **k)
-        e1.record()
-        f = a[1]
-        prof["head"].append((e0, e1, f.shape[0] * f.shape[2] * f.shape[3]))
-        return r
-
     for _ in range(args.warmup):
         out = step_device()
     barrier()
     ops.launch_count(reset=True)
-    ops.head_dense_forward = timed_head
+    ops.profile_enable(True)        # CUDA events around every launch of the library, on the launch stream
     sampler = ClockSampler(local) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -314,8 +356,9 @@ def main():
     ev1.record()
     barrier()
     clocks = sampler.stop() if sampler else None
-    ops.head_dense_forward = orig_head
+    ops.profile_enable(False)
     launches = ops.launch_count(reset=True)
+    prof = ops.profile_results()
     ms_total = ev0.elapsed_time(ev1)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
@@ -325,21 +368,17 @@ def main():
     sums_check = float(out["sums"].sum().item())
     map_total = float(out["map"].double().sum().item())
 
-    head_ms = sum(a.elapsed_time(b) for a, b, _ in prof["head"])
-    head_px = sum(n for _, _, n in prof["head"])
-    head_calls = len(prof["head"])
     hbm_peak, bf16_peak, bf16_sust, peak_src = measured_peaks()
-    head_tflops = FLOP_PER_PX_HEAD * head_px / (head_ms * 1e-3) / 1e12 if head_ms else 0.0
-    roofline = {"kernel": "head_tc_kernel<16,dense> (tcgen05 kind::tf32, 3xTF32 split)" if pb.model.popcorn.USE_TENSOR_CORE_HEAD else "head_forward_kernel<16,dense>", "bound": "tensor", "achieved": head_tflops,
-                "peak": bf16_sust, "unit": "TFLOP/s", "frac": head_tflops / bf16_sust, "traffic": None,
-                "peak_source": f"{peak_src} bf16 cuBLAS sustained (MEASURED_PEAKS.json). The kernel needs ~fp32 operands: it issues "
-                               "3 TF32 MMAs per algorithmic MAC (TF32 = 1/2 the bf16 rate), so its tensor-pipe ceiling is peak/6; "
-                               "achieved counts algorithmic FLOP once",
-                "frac_of_3xtf32_ceiling": head_tflops / (bf16_sust / 6.0),
-                "launches": head_calls, "avg_launch_ms": head_ms / max(head_calls, 1),
-                "share_of_step": head_ms / (ms_total if ms_total else 1.0),
-                "algorithmic": {"flop_per_px": FLOP_PER_PX_HEAD, "bytes_per_px": BYTES_PER_PX_HEAD,
-                                "hbm_gbs": BYTES_PER_PX_HEAD * head_px / (head_ms * 1e-3) / 1e9 if head_ms else 0.0}}
+    kernels = kernel_table(prof, ms_total, hbm_peak, bf16_sust)
+    dom = max(kernels, key=lambda k: k["ms"]) if kernels else None
+    roofline = None
+    if dom is not None:
+        roofline = {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"],
+                    "unit": dom["unit"], "frac": dom["frac"], "traffic": dom.get("traffic"),
+                    "launches": dom["launches"], "avg_launch_ms": dom["ms"] / dom["launches"],
+                    "share_of_step": dom["share_of_step"], "note": dom["note"], "peak_source": peak_src}
+    head = next((k for k in kernels if k["kernel"].startswith("head_")), None)
+    head_tflops = head["tflops"] if head else 0.0
 
     # ---- end-to-end: pinned host raster in, pinned host map + sums out, copies inside the timed region ----
     e2e = None
@@ -399,7 +438,12 @@ def main():
         b.record()
         torch.cuda.synchronize()
         fp32_peak = 2 * 32 * iters * nthr / (a.elapsed_time(b) * 1e-3) / 1e12
-        fp32 = {"peak_tflops_measured_ffma2": fp32_peak, "head_frac": head_tflops / fp32_peak if fp32_peak else None}
+        conv_ms = sum(k["ms"] for k in kernels if k["kernel"].startswith("conv3x3"))
+        conv_fl = sum(k["tflops"] * k["ms"] for k in kernels if k["kernel"].startswith("conv3x3"))
+        fp32 = {"peak_tflops_measured_ffma2": fp32_peak,
+                "conv3x3_all_tflops": conv_fl / conv_ms if conv_ms else None,
+                "conv3x3_all_frac_of_fp32_peak": conv_fl / conv_ms / fp32_peak if conv_ms and fp32_peak else None,
+                "note": "register-resident FFMA2 loop (pc_test_fma_peak): the practical ceiling of the fp32 stencil kernels"}
         if world == 1 and not args.skip_cpu_baseline:
             dt, px = cpu_reference_tiles(2)
             cpu_base = {"value": px / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
@@ -415,7 +459,8 @@ def main():
                            "rows_per_strip": args.rows_per_strip, "ensemble": 1, "head": "dense",
                            "l2": "inputs (>=6 GB per GPU) far larger than the 126 MB L2; no flush needed",
                            "weights": "random-init DDA x2 + head (oracle.random_state_dict seed 1600)"},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "fp32_simt": fp32,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kernels,
+                "fp32_simt": fp32,
                 "cpu_baseline": cpu_base, "train_step": train,
                 "check": {"sum_of_region_sums": sums_check, "map_total": map_total}}
         print(json.dumps(line), flush=True)

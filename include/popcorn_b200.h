@@ -37,6 +37,14 @@ const char* pc_last_error(void);
 /* Number of kernels this library has launched in this process (all threads); reset != 0 zeroes it after reading.
  * bench.py reports it as "gpu_launches". */
 long long pc_launch_count(int reset);
+/* Optional per-kernel timing: while enabled, every launch of this library is bracketed by CUDA events on its own
+ * stream.  pc_profile_enable(1) resets and starts, (0) stops; pc_profile_get(cat) synchronises the events of
+ * category `cat` (0 <= cat < pc_profile_num(), named by pc_profile_name) and returns summed ms and launch count.
+ * bench.py uses it for the live `roofline` numbers. */
+int pc_profile_enable(int on);
+int pc_profile_num(void);
+const char* pc_profile_name(int cat);
+int pc_profile_get(int cat, double* ms, long long* launches, double* units); /* units = pixels processed */
 /* Strided window copy between a (pinned) host raster and device memory on `stream` (cudaMemcpy2DAsync);
  * kind 1 = host->device, 2 = device->host.  Replaces to_cuda_inplace (utils/utils.py:22) / the per-tile .cpu()
  * of run_eval.py:127-135 for row/column windows that are not contiguous in the raster. */

@@ -22,6 +22,10 @@ SIGNATURES = {
     "pc_version": (_i, []),
     "pc_last_error": (C.c_char_p, []),
     "pc_launch_count": (_ll, [_i]),
+    "pc_profile_enable": (_i, [_i]),
+    "pc_profile_num": (_i, []),
+    "pc_profile_name": (C.c_char_p, [_i]),
+    "pc_profile_get": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_double)]),
     "pc_memcpy2d_async": (_i, [_vp, _sz, _vp, _sz, _sz, _sz, _i, _vp]),
     "pc_dda_pack_floats": (_i, []),
     "pc_dda_pack_offset": (_i, [_i, _i]),

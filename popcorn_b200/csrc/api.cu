@@ -1,5 +1,7 @@
 // Library-level entry points: version, per-thread error text, device query cache.
 #include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -16,6 +18,41 @@ void set_error(const char* fmt, ...) {
 
 static long long g_launches = 0;
 void count_launch() { __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED); }
+
+// ---- per-kernel event profiler ------------------------------------------------------------------
+constexpr int PROF_MAX_CAT = 64, PROF_MAX_EV = 1 << 16;
+static char g_prof_names[PROF_MAX_CAT][64];
+static int g_prof_ncat = 0;
+static bool g_prof_on = false;
+static cudaEvent_t* g_prof_ev = nullptr;     // [2 * PROF_MAX_EV], created lazily
+static int g_prof_cat_of[PROF_MAX_EV];
+static double g_prof_units[PROF_MAX_EV];
+static int g_prof_used = 0, g_prof_created = 0;
+
+int prof_register(const char* name) {
+    for (int i = 0; i < g_prof_ncat; ++i)
+        if (strncmp(g_prof_names[i], name, 63) == 0) return i;
+    if (g_prof_ncat >= PROF_MAX_CAT) return PROF_MAX_CAT - 1;
+    strncpy(g_prof_names[g_prof_ncat], name, 63);
+    return g_prof_ncat++;
+}
+
+ProfScope::ProfScope(int cat, cudaStream_t stream, double units) : slot(-1), st(stream) {
+    if (!g_prof_on || g_prof_used >= PROF_MAX_EV) return;
+    if (!g_prof_ev) g_prof_ev = (cudaEvent_t*)calloc(2 * PROF_MAX_EV, sizeof(cudaEvent_t));
+    slot = g_prof_used++;
+    if (slot >= g_prof_created) {
+        cudaEventCreate(&g_prof_ev[2 * slot]);
+        cudaEventCreate(&g_prof_ev[2 * slot + 1]);
+        g_prof_created = slot + 1;
+    }
+    g_prof_cat_of[slot] = cat;
+    g_prof_units[slot] = units;
+    cudaEventRecord(g_prof_ev[2 * slot], st);
+}
+ProfScope::~ProfScope() {
+    if (slot >= 0) cudaEventRecord(g_prof_ev[2 * slot + 1], st);
+}
 
 int num_sms() {
     static int cached[64] = {0};
@@ -36,6 +73,26 @@ extern "C" long long pc_launch_count(int reset) {
     const long long v = __atomic_load_n(&pc::g_launches, __ATOMIC_RELAXED);
     if (reset) __atomic_store_n(&pc::g_launches, 0, __ATOMIC_RELAXED);
     return v;
+}
+extern "C" int pc_profile_enable(int on) {
+    pc::g_prof_on = on != 0;
+    if (on) pc::g_prof_used = 0;
+    return 0;
+}
+extern "C" int pc_profile_num(void) { return pc::g_prof_ncat; }
+extern "C" const char* pc_profile_name(int i) { return (i >= 0 && i < pc::g_prof_ncat) ? pc::g_prof_names[i] : ""; }
+extern "C" int pc_profile_get(int cat, double* ms, long long* launches, double* units) {
+    PC_CHECK_ARG(ms && launches && units, "null pointer");
+    double t = 0, u = 0; long long n = 0;
+    for (int s = 0; s < pc::g_prof_used; ++s) {
+        if (pc::g_prof_cat_of[s] != cat) continue;
+        PC_CUDA(cudaEventSynchronize(pc::g_prof_ev[2 * s + 1]));
+        float e = 0.f;
+        PC_CUDA(cudaEventElapsedTime(&e, pc::g_prof_ev[2 * s], pc::g_prof_ev[2 * s + 1]));
+        t += e; ++n; u += pc::g_prof_units[s];
+    }
+    *ms = t; *launches = n; *units = u;
+    return 0;
 }
 extern "C" int pc_memcpy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width_bytes,
                                  size_t rows, int kind, pc_stream_t stream) {

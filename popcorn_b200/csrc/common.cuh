@@ -11,6 +11,14 @@ namespace pc {
 void set_error(const char* fmt, ...);
 void count_launch();
 
+// optional per-kernel CUDA-event timing (pc_profile_*): a scope records start/stop events on the launch stream
+int prof_register(const char* name);
+struct ProfScope {
+    int slot; cudaStream_t st;
+    ProfScope(int cat, cudaStream_t stream, double units = 0.0);
+    ~ProfScope();
+};
+
 #define PC_CHECK_ARG(cond, msg)                           \
     do {                                                  \
         if (!(cond)) {                                    \

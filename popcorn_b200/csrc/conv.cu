@@ -9,6 +9,7 @@
 //
 // Replaces model/DDA_model/utils/networks.py:121-151 (UNet.forward), :253-330 (DoubleConv/Down/Up/
 // OutConv) and the padding / reorder / sigmoid / crop wrappers of model/popcorn.py:126-158, 279-322.
+#include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -18,7 +19,8 @@ namespace pc {
 
 constexpr int TILE = 32;            // output tile edge per CTA
 constexpr int SROWS = TILE + 2;     // staged rows (1-px halo)
-constexpr int SPITCH = 40;          // staged row pitch (floats): 34 used, 16B-aligned, 2nd LDS.128 in bounds
+constexpr int SPITCH = 40;          // staged row pitch (floats) = TMA box width (inner TMA coordinate must be 16-B aligned)
+constexpr int XOFF = 3;             // staged column of image column x0-1: the box starts at x0-4
 constexpr int MAX_JOBS = 8;
 
 enum { EPI_STORE = 0, EPI_POOL = 1, EPI_DOT = 2 };
@@ -36,7 +38,9 @@ struct ConvJob {
     float* dot_out; int dot_out_rs; int dot_final;
 };
 
-struct ConvParams {
+struct alignas(64) ConvParams {
+    CUtensorMap tmA[MAX_JOBS];           // TMA descriptors of the job's sources (TMA staging only)
+    CUtensorMap tmB[MAX_JOBS];
     int H, W;                            // virtual image == output extent
     int crop_y, crop_x, crop_H, crop_W;  // stores go to (y-crop_y, x-crop_x) if inside [0,crop_H)x[0,crop_W)
     ConvJob jobs[MAX_JOBS];
@@ -45,11 +49,36 @@ struct ConvParams {
 template <int CIN>
 __host__ __device__ constexpr int conv_cc() { return CIN < 4 ? CIN : 4; }       // channels per staged chunk
 
+template <int CIN, int COUT>
+__host__ __device__ constexpr int conv_wfloats_padded() { return (CIN * 9 * COUT + COUT + 31) / 32 * 32; }   // 128-B multiple
+
 template <int CIN, int COUT, int EPI>
 constexpr int conv_smem_floats() {
     constexpr int CC = conv_cc<CIN>();
     constexpr int NBUF = (CIN / CC) > 1 ? 2 : 1;
-    return CIN * 9 * COUT + COUT + NBUF * CC * SROWS * SPITCH;
+    return conv_wfloats_padded<CIN, COUT>() + NBUF * CC * SROWS * SPITCH + 8 /* 2 mbarriers */ + 32 /* align slack */;
+}
+
+// ---- TMA + mbarrier primitives (staging of whole [channels][34][36] boxes by one thread) ----
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) {
+    for (uint32_t spin = 0;; ++spin) {
+        uint32_t done;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+        if (spin > (1u << 22)) __trap();   // a bad descriptor must fault, never hang the GPU
+    }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int x, int y, int c, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(tm), "r"(x), "r"(y), "r"(c), "r"(bar) : "memory");
 }
 
 // 4-byte async copy global -> shared with zero fill when !ok (src-size 0 reads nothing)
@@ -62,7 +91,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int CIN_A, int CIN_B, int COUT, int EPI, bool F32X2>
+template <int CIN_A, int CIN_B, int COUT, int EPI, bool F32X2, bool TMA>
 __global__ void __launch_bounds__(128 * (COUT / 8), (COUT == 8) ? 4 : 2)
 conv3x3_kernel(const __grid_constant__ ConvParams p) {
     constexpr int CIN = CIN_A + CIN_B;
@@ -75,9 +104,11 @@ conv3x3_kernel(const __grid_constant__ ConvParams p) {
     constexpr int XBUF = CC * SROWS * SPITCH;
     static_assert(CIN % CC == 0 && (CIN_A % CC == 0 || CIN_B == 0), "chunks must not straddle sources");
 
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(16) float smem_dyn[];
+    float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_dyn) + 127) & ~(uintptr_t)127);   // TMA dst: 128 B
     float* ws = smem;
-    float* xs = smem + WFLOATS;
+    float* xs = smem + conv_wfloats_padded<CIN, COUT>();
+    const uint32_t bar0 = smem_addr(xs + NBUF * XBUF);      // two 8-byte mbarriers (TMA path)
 
     const ConvJob& job = p.jobs[blockIdx.z];
     const int tx = threadIdx.x, ty = threadIdx.y, tz = threadIdx.z;
@@ -121,15 +152,36 @@ conv3x3_kernel(const __grid_constant__ ConvParams p) {
             const long long roff = rok ? (long long)sy * rs : 0;
 #pragma unroll
             for (int c = 0; c < CC; ++c) {
-                float* d = dst + (c * SROWS + r) * SPITCH + lane;
+                float* d = dst + (c * SROWS + r) * SPITCH + XOFF + lane;
                 cp_async4(d, planes[c] + roff + sxv[0], rok && okv[0]);
                 if (lane < SROWS - 32) cp_async4(d + 32, planes[c] + roff + sxv[1], rok && okv[1]);
             }
         }
     };
 
-    stage(0, xs);
-    cp_async_commit();
+    // TMA staging: one thread arms the chunk's mbarrier with the box size and issues ONE bulk tensor copy; the
+    // hardware zero-fills everything outside the source tensor (= the conv's zero padding / the Up block's F.pad)
+    auto stage_tma = [&](int chunk) {
+        const bool fromA = (chunk * CC) < CIN_A;
+        const uint32_t bar = bar0 + 8 * (chunk & (NBUF - 1));
+        const uint32_t dst = smem_addr(xs + (chunk & (NBUF - 1)) * XBUF);
+        mbar_expect_tx(bar, XBUF * 4);
+        if (fromA) tma_load_3d(dst, &p.tmA[blockIdx.z], x0 - 1 - XOFF - job.a_ox, y0 - 1 - job.a_oy, chunk * CC, bar);
+        else tma_load_3d(dst, &p.tmB[blockIdx.z], x0 - 1 - XOFF - job.b_ox, y0 - 1 - job.b_oy, chunk * CC - CIN_A, bar);
+    };
+
+    if (TMA) {
+        if (tid == 0) {
+            mbar_init(bar0, 1);
+            mbar_init(bar0 + 8, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            stage_tma(0);
+        }
+    } else {
+        stage(0, xs);
+        cp_async_commit();
+    }
     for (int i = tid; i < WFLOATS / 4; i += NT)
         reinterpret_cast<float4*>(ws)[i] = __ldg(reinterpret_cast<const float4*>(job.w) + i);
 
@@ -148,25 +200,30 @@ conv3x3_kernel(const __grid_constant__ ConvParams p) {
 #pragma unroll 1
     for (int chunk = 0; chunk < NCHUNK; ++chunk) {
         float* cur = xs + (chunk & (NBUF - 1)) * XBUF;
-        if (chunk + 1 < NCHUNK) {           // prefetch the next chunk into the other buffer
-            stage(chunk + 1, xs + ((chunk + 1) & (NBUF - 1)) * XBUF);
-            cp_async_commit();
-            cp_async_wait<1>();
+        if (TMA) {
+            if (chunk == 0) __syncthreads();   // weights + barrier init visible to every thread
+            if (chunk + 1 < NCHUNK && tid == 0) stage_tma(chunk + 1);   // prefetch into the other buffer
+            mbar_wait_parity(bar0 + 8 * (chunk & (NBUF - 1)), (chunk / NBUF) & 1);
         } else {
-            cp_async_wait<0>();
+            if (chunk + 1 < NCHUNK) {           // prefetch the next chunk into the other buffer
+                stage(chunk + 1, xs + ((chunk + 1) & (NBUF - 1)) * XBUF);
+                cp_async_commit();
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncthreads();
         }
-        __syncthreads();
         // ---------------- register-tiled stencil: 2x4 pixels x 8 output channels per thread ----------------
         const float* xt = cur + (2 * ty) * SPITCH + 4 * tx;
 #pragma unroll 1
         for (int c = 0; c < CC; ++c) {
-            float xin[4][8];
+            float xin[4][6];   // image columns x-1 .. x+4 of the thread's 4-pixel strip = staged columns 4tx+3 .. 4tx+8
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-                const float4 v0 = *reinterpret_cast<const float4*>(xt + (c * SROWS + r) * SPITCH);
-                const float4 v1 = *reinterpret_cast<const float4*>(xt + (c * SROWS + r) * SPITCH + 4);
-                xin[r][0] = v0.x; xin[r][1] = v0.y; xin[r][2] = v0.z; xin[r][3] = v0.w;
-                xin[r][4] = v1.x; xin[r][5] = v1.y; xin[r][6] = v1.z; xin[r][7] = v1.w;
+                const float* row = xt + (c * SROWS + r) * SPITCH;
+                const float4 v1 = *reinterpret_cast<const float4*>(row + 4);
+                xin[r][0] = row[3]; xin[r][1] = v1.x; xin[r][2] = v1.y; xin[r][3] = v1.z; xin[r][4] = v1.w; xin[r][5] = row[8];
             }
             const float* wc = ws + (chunk * CC + c) * 9 * COUT + 8 * tz;
 #pragma unroll
@@ -399,23 +456,72 @@ static size_t carve(char* base, int B, int nstream, int Hv, int Wv, StreamBufs* 
     return cv.off;
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess) ptr = nullptr;
+        return (EncodeTiledFn)ptr;
+    }();
+    return fn;
+}
+
+// [C][H][W] fp32 planes (row stride rs, plane stride cs, in floats) -> 3-D tensor map with a [cc][34][36] box
+static bool make_tmap(CUtensorMap* tm, const float* ptr, int C, int H, int W, int rs, long long cs, int cc) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn || !ptr || (((uintptr_t)ptr) & 15) || (rs & 3) || (cs & 3) || C < cc) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C};
+    cuuint64_t strides[2] = {(cuuint64_t)rs * 4, (cuuint64_t)cs * 4};
+    cuuint32_t box[3] = {(cuuint32_t)SPITCH, (cuuint32_t)SROWS, (cuuint32_t)cc};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int CIN_A, int CIN_B, int COUT, int EPI, bool X2, bool TMA>
+static int launch_conv_impl(const ConvParams& p, int njobs, cudaStream_t st) {
+    constexpr int smem = conv_smem_floats<CIN_A + CIN_B, COUT, EPI>() * 4;
+    dim3 grid(cdiv(p.W, TILE), cdiv(p.H, TILE), njobs), block(8, 16, COUT / 8);
+    auto k = conv3x3_kernel<CIN_A, CIN_B, COUT, EPI, X2, TMA>;
+    PC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    k<<<grid, block, smem, st>>>(p);
+    return 0;
+}
+
 template <int CIN_A, int CIN_B, int COUT, int EPI>
-static int launch_conv(const ConvParams& p, int njobs, cudaStream_t st) {
+static int launch_conv(ConvParams& p, int njobs, cudaStream_t st) {
     static const bool use_x2 = [] {
         const char* e = getenv("POPCORN_CONV_F32X2");
         return e ? atoi(e) != 0 : true;   // packed fma.rn.f32x2 (FFMA2) is ~13% faster on B200
     }();
-    constexpr int smem = conv_smem_floats<CIN_A + CIN_B, COUT, EPI>() * 4;
-    dim3 grid(cdiv(p.W, TILE), cdiv(p.H, TILE), njobs), block(8, 16, COUT / 8);
-    if (use_x2) {
-        auto k = conv3x3_kernel<CIN_A, CIN_B, COUT, EPI, true>;
-        PC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        k<<<grid, block, smem, st>>>(p);
-    } else {
-        auto k = conv3x3_kernel<CIN_A, CIN_B, COUT, EPI, false>;
-        PC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        k<<<grid, block, smem, st>>>(p);
+    static const bool allow_tma = [] {
+        const char* e = getenv("POPCORN_CONV_TMA");
+        return e ? atoi(e) != 0 : true;
+    }();
+    static const int cat = [] {
+        char nm[64];
+        snprintf(nm, sizeof(nm), "conv3x3<%d,%d,%d,%s>", CIN_A, CIN_B, COUT, EPI == EPI_STORE ? "store" : EPI == EPI_POOL ? "pool" : "dot");
+        return prof_register(nm);
+    }();
+    constexpr int CC = conv_cc<CIN_A + CIN_B>();
+    // TMA staging needs plain (non-reflected, identity-channel) 16-byte-aligned sources: every layer but the first
+    bool tma = allow_tma && CIN_A >= 8;
+    for (int j = 0; tma && j < njobs; ++j) {
+        const ConvJob& J = p.jobs[j];
+        tma = !J.a_reflect && (J.a_ox & 3) == 0 && make_tmap(&p.tmA[j], J.a, CIN_A, J.a_H, J.a_W, J.a_rs, J.a_cs, CC);
+        if (tma && CIN_B > 0) tma = (J.b_ox & 3) == 0 && make_tmap(&p.tmB[j], J.b, CIN_B, J.b_H, J.b_W, J.b_rs, J.b_cs, CC);
     }
+    ProfScope prof(cat, st, (double)p.H * p.W * njobs);
+    int rc;
+    if (tma) rc = use_x2 ? launch_conv_impl<CIN_A, CIN_B, COUT, EPI, true, true>(p, njobs, st)
+                         : launch_conv_impl<CIN_A, CIN_B, COUT, EPI, false, true>(p, njobs, st);
+    else rc = use_x2 ? launch_conv_impl<CIN_A, CIN_B, COUT, EPI, true, false>(p, njobs, st)
+                     : launch_conv_impl<CIN_A, CIN_B, COUT, EPI, false, false>(p, njobs, st);
+    if (rc) return rc;
     PC_LAUNCH_CHECK();
     return 0;
 }
@@ -535,7 +641,11 @@ extern "C" int pc_dda_forward(const float* wpack, const float* x, int B, int C, 
             ConvTJob& J = pt.jobs[j]; J.in = bufs[j].QA.p; J.in_cs = bufs[j].QA.cs; J.in_rs = bufs[j].QA.rs;
             J.w = W_(js(j), 6); J.out = bufs[j].HD.p; J.out_cs = bufs[j].HD.cs; J.out_rs = bufs[j].HD.rs;
         }
-        convt2x2_kernel<16><<<dim3(cdiv(W4, 32), cdiv(H4, 4), nj), dim3(32, 4), 0, st>>>(pt);
+        {
+            static const int cat = prof_register("convt2x2<16>");
+            ProfScope prof(cat, st, (double)H4 * W4 * nj);
+            convt2x2_kernel<16><<<dim3(cdiv(W4, 32), cdiv(H4, 4), nj), dim3(32, 4), 0, st>>>(pt);
+        }
         PC_LAUNCH_CHECK();
         // ---- L7 up2.conv.0 : cat[HC(16), pad(HD)(16)] -> HA(8) ; L8 up2.conv.3 : HA -> HB(8)
         reset(H2, W2);
@@ -555,7 +665,11 @@ extern "C" int pc_dda_forward(const float* wpack, const float* x, int B, int C, 
             ConvTJob& J = pt.jobs[j]; J.in = bufs[j].HB.p; J.in_cs = bufs[j].HB.cs; J.in_rs = bufs[j].HB.rs;
             J.w = W_(js(j), 9); J.out = bufs[j].F2.p; J.out_cs = bufs[j].F2.cs; J.out_rs = bufs[j].F2.rs;
         }
-        convt2x2_kernel<8><<<dim3(cdiv(W2, 32), cdiv(H2, 4), nj), dim3(32, 4), 0, st>>>(pt);
+        {
+            static const int cat = prof_register("convt2x2<8>");
+            ProfScope prof(cat, st, (double)H2 * W2 * nj);
+            convt2x2_kernel<8><<<dim3(cdiv(W2, 32), cdiv(H2, 4), nj), dim3(32, 4), 0, st>>>(pt);
+        }
         PC_LAUNCH_CHECK();
         // ---- L10 up1.conv.0 : cat[F1(8), pad(F2)(8)] -> F0(8)
         reset(Hv, Wv);

@@ -120,7 +120,11 @@ static int launch_head(const HeadArgs& a, long long total_bound, cudaStream_t st
     const int maxg = num_sms() * 2 * 8;
     int grid = (int)(tiles < maxg ? tiles : maxg);
     if (grid < 1) grid = 1;
-    k<<<grid, 256, smem, st>>>(a);
+    {
+        static const int cat = prof_register(SPARSE ? "head_forward_simt<sparse>" : "head_forward_simt<dense>");
+        ProfScope prof(cat, st, (double)total_bound);
+        k<<<grid, 256, smem, st>>>(a);
+    }
     PC_LAUNCH_CHECK();
     return 0;
 }

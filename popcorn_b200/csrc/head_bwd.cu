@@ -262,6 +262,8 @@ extern "C" int pc_head_sparse_backward(const float* hpack, int head_in, const fl
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = bwd_grid(n_max);
     const int PF = bwd_pack_floats(head_in);
+    static const int cat = prof_register("head_backward");
+    ProfScope prof(cat, st, (double)n_max);
     if (head_in == 16) {
         constexpr int smem = ((16 + 3 * BN) * BP + BM + bwd_pack_floats(16) + 2 * BN * BN) * 4;
         auto k = head_backward_kernel<16>;

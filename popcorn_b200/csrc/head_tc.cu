@@ -244,7 +244,11 @@ static int launch_head_tc(const HeadArgs& a, long long total_bound, cudaStream_t
     const int maxg = num_sms() * 2;          // persistent: 2 CTAs per SM, each walks tiles grid-stride
     int grid = (int)(tiles < maxg ? tiles : maxg);
     if (grid < 1) grid = 1;
-    k<<<grid, TM, TC_SMEM_BYTES, st>>>(a);
+    {
+        static const int cat = prof_register(SPARSE ? "head_tc<sparse>" : "head_tc<dense>");
+        ProfScope prof(cat, st, (double)total_bound);
+        k<<<grid, TM, TC_SMEM_BYTES, st>>>(a);
+    }
     PC_LAUNCH_CHECK();
     return 0;
 }

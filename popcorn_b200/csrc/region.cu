@@ -318,6 +318,8 @@ extern "C" int pc_region_sum(const float* dens, const int32_t* ids, long long np
     if (span < 2048) span = 2048;
     const long long nwarps = cdiv(npix, span);
     const int grid = cdiv(nwarps * 32, 256);
+    static const int cat = prof_register("region_sum");
+    ProfScope prof(cat, (cudaStream_t)stream, (double)npix);
     if (R <= SMEM_BINS)
         region_sum_kernel<true><<<grid, 256, R * sizeof(float), (cudaStream_t)stream>>>(dens, ids, npix, R, sums, span);
     else
@@ -389,6 +391,8 @@ extern "C" int pc_accumulate_tile(const float* dens, const float* scale, int t_r
     PC_CHECK_ARG(dens && map, "null pointer");
     if (r1 <= r0 || c1 <= c0) return 0;
     dim3 grid(cdiv(c1 - c0, 256), r1 - r0);
+    static const int cat = prof_register("accumulate");
+    ProfScope prof(cat, (cudaStream_t)stream, (double)(r1 - r0) * (c1 - c0));
     accumulate_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dens, scale, t_rstride, r0, r1, c0, c1, map, map_sq, smap,
                                                               smap_sq, count, m_rstride, y0, x0);
     PC_LAUNCH_CHECK();
@@ -400,6 +404,8 @@ extern "C" int pc_finalize_map(float* map, float* map_sq, float* smap, float* sm
     PC_CHECK_ARG(map && count, "null pointer");
     if (npix <= 0) return 0;
     const int grid = (int)(cdiv(npix, 256) < num_sms() * 16 ? cdiv(npix, 256) : num_sms() * 16);
+    static const int cat = prof_register("finalize");
+    ProfScope prof(cat, (cudaStream_t)stream, (double)npix);
     finalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(map, map_sq, smap, smap_sq, count, npix);
     PC_LAUNCH_CHECK();
     return 0;

@@ -215,3 +215,21 @@ def copy_d2h(dst: torch.Tensor, src: torch.Tensor, stream: Optional[int] = None)
     _lib.check(_lib.lib().pc_memcpy2d_async(dst.data_ptr(), dst.stride(0) * es, src.data_ptr(), src.stride(0) * es,
                                             src.shape[1] * es, src.shape[0], 2, _stream() if stream is None else stream),
                "pc_memcpy2d_async")
+
+
+def profile_enable(on: bool) -> None:
+    """Bracket every library launch with CUDA events (on its own stream) until disabled."""
+    _lib.lib().pc_profile_enable(1 if on else 0)
+
+
+def profile_results() -> dict:
+    """{kernel name: (total ms, launches, pixels processed)} for the launches since the last profile_enable(True)."""
+    import ctypes as C
+    L = _lib.lib()
+    out = {}
+    for i in range(L.pc_profile_num()):
+        ms, n, u = C.c_double(0), C.c_longlong(0), C.c_double(0)
+        _lib.check(L.pc_profile_get(i, C.byref(ms), C.byref(n), C.byref(u)), "pc_profile_get")
+        if n.value:
+            out[L.pc_profile_name(i).decode()] = (ms.value, n.value, u.value)
+    return out

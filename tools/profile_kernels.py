@@ -12,8 +12,9 @@ hp = weights.pack_head(sd).cuda()
 for _ in range(2):
     feats = ops.dda_forward(pack, x, (0, 0, 0, 0), 0)
 bu = torch.rand(1, 1, H, W, device="cuda")
+hp_tc = weights.pack_head_tc(sd).cuda()
 for _ in range(2):
-    dens, scale = ops.head_dense_forward(hp, feats, bu, None, None, None)
+    dens, scale = ops.head_dense_forward(hp_tc, feats, bu, None, None, None, tc=True)
 ids = po.synthetic_regions(H, W, 400).cuda().contiguous()
 n = 1 << 27
 d = torch.rand(n, device="cuda"); big = ids.reshape(-1).repeat(n // ids.numel() + 1)[:n].contiguous()

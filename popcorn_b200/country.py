@@ -202,31 +202,35 @@ class CountryEngine:
         wins = self.windows
         if not wins:
             return
+        # ring of NB device buffers, uploads run NB-1 windows ahead: a big strip's upload must overlap the previous
+        # big strip's compute, not just the small right-column window that sits between them
+        NB = 3
         mh, mw = max(w.h for w in wins), max(w.w for w in wins)
-        bufs = [torch.empty(6 * mh * mw, dtype=torch.float32, device=dev) for _ in range(2)]
-        ready = [torch.cuda.Event() for _ in range(2)]
-        free = [torch.cuda.Event() for _ in range(2)]
+        bufs = [torch.empty(6 * mh * mw, dtype=torch.float32, device=dev) for _ in range(NB)]
+        ready = [torch.cuda.Event() for _ in range(NB)]
+        free = [torch.cuda.Event() for _ in range(NB)]
+        views = {}
 
         def upload(k):
             w = wins[k]
-            b = bufs[k % 2][: 6 * w.h * w.w].view(6, w.h, w.w)
+            b = bufs[k % NB][: 6 * w.h * w.w].view(6, w.h, w.w)
             with torch.cuda.stream(cs):
-                cs.wait_event(free[k % 2])
+                cs.wait_event(free[k % NB])
                 ops.copy_window_h2d(b, raster[:, w.y0 - row_offset: w.y0 - row_offset + w.h, w.x0: w.x0 + w.w],
                                     cs.cuda_stream)
-                ready[k % 2].record(cs)
-            return b
+                ready[k % NB].record(cs)
+            views[k] = b
 
         for e in free:
             e.record(main)
-        nxt = upload(0)
+        for k in range(min(NB - 1, len(wins))):
+            upload(k)
         for k, win in enumerate(wins):
-            cur = nxt
-            if k + 1 < len(wins):
-                nxt = upload(k + 1)
-            main.wait_event(ready[k % 2])
-            self._forward_window(cur[None], win)
-            free[k % 2].record(main)
+            if k + NB - 1 < len(wins):
+                upload(k + NB - 1)
+            main.wait_event(ready[k % NB])
+            self._forward_window(views.pop(k)[None], win)
+            free[k % NB].record(main)
         self.h2d_bytes = sum(6 * w.h * w.w * 4 for w in wins)
 
 

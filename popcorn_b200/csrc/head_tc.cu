@@ -108,15 +108,17 @@ __device__ __forceinline__ void issue_layer(uint32_t tD, uint32_t tAhi, uint32_t
 
 // hidden-layer epilogue: D -> relu(D + bias) -> (hi, lo) -> A operand of the next layer (all in TMEM)
 __device__ __forceinline__ void epilogue_hidden(uint32_t tD, uint32_t tAhi, uint32_t tAlo, const float* bias) {
-#pragma unroll 1
-    for (int c = 0; c < HN; c += 16) {
-        uint32_t v[16], hi[16], lo[16];
-        tmem_ld16(tD + c, v);
-        tc_wait_ld();
+    uint32_t v[4][16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) split_tf32(fmaxf(__uint_as_float(v[i]) + bias[c + i], 0.f), hi[i], lo[i]);
-        tmem_st16(tAhi + c, hi);
-        tmem_st16(tAlo + c, lo);
+    for (int q = 0; q < 4; ++q) tmem_ld16(tD + 16 * q, v[q]);      // all four loads in flight, one wait
+    tc_wait_ld();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) split_tf32(fmaxf(__uint_as_float(v[q][i]) + bias[16 * q + i], 0.f), hi[i], lo[i]);
+        tmem_st16(tAhi + 16 * q, hi);
+        tmem_st16(tAlo + 16 * q, lo);
     }
 }
 
@@ -153,36 +155,55 @@ __global__ void __launch_bounds__(TM, 2) head_tc_kernel(const __grid_constant__ 
     const long long HW = SPARSE ? a.HW : (long long)a.H * a.W;
     const long long total = SPARSE ? (long long)__ldg(a.n_dev) : HW * a.B;
 
-    for (long long base = (long long)blockIdx.x * TM; base < total; base += (long long)gridDim.x * TM) {
-        const long long i = base + tid;
-        const bool valid = i < total;
-        long long p = 0; int b = 0; long long foff = 0, boff = 0, ooff = 0, ioff = 0;
-        if (valid) {
-            p = SPARSE ? (long long)__ldg(a.idx + i) : i;
-            b = (int)(p / HW);
-            const long long q = p - (long long)b * HW;
+    // pixel bookkeeping + feature fetch of one tile; the NEXT tile's features are fetched while the current tile
+    // runs its MMAs / epilogues, so the global-load latency is off the critical path
+    struct Px { long long i; bool valid; int b; long long boff, ooff, ioff; };
+    auto locate = [&](long long base, long long& foff) {
+        Px px;
+        px.i = base + tid;
+        px.valid = px.i < total;
+        px.b = 0; px.boff = 0; px.ooff = 0; px.ioff = 0; foff = 0;
+        if (px.valid) {
+            const long long p = SPARSE ? (long long)__ldg(a.idx + px.i) : px.i;
+            px.b = (int)(p / HW);
+            const long long q = p - (long long)px.b * HW;
             if (SPARSE) {
-                foff = b * a.f_bs + q; boff = p; ooff = p;
+                foff = px.b * a.f_bs + q; px.boff = p; px.ooff = p;
             } else {
                 const int y = (int)(q / a.W), x = (int)(q - (long long)y * a.W);
-                foff = b * a.f_bs + (long long)y * a.f_rs + x;
-                boff = b * a.bu_bs + (long long)y * a.bu_rs + x;
-                ooff = b * a.o_bs + (long long)y * a.o_rs + x;
-                ioff = b * a.id_bs + (long long)y * a.id_rs + x;
+                foff = px.b * a.f_bs + (long long)y * a.f_rs + x;
+                px.boff = px.b * a.bu_bs + (long long)y * a.bu_rs + x;
+                px.ooff = px.b * a.o_bs + (long long)y * a.o_rs + x;
+                px.ioff = px.b * a.id_bs + (long long)y * a.id_rs + x;
             }
         }
+        return px;
+    };
+    float fcur[K1], fnext[K1];
+    long long foff0;
+    Px cur = locate((long long)blockIdx.x * TM, foff0);
+#pragma unroll
+    for (int c = 0; c < K1; ++c) fcur[c] = cur.valid ? __ldg(a.feats + foff0 + (long long)c * a.f_cs) : 0.f;
+
+    for (long long base = (long long)blockIdx.x * TM; base < total; base += (long long)gridDim.x * TM) {
+        const long long i = cur.i;
+        const bool valid = cur.valid;
+        const int b = cur.b;
+        const long long boff = cur.boff, ooff = cur.ooff, ioff = cur.ioff;
         // ---- layer-1 A operand: this pixel's K1 features, split, into TMEM ----
 #pragma unroll
         for (int c0 = 0; c0 < K1; c0 += 8) {
             uint32_t hi[8], lo[8];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const float f = valid ? __ldg(a.feats + foff + (long long)(c0 + c) * a.f_cs) : 0.f;
-                split_tf32(f, hi[c], lo[c]);
-            }
+            for (int c = 0; c < 8; ++c) split_tf32(fcur[c0 + c], hi[c], lo[c]);
             tmem_st8(tAhi + lane_off + c0, hi);
             tmem_st8(tAlo + lane_off + c0, lo);
         }
+        // ---- prefetch the next tile's features (consumed at the top of the next iteration) ----
+        long long foffn;
+        const Px nxt = locate(base + (long long)gridDim.x * TM, foffn);
+#pragma unroll
+        for (int c = 0; c < K1; ++c) fnext[c] = nxt.valid ? __ldg(a.feats + foffn + (long long)c * a.f_cs) : 0.f;
         tc_wait_st();
         tc_fence_before();
         __syncthreads();
@@ -229,6 +250,9 @@ __global__ void __launch_bounds__(TM, 2) head_tc_kernel(const __grid_constant__ 
             }
         }
         if (a.sums) bin_add(a.sums, bin, d);
+        cur = nxt;
+#pragma unroll
+        for (int c = 0; c < K1; ++c) fcur[c] = fnext[c];
     }
 
     tc_fence_before();

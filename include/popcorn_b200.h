@@ -65,6 +65,18 @@ int pc_memcpy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_p
 int pc_dda_pack_floats(void);
 int pc_dda_pack_offset(int stream, int layer);
 
+/* Tensor-core weight section (csrc/conv_tc.cu): the ten 3x3 conv layers of each stream again, as tcgen05 B
+ * operands — per layer [ky][hi|lo] matrices W_ky[co (16 rows, zero-padded)][k = kx*cin + ci] in the UMMA K-major
+ * SWIZZLE_128B layout, each weight split w = hi + lo (hi = top 19 bits: exact TF32) for 3xTF32, then bias[16].
+ * It is appended to the fp32 pack at float offset pc_dda_tc_pack_base() (the fp32 pack rounded up to 256 B) and is
+ * pc_dda_tc_pack_floats() long; pc_dda_tc_pack converts a HOST fp32 pack into a HOST image (pure host code).
+ * pc_dda_forward uses the tensor-core kernels when the pack it is given is long enough to hold the section. */
+int pc_dda_tc_pack_base(void);
+int pc_dda_tc_pack_floats(void);
+int pc_dda_tc_pack(const float* flat_host, float* img_host);
+int pc_conv_tc_layer_floats(int cin);
+int pc_conv_tc_pack_layer(const float* flat_host, int cin, int cout, float* img_host);
+
 /* Head pack: W1t[k=Cin][64], b1[64], W2t[64][64], b2[64], W3t[64][64], b3[64], w4[64] (row 0 of
  * head.6.weight — only channel 0 is used, model/popcorn.py:162-164), b4 (+3 pad).  Cin = 16 or 8. */
 int pc_head_pack_floats(int head_in);
@@ -78,9 +90,11 @@ int pc_head_pack_floats(int head_in);
  *   pad_*      reflect padding applied virtually by the loader (14/14/14/14 for the builtup pass,
  *              the pad-to-64 amounts for the feature pass, 0 otherwise); nothing is materialised
  *   mode       PC_DDA_FEATURES -> out[B,F,H,W] ; PC_DDA_BUILTUP -> out[B,1,H,W]; cropped back to HxW
+ *   wpack      device pack of wpack_floats floats: the fp32 section, optionally followed by the tensor-core
+ *              section (then the 3x3 convs run on tcgen05, 3xTF32; otherwise the fp32 SIMT stencils run)
  * --------------------------------------------------------------------------------------------- */
 size_t pc_dda_workspace_bytes(int B, int C, int Hv, int Wv);
-int pc_dda_forward(const float* wpack, const float* x, int B, int C, int H, int W, long long x_bstride,
+int pc_dda_forward(const float* wpack, long long wpack_floats, const float* x, int B, int C, int H, int W, long long x_bstride,
                    long long x_cstride, int x_rstride, int pad_top, int pad_bottom, int pad_left, int pad_right,
                    int mode, float* out, long long out_bstride, long long out_cstride, int out_rstride,
                    void* workspace, size_t workspace_bytes, pc_stream_t stream);
@@ -192,11 +206,12 @@ int pc_finalize_map(float* map, float* map_sq, float* smap, float* smap_sq, cons
  * Unit-test hooks (tests/test_gpu_kernels.py): ONE fused conv3x3(+folded BN)+ReLU layer, optionally with a
  * second concatenated source placed at an offset (Up block) and a fused 2x2 max-pool output, and ONE
  * ConvTranspose2d(k2,s2) layer, on plain contiguous tensors.  w uses the packed block layouts above.
+ * wtc != NULL (a device copy of the layer's pc_conv_tc_pack_layer image) selects the tensor-core kernel.
  * Same kernels pc_dda_forward schedules; replaces networks.py:258-267 / :289 / :302 one layer at a time.
  * --------------------------------------------------------------------------------------------- */
 int pc_test_conv3x3(const float* a, int cin_a, int a_H, int a_W, int a_oy, int a_ox, int a_reflect, const float* b,
                     int cin_b, int b_H, int b_W, int b_oy, int b_ox, const float* w, int cout, int H, int W,
-                    float* out, float* pool, pc_stream_t stream);
+                    float* out, float* pool, const float* wtc, pc_stream_t stream);
 int pc_test_convt2x2(const float* in, int C, int Hl, int Wl, const float* w, float* out, pc_stream_t stream);
 /* FP32 SIMT ceiling probe: every thread runs 32*iters dependent-chain FMAs (scalar, or packed fma.rn.f32x2);
  * returns the number of threads launched (negative = error is impossible: errors are > 0 codes <= 10002, thread

@@ -31,7 +31,12 @@ SIGNATURES = {
     "pc_dda_pack_offset": (_i, [_i, _i]),
     "pc_head_pack_floats": (_i, [_i]),
     "pc_dda_workspace_bytes": (_sz, [_i, _i, _i, _i]),
-    "pc_dda_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _ll, _ll, _i, _i, _i, _i, _i, _i, _vp, _ll, _ll, _i, _vp, _sz, _vp]),
+    "pc_dda_tc_pack_base": (_i, []),
+    "pc_dda_tc_pack_floats": (_i, []),
+    "pc_dda_tc_pack": (_i, [_vp, _vp]),
+    "pc_conv_tc_layer_floats": (_i, [_i]),
+    "pc_conv_tc_pack_layer": (_i, [_vp, _i, _i, _vp]),
+    "pc_dda_forward": (_i, [_vp, _ll, _vp, _i, _i, _i, _i, _ll, _ll, _i, _i, _i, _i, _i, _i, _vp, _ll, _ll, _i, _vp, _sz, _vp]),
     "pc_head_dense_forward": (_i, [_vp, _i, _vp, _ll, _ll, _i, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _ll, _i, _vp, _ll, _i,
                                    _vp, _vp, _i, _vp]),
     "pc_head_tc_pack_bytes": (_i, []),
@@ -48,7 +53,7 @@ SIGNATURES = {
     "pc_region_scale": (_i, [_vp, _vp, _ll, _i, _vp, _vp]),
     "pc_accumulate_tile": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "pc_finalize_map": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _vp]),
-    "pc_test_conv3x3": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "pc_test_conv3x3": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "pc_test_convt2x2": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "pc_test_fma_peak": (_i, [_i, _i, _i, _vp, _vp]),
 }

@@ -13,7 +13,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "common.cuh"
+#include "conv_common.cuh"
 
 namespace pc {
 
@@ -21,22 +21,6 @@ constexpr int TILE = 32;            // output tile edge per CTA
 constexpr int SROWS = TILE + 2;     // staged rows (1-px halo)
 constexpr int SPITCH = 40;          // staged row pitch (floats) = TMA box width (inner TMA coordinate must be 16-B aligned)
 constexpr int XOFF = 3;             // staged column of image column x0-1: the box starts at x0-4
-constexpr int MAX_JOBS = 8;
-
-enum { EPI_STORE = 0, EPI_POOL = 1, EPI_DOT = 2 };
-
-struct ConvJob {
-    // source A (first CIN_A input channels)
-    const float* a; long long a_cs; int a_rs; int a_H, a_W; int a_oy, a_ox; int a_reflect; unsigned a_chmap;
-    // source B (next CIN_B channels; zero outside its placement) — the upsampled branch of Up blocks
-    const float* b; long long b_cs; int b_rs; int b_H, b_W; int b_oy, b_ox;
-    const float* w;                      // [CIN][9][COUT] then bias[COUT]
-    float* out; long long out_cs; int out_rs; int out_vec;
-    float* pool; long long pool_cs; int pool_rs;
-    const float* dotw;                   // [8] weights + [1] bias of the 1x1 out conv slice (EPI_DOT)
-    const float* dot_in; int dot_in_rs;  // partial logits of the other stream (or null)
-    float* dot_out; int dot_out_rs; int dot_final;
-};
 
 struct alignas(64) ConvParams {
     CUtensorMap tmA[MAX_JOBS];           // TMA descriptors of the job's sources (TMA staging only)
@@ -420,6 +404,20 @@ static int pack_offset(int stream, int layer) {
     return off + 44;
 }
 
+// tensor-core weight images (conv_tc.cu) follow the fp32 pack, 256-byte aligned: one image per 3x3 conv layer
+static int tc_pack_base() { return (int)round_up(pack_offset(3, 13), 64); }
+static int tc_pack_offset(int stream, int layer) {     // floats from the start of the TC section; layer 12 = end
+    int off = 0;
+    for (int s = 0; s < 2; ++s)
+        for (int l = 0; l < 12; ++l) {
+            if (s == stream && l == layer) return off;
+            if (kLayers[l].is_t) continue;
+            const int cin = kLayers[l].cin < 0 ? (s == 0 ? 2 : 4) : kLayers[l].cin;
+            off += conv_tc_layer_floats(cin);
+        }
+    return off;
+}
+
 struct Plane {
     float* p; int C, H, W, rs; long long cs;
 };
@@ -507,6 +505,16 @@ static int launch_conv(ConvParams& p, int njobs, cudaStream_t st) {
         snprintf(nm, sizeof(nm), "conv3x3<%d,%d,%d,%s>", CIN_A, CIN_B, COUT, EPI == EPI_STORE ? "store" : EPI == EPI_POOL ? "pool" : "dot");
         return prof_register(nm);
     }();
+    // tensor-core path (conv_tc.cu): every job carries a pre-swizzled weight image
+    bool tc = conv_tc_enabled();
+    for (int j = 0; tc && j < njobs; ++j) tc = p.jobs[j].wtc != nullptr;
+    if (tc) {
+        TcConvParams tp;
+        memset(&tp, 0, sizeof(tp));
+        tp.H = p.H; tp.W = p.W; tp.crop_y = p.crop_y; tp.crop_x = p.crop_x; tp.crop_H = p.crop_H; tp.crop_W = p.crop_W;
+        for (int j = 0; j < njobs; ++j) tp.jobs[j] = p.jobs[j];
+        return launch_conv_tc(CIN_A, CIN_B, COUT, EPI, tp, njobs, st);
+    }
     constexpr int CC = conv_cc<CIN_A + CIN_B>();
     // TMA staging needs plain (non-reflected, identity-channel) 16-byte-aligned sources: every layer but the first
     bool tma = allow_tma && CIN_A >= 8;
@@ -549,7 +557,26 @@ extern "C" size_t pc_dda_workspace_bytes(int B, int C, int Hv, int Wv) {
     return carve(nullptr, B, ns, Hv, Wv, nullptr, nullptr) + 256;
 }
 
-extern "C" int pc_dda_forward(const float* wpack, const float* x, int B, int C, int H, int W, long long x_bstride,
+extern "C" int pc_dda_tc_pack_base(void) { return tc_pack_base(); }
+extern "C" int pc_dda_tc_pack_floats(void) { return tc_pack_offset(2, 12); }
+extern "C" int pc_dda_tc_pack(const float* flat_host, float* img_host) {
+    PC_CHECK_ARG(flat_host && img_host, "null pointer");
+    for (int s = 0; s < 2; ++s)
+        for (int l = 0; l < 12; ++l) {
+            if (kLayers[l].is_t) continue;
+            const int cin = kLayers[l].cin < 0 ? (s == 0 ? 2 : 4) : kLayers[l].cin;
+            conv_tc_pack_layer(flat_host + pack_offset(s, l), cin, kLayers[l].cout, img_host + tc_pack_offset(s, l));
+        }
+    return 0;
+}
+extern "C" int pc_conv_tc_layer_floats(int cin) { return conv_tc_layer_floats(cin); }
+extern "C" int pc_conv_tc_pack_layer(const float* flat_host, int cin, int cout, float* img_host) {
+    PC_CHECK_ARG(flat_host && img_host && cin >= 1 && cin <= 32 && (cout == 8 || cout == 16), "bad argument");
+    conv_tc_pack_layer(flat_host, cin, cout, img_host);
+    return 0;
+}
+
+extern "C" int pc_dda_forward(const float* wpack, long long wpack_floats, const float* x, int B, int C, int H, int W, long long x_bstride,
                               long long x_cstride, int x_rstride, int pad_top, int pad_bottom, int pad_left,
                               int pad_right, int mode, float* out, long long out_bstride, long long out_cstride,
                               int out_rstride, void* workspace, size_t workspace_bytes, pc_stream_t stream) {
@@ -583,6 +610,8 @@ extern "C" int pc_dda_forward(const float* wpack, const float* x, int B, int C, 
         carve(wsb, nb, ns, Hv, Wv, bufs, dot_tmp);
         const int nj = nb * ns;
         auto W_ = [&](int s, int l) { return wpack + pack_offset(s, l); };
+        const bool have_tc = wpack_floats >= (long long)tc_pack_base() + tc_pack_offset(2, 12);
+        auto WT_ = [&](int s, int l) -> const float* { return have_tc ? wpack + tc_pack_base() + tc_pack_offset(s, l) : nullptr; };
         auto jb = [&](int j) { return b0 + j / ns; };     // batch index of job j
         auto js = [&](int j) { return sids[j % ns]; };    // stream id of job j
         ConvParams p;
@@ -604,7 +633,7 @@ extern "C" int pc_dda_forward(const float* wpack, const float* x, int B, int C, 
                 if (C == 6) j.a_chmap = (s == 0) ? 0x00000504u : 0x03000102u;
                 else if (C == 2) j.a_chmap = 0x00000100u;
                 else j.a_chmap = 0x03000102u;
-                j.w = W_(s, 0);
+                j.w = W_(s, 0); j.wtc = WT_(s, 0);
                 set_out(j, bufs[k * ns + si].F0);
             }
             rc = (s == 0) ? launch_conv<2, 0, 8, EPI_STORE>(p, nb, st) : launch_conv<4, 0, 8, EPI_STORE>(p, nb, st);
@@ -613,27 +642,27 @@ extern "C" int pc_dda_forward(const float* wpack, const float* x, int B, int C, 
         // ---- L1 inc.conv.3 : F0 -> F1 (+ pooled HA)
         reset(Hv, Wv);
         for (int j = 0; j < nj; ++j) {
-            ConvJob& J = p.jobs[j]; set_a(J, bufs[j].F0); J.w = W_(js(j), 1); set_out(J, bufs[j].F1);
+            ConvJob& J = p.jobs[j]; set_a(J, bufs[j].F0); J.w = W_(js(j), 1); J.wtc = WT_(js(j), 1); set_out(J, bufs[j].F1);
             J.pool = bufs[j].HA.p; J.pool_cs = bufs[j].HA.cs; J.pool_rs = bufs[j].HA.rs;
         }
         if ((rc = launch_conv<8, 0, 8, EPI_POOL>(p, nj, st))) return rc;
         // ---- L2 down1.conv.0 : HA -> HB(16)
         reset(H2, W2);
-        for (int j = 0; j < nj; ++j) { ConvJob& J = p.jobs[j]; set_a(J, bufs[j].HA); J.w = W_(js(j), 2); set_out(J, bufs[j].HB); }
+        for (int j = 0; j < nj; ++j) { ConvJob& J = p.jobs[j]; set_a(J, bufs[j].HA); J.w = W_(js(j), 2); J.wtc = WT_(js(j), 2); set_out(J, bufs[j].HB); }
         if ((rc = launch_conv<8, 0, 16, EPI_STORE>(p, nj, st))) return rc;
         // ---- L3 down1.conv.3 : HB -> HC (+ pooled QA)
         reset(H2, W2);
         for (int j = 0; j < nj; ++j) {
-            ConvJob& J = p.jobs[j]; set_a(J, bufs[j].HB); J.w = W_(js(j), 3); set_out(J, bufs[j].HC);
+            ConvJob& J = p.jobs[j]; set_a(J, bufs[j].HB); J.w = W_(js(j), 3); J.wtc = WT_(js(j), 3); set_out(J, bufs[j].HC);
             J.pool = bufs[j].QA.p; J.pool_cs = bufs[j].QA.cs; J.pool_rs = bufs[j].QA.rs;
         }
         if ((rc = launch_conv<16, 0, 16, EPI_POOL>(p, nj, st))) return rc;
         // ---- L4 down2.conv.0 : QA -> QB ; L5 down2.conv.3 : QB -> QA
         reset(H4, W4);
-        for (int j = 0; j < nj; ++j) { ConvJob& J = p.jobs[j]; set_a(J, bufs[j].QA); J.w = W_(js(j), 4); set_out(J, bufs[j].QB); }
+        for (int j = 0; j < nj; ++j) { ConvJob& J = p.jobs[j]; set_a(J, bufs[j].QA); J.w = W_(js(j), 4); J.wtc = WT_(js(j), 4); set_out(J, bufs[j].QB); }
         if ((rc = launch_conv<16, 0, 16, EPI_STORE>(p, nj, st))) return rc;
         reset(H4, W4);
-        for (int j = 0; j < nj; ++j) { ConvJob& J = p.jobs[j]; set_a(J, bufs[j].QB); J.w = W_(js(j), 5); set_out(J, bufs[j].QA); }
+        for (int j = 0; j < nj; ++j) { ConvJob& J = p.jobs[j]; set_a(J, bufs[j].QB); J.w = W_(js(j), 5); J.wtc = WT_(js(j), 5); set_out(J, bufs[j].QA); }
         if ((rc = launch_conv<16, 0, 16, EPI_STORE>(p, nj, st))) return rc;
         // ---- L6 up2.up : QA -> HD [16, 2*H4, 2*W4]
         memset(&pt, 0, sizeof(pt)); pt.Hl = H4; pt.Wl = W4;
@@ -653,11 +682,11 @@ extern "C" int pc_dda_forward(const float* wpack, const float* x, int B, int C, 
             ConvJob& J = p.jobs[j]; set_a(J, bufs[j].HC);
             J.b = bufs[j].HD.p; J.b_cs = bufs[j].HD.cs; J.b_rs = bufs[j].HD.rs; J.b_H = 2 * H4; J.b_W = 2 * W4;
             J.b_oy = (H2 - 2 * H4) / 2; J.b_ox = (W2 - 2 * W4) / 2;   // F.pad split, networks.py:309-312
-            J.w = W_(js(j), 7); set_out(J, bufs[j].HA);
+            J.w = W_(js(j), 7); J.wtc = WT_(js(j), 7); set_out(J, bufs[j].HA);
         }
         if ((rc = launch_conv<16, 16, 8, EPI_STORE>(p, nj, st))) return rc;
         reset(H2, W2);
-        for (int j = 0; j < nj; ++j) { ConvJob& J = p.jobs[j]; set_a(J, bufs[j].HA); J.w = W_(js(j), 8); set_out(J, bufs[j].HB); }
+        for (int j = 0; j < nj; ++j) { ConvJob& J = p.jobs[j]; set_a(J, bufs[j].HA); J.w = W_(js(j), 8); J.wtc = WT_(js(j), 8); set_out(J, bufs[j].HB); }
         if ((rc = launch_conv<8, 0, 8, EPI_STORE>(p, nj, st))) return rc;
         // ---- L9 up1.up : HB(8) -> F2 [8, 2*H2, 2*W2]
         memset(&pt, 0, sizeof(pt)); pt.Hl = H2; pt.Wl = W2;
@@ -677,7 +706,7 @@ extern "C" int pc_dda_forward(const float* wpack, const float* x, int B, int C, 
             ConvJob& J = p.jobs[j]; set_a(J, bufs[j].F1);
             J.b = bufs[j].F2.p; J.b_cs = bufs[j].F2.cs; J.b_rs = bufs[j].F2.rs; J.b_H = 2 * H2; J.b_W = 2 * W2;
             J.b_oy = (Hv - 2 * H2) / 2; J.b_ox = (Wv - 2 * W2) / 2;
-            J.w = W_(js(j), 10); set_out(J, bufs[j].F0);
+            J.w = W_(js(j), 10); J.wtc = WT_(js(j), 10); set_out(J, bufs[j].F0);
         }
         if ((rc = launch_conv<8, 8, 8, EPI_STORE>(p, nj, st))) return rc;
         // ---- L11 up1.conv.3 : F0 -> features (cropped) | logit dot (+sigmoid, cropped)
@@ -685,7 +714,7 @@ extern "C" int pc_dda_forward(const float* wpack, const float* x, int B, int C, 
             reset(Hv, Wv);
             p.crop_y = pad_top; p.crop_x = pad_left; p.crop_H = H; p.crop_W = W;
             for (int j = 0; j < nj; ++j) {
-                ConvJob& J = p.jobs[j]; set_a(J, bufs[j].F0); J.w = W_(js(j), 11);
+                ConvJob& J = p.jobs[j]; set_a(J, bufs[j].F0); J.w = W_(js(j), 11); J.wtc = WT_(js(j), 11);
                 J.out = out + (long long)jb(j) * out_bstride + (long long)(8 * (j % ns)) * out_cstride;
                 J.out_cs = out_cstride; J.out_rs = out_rstride;
                 J.out_vec = (pad_left % 4 == 0) && (out_rstride % 4 == 0) && (out_cstride % 4 == 0) &&
@@ -699,7 +728,7 @@ extern "C" int pc_dda_forward(const float* wpack, const float* x, int B, int C, 
                 const int s = sids[si];
                 const bool last = (si == ns - 1);
                 for (int k = 0; k < nb; ++k) {
-                    ConvJob& J = p.jobs[k]; set_a(J, bufs[k * ns + si].F0); J.w = W_(s, 11);
+                    ConvJob& J = p.jobs[k]; set_a(J, bufs[k * ns + si].F0); J.w = W_(s, 11); J.wtc = WT_(s, 11);
                     // fusion_out_conv weights [sar 0:8 | optical 8:16] + bias; single-modality: own out conv
                     const float* oc = (ns == 2) ? wpack + pack_offset(0, 12) : wpack + pack_offset(s + 1, 12);
                     J.dotw = (ns == 2) ? oc + 8 * si : oc;
@@ -721,7 +750,7 @@ extern "C" int pc_dda_forward(const float* wpack, const float* x, int B, int C, 
 // ---------------------------------------------------------------------------------------------------
 extern "C" int pc_test_conv3x3(const float* a, int cin_a, int a_H, int a_W, int a_oy, int a_ox, int a_reflect,
                                const float* b, int cin_b, int b_H, int b_W, int b_oy, int b_ox, const float* w,
-                               int cout, int H, int W, float* out, float* pool, pc_stream_t stream) {
+                               int cout, int H, int W, float* out, float* pool, const float* wtc, pc_stream_t stream) {
     PC_CHECK_ARG(a && w && out, "null pointer");
     ConvParams p;
     memset(&p, 0, sizeof(p));
@@ -730,7 +759,7 @@ extern "C" int pc_test_conv3x3(const float* a, int cin_a, int a_H, int a_W, int 
     J.a = a; J.a_cs = (long long)a_H * a_W; J.a_rs = a_W; J.a_H = a_H; J.a_W = a_W; J.a_oy = a_oy; J.a_ox = a_ox;
     J.a_reflect = a_reflect; J.a_chmap = 0x03020100u;
     J.b = b; J.b_cs = (long long)b_H * b_W; J.b_rs = b_W; J.b_H = b_H; J.b_W = b_W; J.b_oy = b_oy; J.b_ox = b_ox;
-    J.w = w; J.out = out; J.out_cs = (long long)H * W; J.out_rs = W;
+    J.w = w; J.wtc = wtc; J.out = out; J.out_cs = (long long)H * W; J.out_rs = W;
     J.out_vec = (W % 4 == 0) && (((uintptr_t)out) % 16 == 0);
     J.pool = pool; J.pool_cs = (long long)(H / 2) * (W / 2); J.pool_rs = W / 2;
     cudaStream_t st = (cudaStream_t)stream;

@@ -1,0 +1,40 @@
+// Declarations shared by the SIMT stencil kernels (conv.cu) and the tcgen05 implicit-GEMM kernels (conv_tc.cu).
+#pragma once
+#include "common.cuh"
+
+namespace pc {
+
+constexpr int MAX_JOBS = 8;
+
+enum { EPI_STORE = 0, EPI_POOL = 1, EPI_DOT = 2 };
+
+// One (image, stream) instance of a conv layer.  The input is the channel concatenation of source A (first CIN_A
+// channels; optional reflect folding and plane remap for the first layer) and source B (next CIN_B channels, placed
+// at an offset and zero outside: the zero-padded upsampled branch of an Up block).
+struct ConvJob {
+    const float* a; long long a_cs; int a_rs; int a_H, a_W; int a_oy, a_ox; int a_reflect; unsigned a_chmap;
+    const float* b; long long b_cs; int b_rs; int b_H, b_W; int b_oy, b_ox;
+    const float* w;                      // SIMT: [CIN][9][COUT] then bias[COUT]
+    const float* wtc;                    // tcgen05: pre-split, pre-swizzled image of the layer (conv_tc.cu), or null
+    float* out; long long out_cs; int out_rs; int out_vec;
+    float* pool; long long pool_cs; int pool_rs;
+    const float* dotw;                   // [8] weights + [1] bias of the 1x1 out conv slice (EPI_DOT)
+    const float* dot_in; int dot_in_rs;  // partial logits of the other stream (or null)
+    float* dot_out; int dot_out_rs; int dot_final;
+};
+
+// geometry of one launch of the tensor-core conv (all jobs share it)
+struct TcConvParams {
+    int H, W;                            // virtual image == output extent
+    int crop_y, crop_x, crop_H, crop_W;  // stores go to (y-crop_y, x-crop_x) if inside [0,crop_H)x[0,crop_W)
+    int TR, tiles_x, tiles_y;            // tile = 128 columns x TR rows
+    ConvJob jobs[MAX_JOBS];
+};
+
+// conv_tc.cu
+int conv_tc_layer_floats(int cin);                                              // floats of one layer image
+void conv_tc_pack_layer(const float* flat, int cin, int cout, float* img);       // host: [cin][9][cout]+bias -> image
+bool conv_tc_enabled();
+int launch_conv_tc(int cin_a, int cin_b, int cout, int epi, TcConvParams& p, int njobs, cudaStream_t st);
+
+}  // namespace pc

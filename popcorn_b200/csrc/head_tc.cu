@@ -13,13 +13,12 @@
 // Two CTAs per SM (256 TMEM columns, 84 KB smem each) overlap one tile's epilogue with the other's MMAs.
 // Replaces model/popcorn.py:79-88, 160-190, 195-228 (same contract as head.cu's SIMT kernel).
 #include "head_common.cuh"
+#include "tc_common.cuh"
 
 namespace pc {
 
 constexpr int TM = 128;
-// instruction descriptor, kind::tf32: D=f32 (bits 4-5 = 1), A=B=tf32 (bits 7-9, 10-12 = 2), K-major A and B,
-// N>>3 at bits 17-22, M>>4 at bits 24-28   (cute/arch/mma_sm100_desc.hpp InstrDescriptor)
-constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t IDESC = umma_idesc_tf32(128, 64);
 
 // byte offsets inside the packed TC weight image (host: weights.pack_head_tc)
 constexpr int OFF_W1HI = 0, OFF_W1LO = 8192, OFF_W2HI = 16384, OFF_W2LO = 32768, OFF_W3HI = 49152, OFF_W3LO = 65536;
@@ -29,68 +28,6 @@ constexpr int OFF_MBAR = TC_PACK_BYTES;        // 8-byte mbarrier
 constexpr int OFF_TMEM = OFF_MBAR + 8;         // 4-byte TMEM base address slot
 constexpr int TC_SMEM_BYTES = OFF_TMEM + 8 + 1024;   // + slack to align the base to 1024 B
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
-// start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major, 1) | SBO>>4 [32,46) = 1024 B between 8-row groups |
-// version 1 [46,48) | layout SWIZZLE_128B = 2 [61,64)
-__device__ __forceinline__ uint64_t make_bdesc(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-
-__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}\n"
-        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(IDESC), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t mbar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                 : "r"(taddr)
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-                   "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-                 : "memory");
-}
-
-// bounded spin on an mbarrier phase: a descriptor mistake must trap, never hang the GPU
-__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
-    for (uint32_t spin = 0;; ++spin) {
-        uint32_t done;
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done)
-                     : "r"(mbar), "r"(parity)
-                     : "memory");
-        if (done) return;
-        if (spin > (1u << 26)) __trap();
-    }
-}
-
-// x = hi + lo with hi exactly representable in TF32 (low 13 mantissa bits cleared)
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-    hi = __float_as_uint(x) & 0xFFFFE000u;
-    lo = __float_as_uint(x - __uint_as_float(hi));
-}
-
 // one hidden layer's UMMAs: D[128x64] = A[128xK] * W[64xK]^T, K in steps of 8, three split terms per step
 template <int K>
 __device__ __forceinline__ void issue_layer(uint32_t tD, uint32_t tAhi, uint32_t tAlo, uint32_t sWhi, uint32_t sWlo,
@@ -99,9 +36,9 @@ __device__ __forceinline__ void issue_layer(uint32_t tD, uint32_t tAhi, uint32_t
     for (int j = 0; j < K / 8; ++j) {
         const uint32_t koff = (uint32_t)((j >> 2) * 8192 + (j & 3) * 32);   // 32-float swizzle atoms along K
         const uint64_t bhi = make_bdesc(sWhi + koff), blo = make_bdesc(sWlo + koff);
-        umma_tf32_ts(tD, tAhi + 8 * j, bhi, j > 0 ? 1u : 0u);
-        umma_tf32_ts(tD, tAlo + 8 * j, bhi, 1u);
-        umma_tf32_ts(tD, tAhi + 8 * j, blo, 1u);
+        umma_tf32_ts(tD, tAhi + 8 * j, bhi, IDESC, j > 0 ? 1u : 0u);
+        umma_tf32_ts(tD, tAlo + 8 * j, bhi, IDESC, 1u);
+        umma_tf32_ts(tD, tAhi + 8 * j, blo, IDESC, 1u);
     }
     umma_commit(mbar);
 }
@@ -134,14 +71,8 @@ __global__ void __launch_bounds__(TM, 2) head_tc_kernel(const __grid_constant__ 
 
     for (int i = tid; i < TC_PACK_BYTES / 16; i += TM)
         reinterpret_cast<int4*>(sm)[i] = __ldg(reinterpret_cast<const int4*>(a.pack) + i);
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
+    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 256);
+    if (tid == 0) mbar_init1(mbar);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // weight image (generic stores) -> visible to UMMA
     tc_fence_before();
     __syncthreads();
@@ -257,7 +188,7 @@ __global__ void __launch_bounds__(TM, 2) head_tc_kernel(const __grid_constant__ 
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(256) : "memory");
+    if (warp == 0) tmem_dealloc(tbase, 256);
 }
 
 template <int K1, bool SPARSE>

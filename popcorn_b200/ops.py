@@ -58,7 +58,7 @@ def dda_forward(wpack: torch.Tensor, x: torch.Tensor, pads=(0, 0, 0, 0), mode: i
     ws = (workspace or _ws)
     need = L.pc_dda_workspace_bytes(B, Cc, H + top + bot, W + left + right)
     buf = ws.get(need, x.device)
-    _lib.check(L.pc_dda_forward(wpack.data_ptr(), x.data_ptr(), B, Cc, H, W, x.stride(0), x.stride(1), x.stride(2),
+    _lib.check(L.pc_dda_forward(wpack.data_ptr(), wpack.numel(), x.data_ptr(), B, Cc, H, W, x.stride(0), x.stride(1), x.stride(2),
                                 top, bot, left, right, mode, out.data_ptr(), out.stride(0), out.stride(1),
                                 out.stride(2), buf.data_ptr(), buf.numel(), _stream()), "pc_dda_forward")
     return out

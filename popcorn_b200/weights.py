@@ -48,8 +48,23 @@ def _pad4(t: torch.Tensor) -> torch.Tensor:
     return torch.cat([t, torch.zeros(r, dtype=t.dtype)]) if r else t
 
 
-def pack_dda(sd: Dict[str, torch.Tensor], copy: str) -> torch.Tensor:
-    """One DualStreamUNet copy ('unetmodel' | 'building_extractor') -> flat fp32 CPU tensor."""
+def pack_dda(sd: Dict[str, torch.Tensor], copy: str, tc: bool = True) -> torch.Tensor:
+    """One DualStreamUNet copy ('unetmodel' | 'building_extractor') -> flat fp32 CPU tensor.
+    tc=True appends the tensor-core section (include/popcorn_b200.h "Tensor-core weight section": the 3x3 conv weights
+    pre-split for 3xTF32 and pre-swizzled for tcgen05), which makes pc_dda_forward run its convs on the tensor cores."""
+    flat = _pack_dda_fp32(sd, copy)
+    if not tc:
+        return flat
+    from . import _lib
+    L = _lib.lib()
+    base, n = L.pc_dda_tc_pack_base(), L.pc_dda_tc_pack_floats()
+    out = torch.zeros(base + n, dtype=torch.float32)
+    out[:flat.numel()] = flat
+    _lib.check(L.pc_dda_tc_pack(flat.data_ptr(), out[base:].data_ptr()), "pc_dda_tc_pack")
+    return out
+
+
+def _pack_dda_fp32(sd: Dict[str, torch.Tensor], copy: str) -> torch.Tensor:
     parts = []
     for stream in ("sar_stream", "optical_stream"):
         for kind, pfx, slot in _LAYERS:

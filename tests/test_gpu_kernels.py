@@ -19,39 +19,64 @@ def _pack_conv(w, b):
     return torch.cat([w.permute(1, 2, 3, 0).reshape(-1), b]).contiguous()
 
 
+def _pack_conv_tc(w, b, tc):
+    """tc=True: the layer's tcgen05 weight image (3xTF32 split, SWIZZLE_128B), built by the library's host packer."""
+    if not tc:
+        return None
+    L = _lib.lib()
+    cout, cin = w.shape[:2]
+    flat = _pack_conv(w, b).cpu()
+    img = torch.zeros(L.pc_conv_tc_layer_floats(cin), dtype=torch.float32)
+    _lib.check(L.pc_conv_tc_pack_layer(flat.data_ptr(), cin, cout, img.data_ptr()))
+    return img.cuda()
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+TC = pytest.mark.parametrize("tc", [False, True], ids=["simt", "tcgen05"])
+
+
 @pytest.mark.parametrize("cin,cout", [(2, 8), (4, 8), (8, 8), (8, 16), (16, 16)])
-@pytest.mark.parametrize("H,W", [(64, 64), (37, 53), (32, 100)])
-def test_conv3x3_bias_relu(cin, cout, H, W):
+@pytest.mark.parametrize("H,W", [(64, 64), (37, 53), (32, 100), (70, 300)])
+@TC
+def test_conv3x3_bias_relu(cin, cout, H, W, tc):
     g = torch.Generator().manual_seed(cin * 100 + cout + H)
     x = torch.randn(cin, H, W, generator=g).cuda()
     w = (torch.randn(cout, cin, 3, 3, generator=g) * 0.3).cuda()
     b = torch.randn(cout, generator=g).cuda()
     out = torch.full((cout, H, W), float("nan"), device="cuda")
+    wtc = _pack_conv_tc(w, b, tc)
     _lib.check(_lib.lib().pc_test_conv3x3(x.data_ptr(), cin, H, W, 0, 0, 0, None, 0, 0, 0, 0, 0,
-                                          _pack_conv(w, b).data_ptr(), cout, H, W, out.data_ptr(), None, _st()))
+                                          _pack_conv(w, b).data_ptr(), cout, H, W, out.data_ptr(), None, _p(wtc), _st()))
     ref = F.relu(F.conv2d(x[None].cpu(), w.cpu(), b.cpu(), padding=1))[0]
     assert torch.allclose(out.cpu(), ref, rtol=1e-4, atol=1e-4), float((out.cpu() - ref).abs().max())
 
 
 @pytest.mark.parametrize("c", [8, 16])
-@pytest.mark.parametrize("H,W", [(64, 64), (37, 52), (50, 36)])
-def test_conv3x3_fused_maxpool(c, H, W):
+@pytest.mark.parametrize("H,W", [(64, 64), (37, 52), (50, 36), (66, 260)])
+@TC
+def test_conv3x3_fused_maxpool(c, H, W, tc):
     g = torch.Generator().manual_seed(c + H)
     x = torch.randn(c, H, W, generator=g).cuda()
     w = (torch.randn(c, c, 3, 3, generator=g) * 0.3).cuda()
     b = torch.randn(c, generator=g).cuda()
     out = torch.empty(c, H, W, device="cuda")
     pool = torch.full((c, H // 2, W // 2), float("nan"), device="cuda")
+    wtc = _pack_conv_tc(w, b, tc)
     _lib.check(_lib.lib().pc_test_conv3x3(x.data_ptr(), c, H, W, 0, 0, 0, None, 0, 0, 0, 0, 0,
-                                          _pack_conv(w, b).data_ptr(), c, H, W, out.data_ptr(), pool.data_ptr(), _st()))
+                                          _pack_conv(w, b).data_ptr(), c, H, W, out.data_ptr(), pool.data_ptr(), _p(wtc),
+                                          _st()))
     ref = F.relu(F.conv2d(x[None].cpu(), w.cpu(), b.cpu(), padding=1))
     assert torch.allclose(out.cpu(), ref[0], rtol=1e-4, atol=1e-4)
     assert torch.allclose(pool.cpu(), F.max_pool2d(ref, 2)[0], rtol=1e-4, atol=1e-4)
 
 
 @pytest.mark.parametrize("ca,cb,cout", [(16, 16, 8), (8, 8, 8)])
-@pytest.mark.parametrize("H,W", [(64, 64), (37, 53)])
-def test_conv3x3_concat_with_offset_zero_pad(ca, cb, cout, H, W):
+@pytest.mark.parametrize("H,W", [(64, 64), (37, 53), (41, 259)])
+@TC
+def test_conv3x3_concat_with_offset_zero_pad(ca, cb, cout, H, W, tc):
     """Up block: cat[skip, F.pad(upsampled)] -> conv (networks.py:309-319) without materialising either."""
     g = torch.Generator().manual_seed(ca + H)
     a = torch.randn(ca, H, W, generator=g).cuda()
@@ -61,26 +86,29 @@ def test_conv3x3_concat_with_offset_zero_pad(ca, cb, cout, H, W):
     bias = torch.randn(cout, generator=g).cuda()
     dy, dx = H - bH, W - bW
     out = torch.empty(cout, H, W, device="cuda")
+    wtc = _pack_conv_tc(w, bias, tc)
     _lib.check(_lib.lib().pc_test_conv3x3(a.data_ptr(), ca, H, W, 0, 0, 0, bsrc.data_ptr(), cb, bH, bW, dy // 2, dx // 2,
-                                          _pack_conv(w, bias).data_ptr(), cout, H, W, out.data_ptr(), None, _st()))
+                                          _pack_conv(w, bias).data_ptr(), cout, H, W, out.data_ptr(), None, _p(wtc), _st()))
     bp = F.pad(bsrc.cpu(), (dx // 2, dx - dx // 2, dy // 2, dy - dy // 2))
     ref = F.relu(F.conv2d(torch.cat([a.cpu(), bp])[None], w.cpu(), bias.cpu(), padding=1))[0]
     assert torch.allclose(out.cpu(), ref, rtol=1e-4, atol=1e-4), float((out.cpu() - ref).abs().max())
 
 
 @pytest.mark.parametrize("pad", [(14, 14), (5, 0), (0, 9)])
-def test_conv3x3_virtual_reflect_padding(pad):
+@TC
+def test_conv3x3_virtual_reflect_padding(pad, tc):
     """Reflect padding folded into the loader (popcorn.py:244, 292): conv over the virtually padded image."""
     g = torch.Generator().manual_seed(3)
-    H, W, cin, cout = 45, 61, 4, 8
+    H, W, cin, cout = 45, 161, 4, 8
     py, px = pad
     x = torch.randn(cin, H, W, generator=g).cuda()
     w = (torch.randn(cout, cin, 3, 3, generator=g) * 0.3).cuda()
     b = torch.randn(cout, generator=g).cuda()
     Hv, Wv = H + 2 * py, W + 2 * px
     out = torch.empty(cout, Hv, Wv, device="cuda")
+    wtc = _pack_conv_tc(w, b, tc)
     _lib.check(_lib.lib().pc_test_conv3x3(x.data_ptr(), cin, H, W, py, px, 1, None, 0, 0, 0, 0, 0,
-                                          _pack_conv(w, b).data_ptr(), cout, Hv, Wv, out.data_ptr(), None, _st()))
+                                          _pack_conv(w, b).data_ptr(), cout, Hv, Wv, out.data_ptr(), None, _p(wtc), _st()))
     xp = F.pad(x[None].cpu(), (px, px, py, py), mode="reflect")
     ref = F.relu(F.conv2d(xp, w.cpu(), b.cpu(), padding=1))[0]
     assert torch.allclose(out.cpu(), ref, rtol=1e-4, atol=1e-4)

@@ -39,10 +39,11 @@ def test_dense_forward_vs_reference_golden(model, name):
 
 
 @pytest.mark.parametrize("copy,mode", [("unetmodel", 0), ("building_extractor", 1)])
-@pytest.mark.parametrize("H,W", [(64, 64), (97, 131), (33, 250), (256, 192)])
-def test_dda_forward_vs_oracle(sd, copy, mode, H, W):
+@pytest.mark.parametrize("H,W", [(64, 64), (97, 131), (33, 250), (256, 192), (150, 530)])
+@pytest.mark.parametrize("tc", [False, True], ids=["simt", "tcgen05"])
+def test_dda_forward_vs_oracle(sd, copy, mode, H, W, tc):
     x = po.synthetic_input(H, W, seed=H * W)
-    pack = weights.pack_dda(sd, copy).cuda()
+    pack = weights.pack_dda(sd, copy, tc=tc).cuda()
     if mode == 0:
         pads = po.feature_padding(H, W, False)
         ref = po.unet_features(sd, x, padding=False)

@@ -91,8 +91,12 @@ def test_get_model_surface():
 
 def test_pack_sizes_agree_with_library(sd):
     L = _lib.lib()
-    p = weights.pack_dda(sd, "unetmodel")
+    p = weights.pack_dda(sd, "unetmodel", tc=False)
     assert p.numel() == L.pc_dda_pack_floats() and p.dtype == torch.float32
+    ptc = weights.pack_dda(sd, "unetmodel")          # fp32 section + tensor-core section (host-side conversion)
+    assert ptc.numel() == L.pc_dda_tc_pack_base() + L.pc_dda_tc_pack_floats()
+    assert L.pc_dda_tc_pack_base() % 64 == 0 and L.pc_dda_tc_pack_base() >= L.pc_dda_pack_floats()
+    assert torch.equal(ptc[:p.numel()], p)
     assert weights.pack_head(sd).numel() == L.pc_head_pack_floats(16)
     assert L.pc_head_pack_floats(8) == 8 * 64 + 64 + 2 * (64 * 64 + 64) + 64 + 4
     assert L.pc_dda_pack_offset(0, 0) == 0 and L.pc_dda_pack_offset(0, 1) == 2 * 9 * 8 + 8
@@ -136,3 +140,33 @@ def test_cpu_tensors_are_rejected_loudly(sd):
         m({"input": torch.zeros(1, 6, 32, 32)}, padding=False)
     with pytest.raises(ValueError):
         m({"input": torch.zeros(6, 32, 32)}, padding=False)
+
+
+@pytest.mark.parametrize("cin,cout", [(2, 8), (4, 8), (8, 16), (16, 16), (32, 8)])
+def test_conv_tc_weight_image_layout(cin, cout):
+    """Host packer of the tcgen05 conv weights (include/popcorn_b200.h "Tensor-core weight section"): de-swizzling the
+    image gives back W_ky[co][kx*cin+ci] with hi + lo == w exactly, hi a TF32 number, zero rows/columns as padding."""
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(cin * 31 + cout)
+    w = torch.randn(cout, cin, 3, 3, generator=g)
+    b = torch.randn(cout, generator=g)
+    flat = torch.cat([w.permute(1, 2, 3, 0).reshape(-1), b]).contiguous()
+    n = L.pc_conv_tc_layer_floats(cin)
+    img = torch.full((n,), float("nan"))
+    _lib.check(L.pc_conv_tc_pack_layer(flat.data_ptr(), cin, cout, img.data_ptr()))
+    krow = (3 * cin + 7) // 8 * 8
+    katoms = (krow + 31) // 32
+    mat = katoms * 16 * 32
+    assert n % 64 == 0 and n >= 6 * mat + 16
+    mats = img[:6 * mat].view(3, 2, katoms, 16, 32)
+    rows = torch.arange(16).view(16, 1)
+    kk = torch.arange(32).view(1, 32)
+    pos = ((kk // 4) ^ (rows % 8)) * 4 + kk % 4                     # Swizzle<3,4,3>
+    de = torch.gather(mats, 4, pos.expand(3, 2, katoms, 16, 32))    # de[ky][h][atom][n][kk]
+    de = de.permute(0, 1, 3, 2, 4).reshape(3, 2, 16, katoms * 32)   # [ky][hi|lo][n][k]
+    hi, lo = de[:, 0], de[:, 1]
+    want = torch.zeros(3, 16, katoms * 32)
+    want[:, :cout, :3 * cin] = w.permute(2, 0, 3, 1).reshape(3, cout, 3 * cin)   # [ky][co][kx*cin+ci]
+    assert torch.equal(hi + lo, want)
+    assert torch.equal(hi.view(torch.int32) & 0x1FFF, torch.zeros_like(hi, dtype=torch.int32))
+    assert torch.equal(img[6 * mat: 6 * mat + cout], b) and float(img[6 * mat + cout: 6 * mat + 16].abs().sum()) == 0

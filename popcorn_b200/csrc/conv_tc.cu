@@ -64,7 +64,7 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const ConvJob& job = p.jobs[blockIdx.y];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = uniform_warp_idx();
     const float* bias = reinterpret_cast<const float*>(sm + G::OFF_BIAS);
     const uint32_t mbar = smem_u32(sm + G::OFF_MBAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + G::OFF_TMEM);
@@ -255,7 +255,7 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
             tc_wait_st();
             tc_fence_before();
             __syncthreads();
-            if (tid == 0) { tc_fence_after(); issue_row(r); }
+            if (warp == 0 && elect_one()) { tc_fence_after(); issue_row(r); }
             if (r < nrows) load_row(r + 1);     // in flight while the UMMAs and the epilogue below run
             if (r >= 2) epilogue(r - 2);
         }

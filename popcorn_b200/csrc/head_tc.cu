@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(TM, 2) head_tc_kernel(const __grid_constant__ 
     const float* b1 = vec, *b2 = vec + 64, *b3 = vec + 128, *w4 = vec + 192, *b4 = vec + 256;
     const uint32_t mbar = smem_u32(sm + OFF_MBAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + OFF_TMEM);
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = uniform_warp_idx();
 
     for (int i = tid; i < TC_PACK_BYTES / 16; i += TM)
         reinterpret_cast<int4*>(sm)[i] = __ldg(reinterpret_cast<const int4*>(a.pack) + i);
@@ -138,21 +138,21 @@ __global__ void __launch_bounds__(TM, 2) head_tc_kernel(const __grid_constant__ 
         tc_wait_st();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) { tc_fence_after(); issue_layer<K1>(tD, tAhi, tAlo, sW + OFF_W1HI, sW + OFF_W1LO, mbar); }
+        if (warp == 0 && elect_one()) { tc_fence_after(); issue_layer<K1>(tD, tAhi, tAlo, sW + OFF_W1HI, sW + OFF_W1LO, mbar); }
         mbar_wait(mbar, phase); phase ^= 1;
         tc_fence_after();
         epilogue_hidden(tD + lane_off, tAhi + lane_off, tAlo + lane_off, b1);
         tc_wait_st();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) { tc_fence_after(); issue_layer<HN>(tD, tAhi, tAlo, sW + OFF_W2HI, sW + OFF_W2LO, mbar); }
+        if (warp == 0 && elect_one()) { tc_fence_after(); issue_layer<HN>(tD, tAhi, tAlo, sW + OFF_W2HI, sW + OFF_W2LO, mbar); }
         mbar_wait(mbar, phase); phase ^= 1;
         tc_fence_after();
         epilogue_hidden(tD + lane_off, tAhi + lane_off, tAlo + lane_off, b2);
         tc_wait_st();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) { tc_fence_after(); issue_layer<HN>(tD, tAhi, tAlo, sW + OFF_W3HI, sW + OFF_W3LO, mbar); }
+        if (warp == 0 && elect_one()) { tc_fence_after(); issue_layer<HN>(tD, tAhi, tAlo, sW + OFF_W3HI, sW + OFF_W3LO, mbar); }
         mbar_wait(mbar, phase); phase ^= 1;
         tc_fence_after();
         // ---- output layer on the CUDA cores: o = b4 + sum_n relu(D3[n] + b3[n]) * w4[n] ----

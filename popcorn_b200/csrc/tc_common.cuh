@@ -13,6 +13,19 @@ namespace pc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a fully converged warp.  UMMAs must be issued under elect.sync: ptxas then knows the region is
+// single-lane and feeds UTCHMMA from uniform registers directly; under a plain `tid == 0` branch it wraps EVERY
+// tcgen05.mma in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop (~10 instructions, ~50 cycles per MMA).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+// warp index as a value the compiler knows to be warp-uniform
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 // instruction descriptor, kind::tf32: D=f32 (bits 4-5 = 1), A=B=tf32 (bits 7-9, 10-12 = 2), K-major A and B,
 // N>>3 at bits 17-22, M>>4 at bits 24-28   (cute/arch/mma_sm100_desc.hpp InstrDescriptor)
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(uint32_t M, uint32_t N) {

@@ -467,17 +467,20 @@ static EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
-// [C][H][W] fp32 planes (row stride rs, plane stride cs, in floats) -> 3-D tensor map with a [cc][34][36] box
-static bool make_tmap(CUtensorMap* tm, const float* ptr, int C, int H, int W, int rs, long long cs, int cc) {
+bool make_tmap3d(CUtensorMap* tm, const float* ptr, int C, int H, int W, int rs, long long cs, int boxw, int boxh, int boxc) {
     EncodeTiledFn fn = encode_tiled_fn();
-    if (!fn || !ptr || (((uintptr_t)ptr) & 15) || (rs & 3) || (cs & 3) || C < cc) return false;
+    if (!fn || !ptr || (((uintptr_t)ptr) & 15) || (rs & 3) || (cs & 3) || C < boxc) return false;
     cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C};
     cuuint64_t strides[2] = {(cuuint64_t)rs * 4, (cuuint64_t)cs * 4};
-    cuuint32_t box[3] = {(cuuint32_t)SPITCH, (cuuint32_t)SROWS, (cuuint32_t)cc};
+    cuuint32_t box[3] = {(cuuint32_t)boxw, (cuuint32_t)boxh, (cuuint32_t)boxc};
     cuuint32_t estr[3] = {1, 1, 1};
     return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), dims, strides, box, estr,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// the SIMT kernels stage [cc][34][40] boxes
+static bool make_tmap(CUtensorMap* tm, const float* ptr, int C, int H, int W, int rs, long long cs, int cc) {
+    return make_tmap3d(tm, ptr, C, H, W, rs, cs, SPITCH, SROWS, cc);
 }
 
 template <int CIN_A, int CIN_B, int COUT, int EPI, bool X2, bool TMA>
@@ -505,15 +508,21 @@ static int launch_conv(ConvParams& p, int njobs, cudaStream_t st) {
         snprintf(nm, sizeof(nm), "conv3x3<%d,%d,%d,%s>", CIN_A, CIN_B, COUT, EPI == EPI_STORE ? "store" : EPI == EPI_POOL ? "pool" : "dot");
         return prof_register(nm);
     }();
-    // tensor-core path (conv_tc.cu): every job carries a pre-swizzled weight image
-    bool tc = conv_tc_enabled();
-    for (int j = 0; tc && j < njobs; ++j) tc = p.jobs[j].wtc != nullptr;
+    // tensor-core path (conv_tc.cu): every job carries a pre-swizzled weight image and its sources can be read by TMA
+    // (plain planes: not the reflect-padded, channel-remapped first layer, which stays on the fp32 stencil)
+    bool tc = conv_tc_enabled() && CIN_A >= 8;
+    for (int j = 0; tc && j < njobs; ++j) tc = p.jobs[j].wtc != nullptr && !p.jobs[j].a_reflect;
     if (tc) {
         TcConvParams tp;
         memset(&tp, 0, sizeof(tp));
         tp.H = p.H; tp.W = p.W; tp.crop_y = p.crop_y; tp.crop_x = p.crop_x; tp.crop_H = p.crop_H; tp.crop_W = p.crop_W;
-        for (int j = 0; j < njobs; ++j) tp.jobs[j] = p.jobs[j];
-        return launch_conv_tc(CIN_A, CIN_B, COUT, EPI, tp, njobs, st);
+        for (int j = 0; tc && j < njobs; ++j) {
+            const ConvJob& J = p.jobs[j];
+            tp.jobs[j] = J;
+            tc = make_tmap3d(&tp.tmA[j], J.a, CIN_A, J.a_H, J.a_W, J.a_rs, J.a_cs, TC_BOXW, 1, CIN_A);
+            if (tc && CIN_B > 0) tc = make_tmap3d(&tp.tmB[j], J.b, CIN_B, J.b_H, J.b_W, J.b_rs, J.b_cs, TC_BOXW, 1, CIN_B);
+        }
+        if (tc) return launch_conv_tc(CIN_A, CIN_B, COUT, EPI, tp, njobs, st);
     }
     constexpr int CC = conv_cc<CIN_A + CIN_B>();
     // TMA staging needs plain (non-reflected, identity-channel) 16-byte-aligned sources: every layer but the first

@@ -1,10 +1,13 @@
 // Declarations shared by the SIMT stencil kernels (conv.cu) and the tcgen05 implicit-GEMM kernels (conv_tc.cu).
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace pc {
 
 constexpr int MAX_JOBS = 8;
+constexpr int TC_BOXW = 136;         // floats per staged row: box starts at x0-4 (TMA needs a 16-byte aligned inner coordinate), 128 px + halo
 
 enum { EPI_STORE = 0, EPI_POOL = 1, EPI_DOT = 2 };
 
@@ -24,12 +27,18 @@ struct ConvJob {
 };
 
 // geometry of one launch of the tensor-core conv (all jobs share it)
-struct TcConvParams {
+struct alignas(64) TcConvParams {
+    CUtensorMap tmA[MAX_JOBS];           // TMA descriptors of the jobs' sources: box = [channels][1 row][TC_BOXW floats]
+    CUtensorMap tmB[MAX_JOBS];
     int H, W;                            // virtual image == output extent
     int crop_y, crop_x, crop_H, crop_W;  // stores go to (y-crop_y, x-crop_x) if inside [0,crop_H)x[0,crop_W)
     int TR, tiles_x, tiles_y;            // tile = 128 columns x TR rows
     ConvJob jobs[MAX_JOBS];
 };
+
+// conv.cu: [C][H][W] fp32 planes (row stride rs, plane stride cs, in floats) -> 3-D tensor map with a [boxc][boxh][boxw] box;
+// false when the source does not meet TMA's alignment rules (16-byte base and strides)
+bool make_tmap3d(CUtensorMap* tm, const float* ptr, int C, int H, int W, int rs, long long cs, int boxw, int boxh, int boxc);
 
 // conv_tc.cu
 int conv_tc_layer_floats(int cin);                                              // floats of one layer image

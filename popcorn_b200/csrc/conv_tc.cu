@@ -1,24 +1,31 @@
 // 3x3 convolutions of the DDA UNet as implicit GEMMs on the 5th-gen tensor cores (tcgen05 + TMEM), 3xTF32.
 //
-// Mapping (per CTA: a tile of 128 columns x TR rows of one (image, stream) job, 128 threads):
-//   * UMMA M = 128 = the 128 pixels of one image row segment; thread t owns pixel x0+t == TMEM lane t;
-//   * K of one input row = (kx, ci): the row is written to TMEM THREE times, shifted by -1/0/+1 pixel (the thread
-//     loads its own pixel coalesced, gets the neighbours by warp shuffle; lanes 0/31 load the halo pixel), each
-//     value split x = hi + lo (hi = top 19 bits = exact TF32) -> A operand [128 x 3*Cin] hi and lo, in TMEM;
+// Mapping (one persistent CTA per SM walks tiles of 128 columns x TR rows of one (image, stream) job):
+//   * UMMA M = 128 = the 128 pixels of one image row segment; pixel x0+t == TMEM lane t;
+//   * K of one input row = (kx, ci): the row is written to TMEM THREE times, shifted by -1/0/+1 pixel, each value
+//     split x = hi + lo (hi = top 19 bits = exact TF32) -> A operand [128 x 3*Cin] hi and lo, in TMEM;
 //   * the ky shift is NOT a lane shift: input row r feeds output rows r+1 (ky=0), r (ky=1), r-1 (ky=2), i.e. three
-//     different fp32 accumulators D[128 x 16] that live in a 4-slot TMEM ring (slot = output row & 3);
+//     different fp32 accumulators D[128 x 16] that live in an 8-slot TMEM ring (slot = running output row % 8);
 //   * B operand = the folded weights W_ky[co][(kx,ci)] (N = 16: Cout 16, or Cout 8 zero-padded), pre-split and
 //     pre-swizzled on the host (K-major SWIZZLE_128B), copied to shared memory once per CTA;
-//   * per input row, one thread issues 3 (ky) x 3*Cin/8 (k-steps) x 3 (hi*hi + lo*hi + hi*lo) tcgen05.mma
-//     kind::tf32 and commits them to an mbarrier; while they run, the CTA prefetches the next input row into
-//     registers and runs the epilogue of output row r-2 (tcgen05.ld -> bias + ReLU -> store | 2x2 maxpool |
-//     1x1 logit dot + sigmoid).  Several CTAs per SM (TMEM 128/256 columns each) keep the tensor pipe busy.
+//   * per input row: 3 (ky) x 3*Cin/8 (k-steps) x 3 (hi*hi + lo*hi + hi*lo) tcgen05.mma kind::tf32, N/2 = 8 cycles
+//     each (tools/probe/umma_probe.cu) -> 27*Cin cycles per 128 pixels.
+// Warp-specialised pipeline (576 threads), every hand-off is an mbarrier, nothing is block-synchronous:
+//   warp 17     TMA     : one lane streams input rows (all channels, 136 floats: 128 px + halo, zero-filled outside
+//                         the source = conv padding / the Up block's F.pad) into an NS-deep shared-memory ring
+//   warps 0-7   stagers : two groups alternate rows: wait s_full -> 3*Cin ld.shared (x-1, x, x+1) -> split ->
+//                         tcgen05.st into one of NA A buffers -> arrive s_empty, full_a
+//   warp 16     MMA     : one lane waits full_a (+ d_empty for the accumulator slot a row opens), issues the row's
+//                         UMMAs, commits to empty_a and, for the output row this input row completes, to d_full
+//   warps 8-15  epilogue: two groups alternate row pairs: wait d_full -> tcgen05.ld -> arrive d_empty -> bias + ReLU
+//                         -> store | 2x2 maxpool | 1x1 logit dot + sigmoid (+ crop)
 // Precision: ~21-bit operands, fp32 accumulation — what the 1e-2 per-pixel bar needs; plain
-// single-pass TF32 fails it.  The CUDA cores only move data: Cin loads + 2*Cin shuffles + 3*Cin splits per pixel
-// instead of 9*Cin*Cout FMAs.
+// single-pass TF32 fails it.  The CUDA cores only move data (3*Cin shared loads + splits per pixel instead of
+// 9*Cin*Cout FMAs), so the layers become HBM-bound ((Cin+Cout)*4 B per pixel).
+// The reflect-padded, channel-remapped first layer (Cin 2 | 4, HBM-bound at fp32 SIMT) stays on conv.cu's stencil.
 //
 // Replaces model/DDA_model/utils/networks.py:253-271 (DoubleConv: Conv2d 3x3 pad 1 + BatchNorm2d(eval) + ReLU),
-// :284-295 (MaxPool2d in Down), :318 (skip concat), :323-330 (OutConv) and popcorn.py:244,296-300,317-320.
+// :284-295 (MaxPool2d in Down), :318 (skip concat), :323-330 (OutConv) and popcorn.py:317-320.
 #include <stdlib.h>
 #include <string.h>
 
@@ -27,9 +34,13 @@
 
 namespace pc {
 
-constexpr int TCM = 128;           // pixels per UMMA = threads per CTA
+constexpr int TCM = 128;           // pixels per UMMA
 constexpr int TCN = 16;            // UMMA N (output channels, zero-padded)
-constexpr int DSLOTS = 4;          // accumulator ring
+constexpr int ND = 8;              // accumulator ring (output rows in flight)
+constexpr int NGROUP = 2;          // stager groups / epilogue groups (4 warps each: one per TMEM lane quarter)
+constexpr int WS_THREADS = (4 * NGROUP * 2 + 2) * 32;    // stagers + epilogue + MMA warp + TMA warp
+constexpr int W_EPI0 = 4 * NGROUP, W_MMA = 8 * NGROUP, W_TMA = 8 * NGROUP + 1;
+constexpr int TMEM_ALL = 512;
 
 template <int CIN>
 struct TcGeom {
@@ -39,25 +50,38 @@ struct TcGeom {
     static constexpr int BMAT = KATOMS * TCN * 128;             // bytes of one swizzled [16 x KROW] matrix
     static constexpr int OFF_BIAS = 6 * BMAT;                   // matrices: [ky][hi, lo]
     static constexpr int IMG_BYTES = OFF_BIAS + 64;             // + bias[16]
-    static constexpr int A_COLS = 2 * KROW;                     // hi at [0, KROW), lo at [KROW, 2*KROW)
-    static constexpr int D_COL0 = A_COLS;                       // 4 accumulator slots of 16 columns
-    static constexpr int TMEM_COLS = (A_COLS + DSLOTS * TCN) <= 128 ? 128 : 256;
-    static constexpr int CTAS = 512 / TMEM_COLS;                // resident CTAs per SM (TMEM is the limit)
-    static constexpr int OFF_MBAR = IMG_BYTES;
-    static constexpr int OFF_TMEM = OFF_MBAR + 8;
-    // shared-memory request: padded so that no more than CTAS CTAs fit on an SM (a CTA beyond the TMEM capacity
-    // would block in tcgen05.alloc while holding an SM slot)
-    static constexpr int SMEM_MIN = 227 * 1024 / (CTAS + 1) + 1024;
-    static constexpr int SMEM_BYTES = (OFF_TMEM + 8 + 1024) > SMEM_MIN ? (OFF_TMEM + 8 + 1024) : SMEM_MIN;
-    static_assert(A_COLS + DSLOTS * TCN <= 256, "TMEM budget");
-    static_assert(A_COLS % 16 == 0, "accumulator slots must start on a 16-column boundary");
+    static constexpr int A_COLS = 2 * KROW;                     // one A buffer: hi at [0, KROW), lo at [KROW, 2*KROW)
+    static constexpr int NA_FIT = (TMEM_ALL - ND * TCN) / A_COLS;
+    static constexpr int NA = NA_FIT >= 4 ? 4 : 2;              // A buffers (power of two)
+    static constexpr int D_COL0 = NA * A_COLS;                  // accumulator slots of 16 columns
+    static constexpr int STAGE_BYTES = CIN * TC_BOXW * 4;       // one input row, all channels
+    static constexpr int NS = CIN <= 8 ? 16 : CIN <= 16 ? 8 : 5;   // shared-memory ring depth (~70-87 KB in flight per SM)
+    static constexpr int OFF_STAGE = (IMG_BYTES + 127) / 128 * 128;
+    static constexpr int OFF_BARS = OFF_STAGE + NS * STAGE_BYTES;   // s_full[NS] s_empty[NS] full_a[NA] empty_a[NA] d_full[ND] d_empty[ND]
+    static constexpr int NBARS = 2 * NS + 2 * NA + 2 * ND;
+    static constexpr int OFF_TMEM = OFF_BARS + 8 * NBARS;
+    static constexpr int SMEM_NEED = OFF_TMEM + 16 + 1024;
+    // > half of the SM's shared memory: exactly one CTA per SM (it owns all 512 TMEM columns)
+    static constexpr int SMEM_BYTES = SMEM_NEED > 116 * 1024 ? SMEM_NEED : 116 * 1024;
+    static_assert(NA_FIT >= 2, "TMEM budget");
+    static_assert(D_COL0 % 16 == 0 && D_COL0 + ND * TCN <= TMEM_ALL, "accumulator ring placement");
+    static_assert(STAGE_BYTES % 128 == 0 && SMEM_BYTES <= 227 * 1024, "shared memory layout");
 };
 
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int x, int y, int c, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(tm), "r"(x), "r"(y), "r"(c), "r"(bar) : "memory");
+}
+
 template <int CIN_A, int CIN_B, int COUT, int EPI>
-__global__ void __launch_bounds__(TCM, TcGeom<CIN_A + CIN_B>::CTAS)
+__global__ void __launch_bounds__(WS_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
     constexpr int CIN = CIN_A + CIN_B;
     using G = TcGeom<CIN>;
+    constexpr int NA = G::NA, NS = G::NS;
     constexpr uint32_t IDESC = umma_idesc_tf32(TCM, TCN);
     constexpr unsigned FULL = 0xffffffffu;
 
@@ -66,208 +90,206 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
     const ConvJob& job = p.jobs[blockIdx.y];
     const int tid = threadIdx.x, lane = tid & 31, warp = uniform_warp_idx();
     const float* bias = reinterpret_cast<const float*>(sm + G::OFF_BIAS);
-    const uint32_t mbar = smem_u32(sm + G::OFF_MBAR);
+    const uint32_t bars = smem_u32(sm + G::OFF_BARS);
+    auto s_full = [&](int i) { return bars + 8u * (uint32_t)i; };
+    auto s_empty = [&](int i) { return bars + 8u * (uint32_t)(NS + i); };
+    auto full_a = [&](int i) { return bars + 8u * (uint32_t)(2 * NS + i); };
+    auto empty_a = [&](int i) { return bars + 8u * (uint32_t)(2 * NS + NA + i); };
+    auto d_full = [&](int i) { return bars + 8u * (uint32_t)(2 * NS + 2 * NA + i); };
+    auto d_empty = [&](int i) { return bars + 8u * (uint32_t)(2 * NS + 2 * NA + ND + i); };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + G::OFF_TMEM);
 
-    for (int i = tid; i < G::IMG_BYTES / 16; i += TCM)
+    for (int i = tid; i < G::IMG_BYTES / 16; i += WS_THREADS)
         reinterpret_cast<int4*>(sm)[i] = __ldg(reinterpret_cast<const int4*>(job.wtc) + i);
-    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), G::TMEM_COLS);
-    if (tid == 0) mbar_init1(mbar);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // weight image (generic stores) -> visible to UMMA
+    if (warp == W_MMA) tmem_alloc(smem_u32(tmem_slot), TMEM_ALL);
+    if (tid == 0) {
+        for (int i = 0; i < NS; ++i) { mbar_init(s_full(i), 1); mbar_init(s_empty(i), 4); }     // 4 = the stager warps of a group
+        for (int i = 0; i < NA; ++i) { mbar_init(full_a(i), 4); mbar_init(empty_a(i), 1); }
+        for (int i = 0; i < ND; ++i) { mbar_init(d_full(i), 1); mbar_init(d_empty(i), 4); }     // 4 = the epilogue warps of a group
+        mbar_init_fence();
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // weights + barriers (generic stores) -> visible to UMMA / TMA
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tbase = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;          // this warp's 32 TMEM lanes
-    const uint32_t tAhi = tbase, tAlo = tbase + G::KROW, tD = tbase + G::D_COL0;
-    const uint32_t sW = smem_u32(sm);
-    uint32_t phase = 0;
+    const uint32_t tD = tbase + G::D_COL0;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;    // a warp may touch TMEM lanes 32*(warp%4) .. +31
+    const int px = (warp & 3) * 32 + lane;                          // pixel of this thread inside a tile row
 
-    const int H = p.H, W = p.W;
-    float dotw[EPI == EPI_DOT ? 8 : 1];
-    float dotb = 0.f;
-    if (EPI == EPI_DOT) {
-#pragma unroll
-        for (int o = 0; o < 8; ++o) dotw[o] = __ldg(job.dotw + o);
-        dotb = __ldg(job.dotw + 8);
-    }
-
+    const int H = p.H, W = p.W, TR = p.TR;
     const int ntiles = p.tiles_x * p.tiles_y;
-#pragma unroll 1
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
-        const int x0 = tx * TCM, y0 = ty * p.TR;
-        const int nrows = (H - y0) < p.TR ? (H - y0) : p.TR;
-        const int vx = x0 + tid;
-        // ---- column bookkeeping of this thread: own pixel and (lanes 0 / 31) the halo pixel of its warp ----
-        const bool is_edge = (lane == 0) || (lane == 31);
-        const int vxe = (lane == 0) ? vx - 1 : vx + 1;
-        const bool in_x = vx < W, in_xe = is_edge && vxe >= 0 && vxe < W;
-        int a_sx = vx - job.a_ox, a_sxe = vxe - job.a_ox;
-        bool a_ok = in_x, a_oke = in_xe;
-        if (job.a_reflect) {
-            a_sx = a_sx < 0 ? -a_sx : a_sx;     a_sx = a_sx >= job.a_W ? 2 * (job.a_W - 1) - a_sx : a_sx;
-            a_sxe = a_sxe < 0 ? -a_sxe : a_sxe; a_sxe = a_sxe >= job.a_W ? 2 * (job.a_W - 1) - a_sxe : a_sxe;
-        } else {
-            a_ok = a_ok && a_sx >= 0 && a_sx < job.a_W;
-            a_oke = a_oke && a_sxe >= 0 && a_sxe < job.a_W;
-        }
-        const int b_sx = vx - job.b_ox, b_sxe = vxe - job.b_ox;
-        const bool b_ok = CIN_B > 0 && in_x && b_sx >= 0 && b_sx < job.b_W;
-        const bool b_oke = CIN_B > 0 && in_xe && b_sxe >= 0 && b_sxe < job.b_W;
+    auto tile_rows = [&](int tile) { const int y0 = (tile / p.tiles_x) * TR; return (H - y0) < TR ? (H - y0) : TR; };
 
-        float v[CIN], e[CIN];     // input row in flight: own pixel / halo pixel (lanes 0, 31)
-        auto load_row = [&](int r) {
-            const int vy = y0 + r;
-            const bool rin = vy >= 0 && vy < H;
-            {
-                int sy = vy - job.a_oy;
-                bool rok = rin;
-                if (job.a_reflect) { sy = sy < 0 ? -sy : sy; sy = sy >= job.a_H ? 2 * (job.a_H - 1) - sy : sy; }
-                else rok = rok && sy >= 0 && sy < job.a_H;
-                const float* rowp = job.a + (rok ? (long long)sy * job.a_rs : 0ll);
-                const bool ok = rok && a_ok, oke = rok && a_oke;
-#pragma unroll
-                for (int c = 0; c < CIN_A; ++c) {
-                    int plane = c;
-                    if (CIN_A <= 4) plane = (job.a_chmap >> (8 * c)) & 0xff;
-                    const float* pp = rowp + plane * job.a_cs;
-                    v[c] = 0.f; e[c] = 0.f;
-                    if (ok) v[c] = __ldg(pp + a_sx);
-                    if (oke) e[c] = __ldg(pp + a_sxe);
-                }
-            }
-            if (CIN_B > 0) {
-                const int sy = vy - job.b_oy;
-                const bool rok = rin && sy >= 0 && sy < job.b_H;
-                const float* rowp = job.b + (rok ? (long long)sy * job.b_rs : 0ll);
-                const bool ok = rok && b_ok, oke = rok && b_oke;
-#pragma unroll
-                for (int c = 0; c < CIN_B; ++c) {
-                    const float* pp = rowp + c * job.b_cs;
-                    v[CIN_A + c] = 0.f; e[CIN_A + c] = 0.f;
-                    if (ok) v[CIN_A + c] = __ldg(pp + b_sx);
-                    if (oke) e[CIN_A + c] = __ldg(pp + b_sxe);
-                }
-            }
-        };
-        // registers -> TMEM: A[lane][kx*CIN + ci] = in[ci][x + kx - 1], split into hi / lo
-        auto stage_row = [&]() {
+    if (warp < W_EPI0) {
+        // =========================== stagers: shared-memory row -> TMEM (A operand) ===========================
+        const int group = warp >> 2;
+        int total = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) total += tile_rows(t) + 2;
+        const float* stage0 = reinterpret_cast<const float*>(sm + G::OFF_STAGE) + px + 3;   // box column 3 = image column x-1
+#pragma unroll 1
+        for (int i = group; i < total; i += NGROUP) {
+            const int s = i % NS, buf = i & (NA - 1), n = i / NA;
+            mbar_wait_sleep(s_full(s), (uint32_t)(i / NS) & 1u);                       // the row has landed
+            if (n >= 1) mbar_wait_sleep(empty_a(buf), (uint32_t)(n - 1) & 1u);        // UMMAs that read this A buffer are done
+            tc_fence_after();
+            const float* st = stage0 + s * (G::STAGE_BYTES / 4);
+            const uint32_t tA = tbase + (uint32_t)buf * G::A_COLS + lane_off;
 #pragma unroll
             for (int j = 0; j < G::KSTEPS; ++j) {
                 uint32_t hi[8], lo[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    const int col = 8 * j + q;
-                    float val = 0.f;
-                    if (col < 3 * CIN) {
-                        const int kx = col / CIN, ci = col % CIN;
-                        if (kx == 1) {
-                            val = v[ci];
-                        } else if (kx == 0) {
-                            const float t = __shfl_up_sync(FULL, v[ci], 1);
-                            val = lane == 0 ? e[ci] : t;
-                        } else {
-                            const float t = __shfl_down_sync(FULL, v[ci], 1);
-                            val = lane == 31 ? e[ci] : t;
-                        }
-                    }
+                    const int col = 8 * j + q;                                          // A column = kx * CIN + ci
+                    const float val = (col < 3 * CIN) ? st[(col % CIN) * TC_BOXW + col / CIN] : 0.f;
                     split_tf32(val, hi[q], lo[q]);
                 }
-                tmem_st8(tAhi + lane_off + 8 * j, hi);
-                tmem_st8(tAlo + lane_off + 8 * j, lo);
+                tmem_st8(tA + 8 * j, hi);
+                tmem_st8(tA + G::KROW + 8 * j, lo);
             }
-        };
-        // all UMMAs of input row r (tile-local, -1 .. nrows), issued by one thread
-        auto issue_row = [&](int r) {
-#pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-                const int y = r - ky + 1;
-                if (y < 0 || y >= nrows) continue;
-                const uint32_t d = tD + TCN * (uint32_t)(y & (DSLOTS - 1));
-                const uint32_t whi = sW + (2 * ky) * G::BMAT, wlo = sW + (2 * ky + 1) * G::BMAT;
-#pragma unroll
-                for (int j = 0; j < G::KSTEPS; ++j) {
-                    const uint32_t koff = (uint32_t)((j >> 2) * (TCN * 128) + (j & 3) * 32);
-                    const uint64_t bhi = make_bdesc(whi + koff), blo = make_bdesc(wlo + koff);
-                    umma_tf32_ts(d, tAhi + 8 * j, bhi, IDESC, (ky == 0 && j == 0) ? 0u : 1u);   // ky = 0 opens the row
-                    umma_tf32_ts(d, tAlo + 8 * j, bhi, IDESC, 1u);
-                    umma_tf32_ts(d, tAhi + 8 * j, blo, IDESC, 1u);
-                }
-            }
-            umma_commit(mbar);
-        };
-        float prev[EPI == EPI_POOL ? COUT : 1];   // horizontally pooled even row, waiting for the odd row
-        auto epilogue = [&](int y) {
-            uint32_t d[COUT];
-            if (COUT == 16) tmem_ld16(tD + lane_off + TCN * (uint32_t)(y & (DSLOTS - 1)), reinterpret_cast<uint32_t(&)[16]>(d));
-            else tmem_ld8(tD + lane_off + TCN * (uint32_t)(y & (DSLOTS - 1)), reinterpret_cast<uint32_t(&)[8]>(d));
-            tc_wait_ld();
-            float acc[COUT];
-#pragma unroll
-            for (int o = 0; o < COUT; ++o) acc[o] = fmaxf(__uint_as_float(d[o]) + bias[o], 0.f);
-            const int oy = y0 + y;
-            const int yy = oy - p.crop_y, xx = vx - p.crop_x;
-            const bool inside = in_x && yy >= 0 && yy < p.crop_H && xx >= 0 && xx < p.crop_W;
-            if (EPI == EPI_DOT) {
-                if (inside) {
-                    float s = 0.f;
-#pragma unroll
-                    for (int o = 0; o < 8; ++o) s = fmaf(acc[o], dotw[o], s);
-                    if (job.dot_in) s += job.dot_in[(long long)yy * job.dot_in_rs + xx];
-                    if (job.dot_final) {
-                        s += dotb;
-                        s = 1.f / (1.f + expf(-s));
-                    }
-                    job.dot_out[(long long)yy * job.dot_out_rs + xx] = s;
-                }
-                return;
-            }
-            if (job.out && inside) {
-                float* dst = job.out + (long long)yy * job.out_rs + xx;
-#pragma unroll
-                for (int o = 0; o < COUT; ++o) dst[(long long)o * job.out_cs] = acc[o];
-            }
-            if (EPI == EPI_POOL) {
-                const int py = oy >> 1, px = vx >> 1;
-                const bool st = (y & 1) && !(lane & 1) && py < (H >> 1) && px < (W >> 1);
-#pragma unroll
-                for (int o = 0; o < COUT; ++o) {
-                    const float hm = fmaxf(acc[o], __shfl_xor_sync(FULL, acc[o], 1));
-                    if (y & 1) {
-                        if (st) job.pool[(long long)o * job.pool_cs + (long long)py * job.pool_rs + px] = fmaxf(prev[o], hm);
-                    } else {
-                        prev[o] = hm;
-                    }
-                }
-            }
-        };
-
-        // ---- software pipeline over the input rows of the tile ----
-        load_row(-1);
-#pragma unroll 1
-        for (int r = -1; r <= nrows; ++r) {
-            if (r > -1) {                       // UMMAs of row r-1 done: the A buffer is free, output row r-2 is final
-                mbar_wait(mbar, phase); phase ^= 1;
-                tc_fence_after();
-            }
-            stage_row();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_empty(s));                                   // the ring slot may be refilled
             tc_wait_st();
             tc_fence_before();
-            __syncthreads();
-            if (warp == 0 && elect_one()) { tc_fence_after(); issue_row(r); }
-            if (r < nrows) load_row(r + 1);     // in flight while the UMMAs and the epilogue below run
-            if (r >= 2) epilogue(r - 2);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_a(buf));
         }
-        mbar_wait(mbar, phase); phase ^= 1;
-        tc_fence_after();
-        epilogue(nrows - 1);
-        tc_fence_before();                      // the next tile's first UMMA follows its first __syncthreads
+    } else if (warp < W_MMA) {
+        // =========================== epilogue: TMEM accumulators -> bias + ReLU -> global ===========================
+        const int group = (warp - W_EPI0) >> 2;
+        float dotw[EPI == EPI_DOT ? 8 : 1];
+        float dotb = 0.f;
+        if (EPI == EPI_DOT) {
+#pragma unroll
+            for (int o = 0; o < 8; ++o) dotw[o] = __ldg(job.dotw + o);
+            dotb = __ldg(job.dotw + 8);
+        }
+        float prev[EPI == EPI_POOL ? COUT : 1];   // horizontally pooled even row, waiting for the odd row
+        int g0 = 0;
+#pragma unroll 1
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+            const int y0 = ty * TR, nrows = tile_rows(tile);
+            const int vx = tx * TCM + px;
+            const bool in_x = vx < W;
+#pragma unroll 1
+            for (int y = 0; y < nrows; ++y) {
+                if (((y >> 1) & (NGROUP - 1)) != group) continue;                    // row pairs alternate between the groups
+                const int g = g0 + y, slot = g & (ND - 1);
+                mbar_wait_sleep(d_full(slot), (uint32_t)(g / ND) & 1u);
+                tc_fence_after();
+                uint32_t d[COUT];
+                if (COUT == 16) tmem_ld16(tD + lane_off + TCN * (uint32_t)slot, reinterpret_cast<uint32_t(&)[16]>(d));
+                else tmem_ld8(tD + lane_off + TCN * (uint32_t)slot, reinterpret_cast<uint32_t(&)[8]>(d));
+                tc_wait_ld();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(d_empty(slot));          // the slot may be re-opened by a later row
+                float acc[COUT];
+#pragma unroll
+                for (int o = 0; o < COUT; ++o) acc[o] = fmaxf(__uint_as_float(d[o]) + bias[o], 0.f);
+                const int oy = y0 + y;
+                const int yy = oy - p.crop_y, xx = vx - p.crop_x;
+                const bool inside = in_x && yy >= 0 && yy < p.crop_H && xx >= 0 && xx < p.crop_W;
+                if (EPI == EPI_DOT) {
+                    if (inside) {
+                        float s = 0.f;
+#pragma unroll
+                        for (int o = 0; o < 8; ++o) s = fmaf(acc[o], dotw[o], s);
+                        if (job.dot_in) s += job.dot_in[(long long)yy * job.dot_in_rs + xx];
+                        if (job.dot_final) {
+                            s += dotb;
+                            s = 1.f / (1.f + expf(-s));
+                        }
+                        job.dot_out[(long long)yy * job.dot_out_rs + xx] = s;
+                    }
+                } else {
+                    if (job.out && inside) {
+                        float* dst = job.out + (long long)yy * job.out_rs + xx;
+#pragma unroll
+                        for (int o = 0; o < COUT; ++o) dst[(long long)o * job.out_cs] = acc[o];
+                    }
+                    if (EPI == EPI_POOL) {
+                        const int py = oy >> 1, pxl = vx >> 1;
+                        const bool st = (y & 1) && !(lane & 1) && py < (H >> 1) && pxl < (W >> 1);
+#pragma unroll
+                        for (int o = 0; o < COUT; ++o) {
+                            const float hm = fmaxf(acc[o], __shfl_xor_sync(FULL, acc[o], 1));
+                            if (y & 1) {
+                                if (st) job.pool[(long long)o * job.pool_cs + (long long)py * job.pool_rs + pxl] = fmaxf(prev[o], hm);
+                            } else {
+                                prev[o] = hm;
+                            }
+                        }
+                    }
+                }
+            }
+            g0 += nrows;
+        }
+    } else if (warp == W_MMA) {
+        if (elect_one()) {
+            // =========================== MMA issuer ===========================
+            const uint32_t sW = smem_u32(sm);
+            int i = 0, g0 = 0;
+#pragma unroll 1
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int nrows = tile_rows(tile);
+#pragma unroll 1
+                for (int r = -1; r <= nrows; ++r, ++i) {
+                    const int buf = i & (NA - 1);
+                    mbar_wait_sleep(full_a(buf), (uint32_t)(i / NA) & 1u);
+                    if (r + 1 < nrows) {             // this input row opens output row r+1: its accumulator slot must be drained
+                        const int g = g0 + r + 1;
+                        if (g >= ND) mbar_wait_sleep(d_empty(g & (ND - 1)), (uint32_t)(g / ND - 1) & 1u);
+                    }
+                    tc_fence_after();
+                    const uint32_t tAhi = tbase + (uint32_t)buf * G::A_COLS, tAlo = tAhi + G::KROW;
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const int y = r - ky + 1;
+                        if (y < 0 || y >= nrows) continue;
+                        const uint32_t d = tD + TCN * (uint32_t)((g0 + y) & (ND - 1));
+                        const uint32_t whi = sW + (2 * ky) * G::BMAT, wlo = sW + (2 * ky + 1) * G::BMAT;
+#pragma unroll
+                        for (int j = 0; j < G::KSTEPS; ++j) {
+                            const uint32_t koff = (uint32_t)((j >> 2) * (TCN * 128) + (j & 3) * 32);
+                            const uint64_t bhi = make_bdesc(whi + koff), blo = make_bdesc(wlo + koff);
+                            umma_tf32_ts(d, tAhi + 8 * j, bhi, IDESC, (ky == 0 && j == 0) ? 0u : 1u);   // ky = 0 opens the row
+                            umma_tf32_ts(d, tAlo + 8 * j, bhi, IDESC, 1u);
+                            umma_tf32_ts(d, tAhi + 8 * j, blo, IDESC, 1u);
+                        }
+                    }
+                    umma_commit(empty_a(buf));                                    // the A buffer may be refilled
+                    if (r >= 1) umma_commit(d_full((g0 + r - 1) & (ND - 1)));      // output row r-1 is final
+                }
+                g0 += nrows;
+            }
+        }
+    } else if (elect_one()) {
+        // =========================== TMA producer: global rows -> shared-memory ring ===========================
+        const uint32_t stage_base = smem_u32(sm + G::OFF_STAGE);
+        const CUtensorMap* tmA = &p.tmA[blockIdx.y];
+        const CUtensorMap* tmB = &p.tmB[blockIdx.y];
+        int i = 0;
+#pragma unroll 1
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+            const int x0 = tx * TCM, y0 = ty * TR, nrows = tile_rows(tile);
+#pragma unroll 1
+            for (int r = -1; r <= nrows; ++r, ++i) {
+                const int s = i % NS, n = i / NS;
+                if (n >= 1) mbar_wait_sleep(s_empty(s), (uint32_t)(n - 1) & 1u);
+                const uint32_t dst = stage_base + (uint32_t)s * G::STAGE_BYTES;
+                mbar_expect_tx(s_full(s), G::STAGE_BYTES);
+                tma_load_3d(dst, tmA, x0 - 4 - job.a_ox, y0 + r - job.a_oy, 0, s_full(s));
+                if (CIN_B > 0) tma_load_3d(dst + CIN_A * TC_BOXW * 4, tmB, x0 - 4 - job.b_ox, y0 + r - job.b_oy, 0, s_full(s));
+            }
+        }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tbase, G::TMEM_COLS);
+    if (warp == W_MMA) tmem_dealloc(tbase, TMEM_ALL);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -339,12 +361,12 @@ static int launch_tc_impl(TcConvParams& p, int njobs, cudaStream_t st) {
     p.tiles_x = cdiv(p.W, TCM);
     p.tiles_y = cdiv(p.H, p.TR);
     const int ntiles = p.tiles_x * p.tiles_y;
-    int per_job = cdiv((long long)num_sms() * G::CTAS, njobs);       // persistent CTAs of one job
+    int per_job = num_sms() / njobs;                                  // persistent CTAs of one job, one CTA per SM
     if (per_job > ntiles) per_job = ntiles;
     if (per_job < 1) per_job = 1;
     {
         ProfScope prof(cat, st, (double)p.H * p.W * njobs);
-        k<<<dim3(per_job, njobs), TCM, G::SMEM_BYTES, st>>>(p);
+        k<<<dim3(per_job, njobs), WS_THREADS, G::SMEM_BYTES, st>>>(p);
     }
     PC_LAUNCH_CHECK();
     return 0;
@@ -353,8 +375,6 @@ static int launch_tc_impl(TcConvParams& p, int njobs, cudaStream_t st) {
 int launch_conv_tc(int cin_a, int cin_b, int cout, int epi, TcConvParams& p, int njobs, cudaStream_t st) {
     const int key = ((cin_a * 100 + cin_b) * 100 + cout) * 10 + epi;
     switch (key) {
-        case ((2 * 100 + 0) * 100 + 8) * 10 + EPI_STORE: return launch_tc_impl<2, 0, 8, EPI_STORE>(p, njobs, st);
-        case ((4 * 100 + 0) * 100 + 8) * 10 + EPI_STORE: return launch_tc_impl<4, 0, 8, EPI_STORE>(p, njobs, st);
         case ((8 * 100 + 0) * 100 + 8) * 10 + EPI_STORE: return launch_tc_impl<8, 0, 8, EPI_STORE>(p, njobs, st);
         case ((8 * 100 + 0) * 100 + 8) * 10 + EPI_POOL: return launch_tc_impl<8, 0, 8, EPI_POOL>(p, njobs, st);
         case ((8 * 100 + 0) * 100 + 8) * 10 + EPI_DOT: return launch_tc_impl<8, 0, 8, EPI_DOT>(p, njobs, st);

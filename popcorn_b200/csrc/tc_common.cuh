@@ -94,6 +94,26 @@ __device__ __forceinline__ void mbar_init1(uint32_t mbar) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
+}
+// mbarrier.try_wait suspends the thread in hardware for a bounded time instead of busy-polling shared memory
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t mbar, uint32_t parity) {
+    for (uint32_t spin = 0;; ++spin) {
+        uint32_t done;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(mbar), "r"(parity)
+                     : "memory");
+        if (done) return;
+        if (spin > (1u << 24)) __trap();     // a protocol mistake must fault, never hang the GPU
+    }
+}
+
 // bounded spin on an mbarrier phase: a descriptor mistake must trap, never hang the GPU
 __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
     for (uint32_t spin = 0;; ++spin) {

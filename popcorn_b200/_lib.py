@@ -10,7 +10,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpopcorn_b200.so")
+LIB_PATH = os.environ.get("POPCORN_B200_LIB") or os.path.join(_HERE, "libpopcorn_b200.so")   # override: development builds
 CSRC = os.path.join(_HERE, "csrc")
 
 _lib = None

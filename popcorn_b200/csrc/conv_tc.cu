@@ -6,10 +6,13 @@
 //     split x = hi + lo (hi = top 19 bits = exact TF32) -> A operand [128 x 3*Cin] hi and lo, in TMEM;
 //   * the ky shift is NOT a lane shift: input row r feeds output rows r+1 (ky=0), r (ky=1), r-1 (ky=2), i.e. three
 //     different fp32 accumulators D[128 x 16] that live in an 8-slot TMEM ring (slot = running output row % 8);
-//   * B operand = the folded weights W_ky[co][(kx,ci)] (N = 16: Cout 16, or Cout 8 zero-padded), pre-split and
-//     pre-swizzled on the host (K-major SWIZZLE_128B), copied to shared memory once per CTA;
-//   * per input row: 3 (ky) x 3*Cin/8 (k-steps) x 3 (hi*hi + lo*hi + hi*lo) tcgen05.mma kind::tf32, N/2 = 8 cycles
-//     each (tools/probe/umma_probe.cu) -> 27*Cin cycles per 128 pixels.
+//   * B operand = the folded weights [W_ky2 | W_ky1 | W_ky0][co][(kx,ci)] (48 rows: 3 x Cout 16, or Cout 8 zero-padded),
+//     pre-split and pre-swizzled on the host (K-major SWIZZLE_128B), copied to shared memory once per CTA; the three
+//     accumulators of rows r-1, r, r+1 are adjacent ring slots, so ONE N=48 UMMA per k-step and split term feeds all
+//     three (two UMMAs where the ring wraps; fewer rows at tile borders).  Accumulators are always accumulated into:
+//     the epilogue zeroes a slot after reading it;
+//   * per input row: 3*Cin/8 (k-steps) x 3 (hi*hi + lo*hi + hi*lo) tcgen05.mma kind::tf32, N/2 = 24 cycles each
+//     (tools/probe/umma_probe.cu) -> 27*Cin cycles per 128 pixels.
 // Warp-specialised pipeline (576 threads), every hand-off is an mbarrier, nothing is block-synchronous:
 //   warp 17     TMA     : one lane streams input rows (all channels, 136 floats: 128 px + halo, zero-filled outside
 //                         the source = conv padding / the Up block's F.pad) into an NS-deep shared-memory ring
@@ -32,7 +35,24 @@
 #include "conv_common.cuh"
 #include "tc_common.cuh"
 
+#ifndef PC_TC_PROBE
+#define PC_TC_PROBE 0              // 1: CTA (0,0) accumulates per-role cycle counters into g_tc_dbg (development only)
+#endif
+
 namespace pc {
+
+#if PC_TC_PROBE
+__device__ long long g_tc_dbg[32];
+#define TCP_T(var) const long long var = clock64()
+#define TCP_DECL long long tcp_acc[5] = {0, 0, 0, 0, 0}
+#define TCP_ADD(slot, a, b) tcp_acc[(slot) & 7] += (b) - (a)
+#define TCP_FLUSH(base) do { if (blockIdx.x == 0 && blockIdx.y == 0) for (int q = 0; q < 5; ++q) g_tc_dbg[(base) + q] = tcp_acc[q]; } while (0)
+#else
+#define TCP_T(var)
+#define TCP_DECL
+#define TCP_ADD(slot, a, b)
+#define TCP_FLUSH(base)
+#endif
 
 constexpr int TCM = 128;           // pixels per UMMA
 constexpr int TCN = 16;            // UMMA N (output channels, zero-padded)
@@ -47,15 +67,16 @@ struct TcGeom {
     static constexpr int KROW = (3 * CIN + 7) / 8 * 8;          // A columns per half (hi | lo) of one input row
     static constexpr int KSTEPS = KROW / 8;
     static constexpr int KATOMS = (KROW + 31) / 32;             // 32-float swizzle atoms along K
-    static constexpr int BMAT = KATOMS * TCN * 128;             // bytes of one swizzled [16 x KROW] matrix
-    static constexpr int OFF_BIAS = 6 * BMAT;                   // matrices: [ky][hi, lo]
+    static constexpr int BATOM = 3 * TCN * 128;                 // bytes of one K-atom: 48 rows = [W_ky2 | W_ky1 | W_ky0] x 128 B
+    static constexpr int BMAT = KATOMS * BATOM;                 // bytes of one swizzled [48 x KROW] matrix
+    static constexpr int OFF_BIAS = 2 * BMAT;                   // matrices: [hi, lo]
     static constexpr int IMG_BYTES = OFF_BIAS + 64;             // + bias[16]
     static constexpr int A_COLS = 2 * KROW;                     // one A buffer: hi at [0, KROW), lo at [KROW, 2*KROW)
     static constexpr int NA_FIT = (TMEM_ALL - ND * TCN) / A_COLS;
     static constexpr int NA = NA_FIT >= 4 ? 4 : 2;              // A buffers (power of two)
     static constexpr int D_COL0 = NA * A_COLS;                  // accumulator slots of 16 columns
     static constexpr int STAGE_BYTES = CIN * TC_BOXW * 4;       // one input row, all channels
-    static constexpr int NS = CIN <= 8 ? 16 : CIN <= 16 ? 8 : 5;   // shared-memory ring depth (~70-87 KB in flight per SM)
+    static constexpr int NS = CIN <= 8 ? 16 : CIN <= 16 ? 8 : 4;   // shared-memory ring depth (~70 KB in flight per SM)
     static constexpr int OFF_STAGE = (IMG_BYTES + 127) / 128 * 128;
     static constexpr int OFF_BARS = OFF_STAGE + NS * STAGE_BYTES;   // s_full[NS] s_empty[NS] full_a[NA] empty_a[NA] d_full[ND] d_empty[ND]
     static constexpr int NBARS = 2 * NS + 2 * NA + 2 * ND;
@@ -115,6 +136,17 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
     const uint32_t tbase = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
     const uint32_t tD = tbase + G::D_COL0;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;    // a warp may touch TMEM lanes 32*(warp%4) .. +31
+    if (warp >= W_EPI0 && warp < W_EPI0 + 4) {                      // UMMAs only ever accumulate: start from zero
+        uint32_t z[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) z[i] = 0u;
+#pragma unroll
+        for (int i = 0; i < ND; ++i) tmem_st16(tD + lane_off + TCN * i, z);
+        tc_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
     const int px = (warp & 3) * 32 + lane;                          // pixel of this thread inside a tile row
 
     const int H = p.H, W = p.W, TR = p.TR;
@@ -127,12 +159,16 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
         int total = 0;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x) total += tile_rows(t) + 2;
         const float* stage0 = reinterpret_cast<const float*>(sm + G::OFF_STAGE) + px + 3;   // box column 3 = image column x-1
+        TCP_DECL;
 #pragma unroll 1
         for (int i = group; i < total; i += NGROUP) {
             const int s = i % NS, buf = i & (NA - 1), n = i / NA;
+            TCP_T(t0);
             mbar_wait_sleep(s_full(s), (uint32_t)(i / NS) & 1u);                       // the row has landed
+            TCP_T(t1);
             if (n >= 1) mbar_wait_sleep(empty_a(buf), (uint32_t)(n - 1) & 1u);        // UMMAs that read this A buffer are done
             tc_fence_after();
+            TCP_T(t2);
             const float* st = stage0 + s * (G::STAGE_BYTES / 4);
             const uint32_t tA = tbase + (uint32_t)buf * G::A_COLS + lane_off;
 #pragma unroll
@@ -149,11 +185,15 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(s_empty(s));                                   // the ring slot may be refilled
+            TCP_T(t3);
             tc_wait_st();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(full_a(buf));
+            TCP_T(t4);
+            TCP_ADD(0, t0, t1); TCP_ADD(1, t1, t2); TCP_ADD(2, t2, t3); TCP_ADD(3, t3, t4); TCP_ADD(4, t4 - 1, t4);
         }
+        if (tid == 0) TCP_FLUSH(8);
     } else if (warp < W_MMA) {
         // =========================== epilogue: TMEM accumulators -> bias + ReLU -> global ===========================
         const int group = (warp - W_EPI0) >> 2;
@@ -166,6 +206,7 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
         }
         float prev[EPI == EPI_POOL ? COUT : 1];   // horizontally pooled even row, waiting for the odd row
         int g0 = 0;
+        TCP_DECL;
 #pragma unroll 1
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
@@ -176,15 +217,26 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
             for (int y = 0; y < nrows; ++y) {
                 if (((y >> 1) & (NGROUP - 1)) != group) continue;                    // row pairs alternate between the groups
                 const int g = g0 + y, slot = g & (ND - 1);
+                TCP_T(t0);
                 mbar_wait_sleep(d_full(slot), (uint32_t)(g / ND) & 1u);
                 tc_fence_after();
+                TCP_T(t1);
                 uint32_t d[COUT];
                 if (COUT == 16) tmem_ld16(tD + lane_off + TCN * (uint32_t)slot, reinterpret_cast<uint32_t(&)[16]>(d));
                 else tmem_ld8(tD + lane_off + TCN * (uint32_t)slot, reinterpret_cast<uint32_t(&)[8]>(d));
                 tc_wait_ld();
+                {
+                    uint32_t z[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) z[i] = 0u;
+                    tmem_st16(tD + lane_off + TCN * (uint32_t)slot, z);              // the next row using the slot accumulates from zero
+                }
+                tc_wait_st();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(d_empty(slot));          // the slot may be re-opened by a later row
+                TCP_T(t2);
+                TCP_ADD(0, t0, t1); TCP_ADD(1, t1, t2); TCP_ADD(2, t2 - 1, t2);
                 float acc[COUT];
 #pragma unroll
                 for (int o = 0; o < COUT; ++o) acc[o] = fmaxf(__uint_as_float(d[o]) + bias[o], 0.f);
@@ -226,44 +278,97 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
             }
             g0 += nrows;
         }
+        if (tid == W_EPI0 * 32) TCP_FLUSH(16);
     } else if (warp == W_MMA) {
         if (elect_one()) {
             // =========================== MMA issuer ===========================
             const uint32_t sW = smem_u32(sm);
-            int i = 0, g0 = 0;
+            constexpr uint32_t ID48 = umma_idesc_tf32(TCM, 3 * TCN);
+            const uint64_t bd_hi = make_bdesc(sW), bd_lo = make_bdesc(sW + G::BMAT);
+            TCP_DECL;
+            // flattened (tile, input row) walk; the mbarrier probes of row i+1 are issued before the UMMAs of row i so that
+            // their round trip through the synchronisation unit is hidden behind the UMMA issue
+            int tile = blockIdx.x;
+            if (tile < ntiles) {
+                int nrows = tile_rows(tile), r = -1, g0 = 0, i = 0;
+                uint32_t ok_full = mbar_test(full_a(0), 0u);
+                uint32_t ok_d = 1u;                                   // rows 0 .. ND-1 open freshly zeroed slots
 #pragma unroll 1
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const int nrows = tile_rows(tile);
-#pragma unroll 1
-                for (int r = -1; r <= nrows; ++r, ++i) {
+                for (;;) {
                     const int buf = i & (NA - 1);
-                    mbar_wait_sleep(full_a(buf), (uint32_t)(i / NA) & 1u);
-                    if (r + 1 < nrows) {             // this input row opens output row r+1: its accumulator slot must be drained
+                    TCP_T(t0);
+                    if (!ok_full) mbar_wait_sleep(full_a(buf), (uint32_t)(i / NA) & 1u);
+                    TCP_T(t1);
+                    if (!ok_d) {                     // this input row opens output row r+1: its accumulator slot must be drained
                         const int g = g0 + r + 1;
-                        if (g >= ND) mbar_wait_sleep(d_empty(g & (ND - 1)), (uint32_t)(g / ND - 1) & 1u);
+                        mbar_wait_sleep(d_empty(g & (ND - 1)), (uint32_t)(g / ND - 1) & 1u);
                     }
                     tc_fence_after();
-                    const uint32_t tAhi = tbase + (uint32_t)buf * G::A_COLS, tAlo = tAhi + G::KROW;
-#pragma unroll
-                    for (int ky = 0; ky < 3; ++ky) {
-                        const int y = r - ky + 1;
-                        if (y < 0 || y >= nrows) continue;
-                        const uint32_t d = tD + TCN * (uint32_t)((g0 + y) & (ND - 1));
-                        const uint32_t whi = sW + (2 * ky) * G::BMAT, wlo = sW + (2 * ky + 1) * G::BMAT;
-#pragma unroll
-                        for (int j = 0; j < G::KSTEPS; ++j) {
-                            const uint32_t koff = (uint32_t)((j >> 2) * (TCN * 128) + (j & 3) * 32);
-                            const uint64_t bhi = make_bdesc(whi + koff), blo = make_bdesc(wlo + koff);
-                            umma_tf32_ts(d, tAhi + 8 * j, bhi, IDESC, (ky == 0 && j == 0) ? 0u : 1u);   // ky = 0 opens the row
-                            umma_tf32_ts(d, tAlo + 8 * j, bhi, IDESC, 1u);
-                            umma_tf32_ts(d, tAhi + 8 * j, blo, IDESC, 1u);
+                    TCP_T(t2);
+                    // ---- next row's coordinates and barrier probes ----
+                    int tile_n = tile, r_n = r + 1, nrows_n = nrows, g0_n = g0;
+                    bool more = true;
+                    if (r_n > nrows) {
+                        tile_n += gridDim.x;
+                        more = tile_n < ntiles;
+                        r_n = -1;
+                        g0_n = g0 + nrows;
+                        if (more) nrows_n = tile_rows(tile_n);
+                    }
+                    if (more) {
+                        ok_full = mbar_test(full_a((i + 1) & (NA - 1)), (uint32_t)((i + 1) / NA) & 1u);
+                        ok_d = 1u;
+                        if (r_n + 1 < nrows_n) {
+                            const int g = g0_n + r_n + 1;
+                            if (g >= ND) ok_d = mbar_test(d_empty(g & (ND - 1)), (uint32_t)(g / ND - 1) & 1u);
                         }
                     }
+                    const uint32_t tAhi = tbase + (uint32_t)buf * G::A_COLS, tAlo = tAhi + G::KROW;
+                    const int sa3 = (g0 + r - 1) & (ND - 1);
+                    if (r >= 1 && r <= nrows - 2 && sa3 <= ND - 3) {
+                        // common case: three valid output rows r-1, r, r+1 in adjacent slots -> ONE N=48 UMMA per k-step and
+                        // split term, loop-invariant B descriptors
+                        const uint32_t d = tD + TCN * (uint32_t)sa3;
+#pragma unroll
+                        for (int j = 0; j < G::KSTEPS; ++j) {
+                            const uint64_t koff = (uint64_t)(((j >> 2) * G::BATOM + (j & 3) * 32) >> 4);   // address field: 16-byte units
+                            umma_tf32_ts(d, tAhi + 8 * j, bd_hi + koff, ID48, 1u);
+                            umma_tf32_ts(d, tAlo + 8 * j, bd_hi + koff, ID48, 1u);
+                            umma_tf32_ts(d, tAhi + 8 * j, bd_lo + koff, ID48, 1u);
+                        }
+                    } else {
+                        // tile borders and ring wrap: valid output rows [ya, yb] within {r-1, r, r+1}; their accumulators are
+                        // consecutive ring slots -> one UMMA of N = 16 * rows, or two where the ring wraps (slot 7 -> 0)
+                        const int ya = r - 1 < 0 ? 0 : r - 1, yb = r + 1 > nrows - 1 ? nrows - 1 : r + 1;
+                        const int sa = (g0 + ya) & (ND - 1), len = yb - ya + 1;
+                        const int len1 = len < ND - sa ? len : ND - sa, len2 = len - len1;
+                        const int blk = ya - (r - 1);                              // first 16-row block of B: 0 = ky 2, 1 = ky 1, 2 = ky 0
+                        const uint32_t d1 = tD + TCN * (uint32_t)sa, d2 = tD;
+                        const uint32_t id1 = umma_idesc_tf32(TCM, TCN * len1), id2 = umma_idesc_tf32(TCM, TCN * len2);
+                        const uint64_t o1 = (uint64_t)((uint32_t)blk * (TCN * 128) >> 4), o2 = (uint64_t)((uint32_t)(blk + len1) * (TCN * 128) >> 4);
+#pragma unroll 1
+                        for (int j = 0; j < G::KSTEPS; ++j) {
+                            const uint64_t koff = (uint64_t)(((j >> 2) * G::BATOM + (j & 3) * 32) >> 4);
+                            umma_tf32_ts(d1, tAhi + 8 * j, bd_hi + o1 + koff, id1, 1u);
+                            umma_tf32_ts(d1, tAlo + 8 * j, bd_hi + o1 + koff, id1, 1u);
+                            umma_tf32_ts(d1, tAhi + 8 * j, bd_lo + o1 + koff, id1, 1u);
+                            if (len2 > 0) {
+                                umma_tf32_ts(d2, tAhi + 8 * j, bd_hi + o2 + koff, id2, 1u);
+                                umma_tf32_ts(d2, tAlo + 8 * j, bd_hi + o2 + koff, id2, 1u);
+                                umma_tf32_ts(d2, tAhi + 8 * j, bd_lo + o2 + koff, id2, 1u);
+                            }
+                        }
+                    }
+                    TCP_T(t3);
                     umma_commit(empty_a(buf));                                    // the A buffer may be refilled
                     if (r >= 1) umma_commit(d_full((g0 + r - 1) & (ND - 1)));      // output row r-1 is final
+                    TCP_T(t4);
+                    TCP_ADD(0, t0, t1); TCP_ADD(1, t1, t2); TCP_ADD(2, t2, t3); TCP_ADD(3, t3, t4); TCP_ADD(4, t4 - 1, t4);
+                    if (!more) break;
+                    tile = tile_n; r = r_n; nrows = nrows_n; g0 = g0_n; ++i;
                 }
-                g0 += nrows;
             }
+            TCP_FLUSH(0);
         }
     } else if (elect_one()) {
         // =========================== TMA producer: global rows -> shared-memory ring ===========================
@@ -297,37 +402,51 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
 // ---------------------------------------------------------------------------------------------------
 static int tc_geom_img_floats(int cin) {
     const int krow = (3 * cin + 7) / 8 * 8, katoms = (krow + 31) / 32;
-    return (6 * katoms * TCN * 128 + 64) / 4;
+    return (2 * katoms * 3 * TCN * 128 + 64) / 4;
 }
 
 int conv_tc_layer_floats(int cin) { return (int)round_up(tc_geom_img_floats(cin), 64); }   // 256-B multiple
 
-// flat = [cin][ky][kx][cout] + bias[cout] (the SIMT pack)  ->  [ky][hi|lo][katom][16 rows][32 floats] swizzled + bias[16]
+// flat = [cin][ky][kx][cout] + bias[cout] (the SIMT pack)  ->  [hi|lo][katom][48 rows][32 floats] swizzled + bias[16];
+// row 16*b + co of a matrix holds W_ky[co][k = kx*cin + ci] with ky = 2 - b (the block order of three adjacent output rows)
 void conv_tc_pack_layer(const float* flat, int cin, int cout, float* img) {
     const int krow = (3 * cin + 7) / 8 * 8, katoms = (krow + 31) / 32;
-    const int mat = katoms * TCN * 32;                  // floats per matrix
+    const int rows = 3 * TCN;
+    const int mat = katoms * rows * 32;                 // floats per matrix
     const int total = conv_tc_layer_floats(cin);
     memset(img, 0, sizeof(float) * total);
     for (int ky = 0; ky < 3; ++ky)
-        for (int n = 0; n < cout; ++n)
+        for (int co = 0; co < cout; ++co)
             for (int kx = 0; kx < 3; ++kx)
                 for (int ci = 0; ci < cin; ++ci) {
-                    const float w = flat[((ci * 3 + ky) * 3 + kx) * cout + n];
+                    const float w = flat[((ci * 3 + ky) * 3 + kx) * cout + co];
                     uint32_t bits;
                     memcpy(&bits, &w, 4);
                     bits &= 0xFFFFE000u;
                     float hi;
                     memcpy(&hi, &bits, 4);
                     const float lo = w - hi;
+                    const int n = (2 - ky) * TCN + co;
                     const int k = kx * cin + ci;
                     const int atom = k / 32, kk = k % 32;
                     const int pos = (((kk / 4) ^ (n % 8)) * 4) + kk % 4;      // Swizzle<3,4,3>: 16-B chunk ^= row % 8
-                    const int idx = atom * (TCN * 32) + n * 32 + pos;
-                    img[(2 * ky) * mat + idx] = hi;
-                    img[(2 * ky + 1) * mat + idx] = lo;
+                    const int idx = atom * (rows * 32) + n * 32 + pos;
+                    img[idx] = hi;
+                    img[mat + idx] = lo;
                 }
-    for (int n = 0; n < cout; ++n) img[6 * mat + n] = flat[cin * 9 * cout + n];
+    for (int n = 0; n < cout; ++n) img[2 * mat + n] = flat[cin * 9 * cout + n];
 }
+
+#if PC_TC_PROBE
+}  // namespace pc
+extern "C" int pc_debug_tc_counters(long long* out32, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out32, pc::g_tc_dbg, sizeof(long long) * 32);
+    if (reset) { long long z[32] = {0}; cudaMemcpyToSymbol(pc::g_tc_dbg, z, sizeof(z)); }
+    return 0;
+}
+namespace pc {
+#endif
 
 bool conv_tc_enabled() {
     static const bool on = [] {

@@ -101,6 +101,16 @@ __device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mbar) : "memory");
 }
+// one non-blocking probe of an mbarrier phase; the result can be consumed much later, which hides the ~100-cycle
+// round trip of the synchronisation unit behind other work (software-pipelined waits)
+__device__ __forceinline__ uint32_t mbar_test(uint32_t mbar, uint32_t parity) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done)
+                 : "r"(mbar), "r"(parity)
+                 : "memory");
+    return done;
+}
 // mbarrier.try_wait suspends the thread in hardware for a bounded time instead of busy-polling shared memory
 __device__ __forceinline__ void mbar_wait_sleep(uint32_t mbar, uint32_t parity) {
     for (uint32_t spin = 0;; ++spin) {

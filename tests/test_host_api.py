@@ -145,7 +145,7 @@ def test_cpu_tensors_are_rejected_loudly(sd):
 @pytest.mark.parametrize("cin,cout", [(2, 8), (4, 8), (8, 16), (16, 16), (32, 8)])
 def test_conv_tc_weight_image_layout(cin, cout):
     """Host packer of the tcgen05 conv weights (include/popcorn_b200.h "Tensor-core weight section"): de-swizzling the
-    image gives back W_ky[co][kx*cin+ci] with hi + lo == w exactly, hi a TF32 number, zero rows/columns as padding."""
+    image gives back [W_ky2 | W_ky1 | W_ky0][co][kx*cin+ci] with hi + lo == w exactly, hi a TF32 number, zero rows/columns as padding."""
     L = _lib.lib()
     g = torch.Generator().manual_seed(cin * 31 + cout)
     w = torch.randn(cout, cin, 3, 3, generator=g)
@@ -156,17 +156,18 @@ def test_conv_tc_weight_image_layout(cin, cout):
     _lib.check(L.pc_conv_tc_pack_layer(flat.data_ptr(), cin, cout, img.data_ptr()))
     krow = (3 * cin + 7) // 8 * 8
     katoms = (krow + 31) // 32
-    mat = katoms * 16 * 32
-    assert n % 64 == 0 and n >= 6 * mat + 16
-    mats = img[:6 * mat].view(3, 2, katoms, 16, 32)
-    rows = torch.arange(16).view(16, 1)
+    mat = katoms * 48 * 32
+    assert n % 64 == 0 and n >= 2 * mat + 16
+    mats = img[:2 * mat].view(2, katoms, 48, 32)
+    rows = torch.arange(48).view(48, 1)
     kk = torch.arange(32).view(1, 32)
     pos = ((kk // 4) ^ (rows % 8)) * 4 + kk % 4                     # Swizzle<3,4,3>
-    de = torch.gather(mats, 4, pos.expand(3, 2, katoms, 16, 32))    # de[ky][h][atom][n][kk]
-    de = de.permute(0, 1, 3, 2, 4).reshape(3, 2, 16, katoms * 32)   # [ky][hi|lo][n][k]
-    hi, lo = de[:, 0], de[:, 1]
-    want = torch.zeros(3, 16, katoms * 32)
-    want[:, :cout, :3 * cin] = w.permute(2, 0, 3, 1).reshape(3, cout, 3 * cin)   # [ky][co][kx*cin+ci]
+    de = torch.gather(mats, 3, pos.expand(2, katoms, 48, 32))       # de[h][atom][n][kk]
+    de = de.permute(0, 2, 1, 3).reshape(2, 48, katoms * 32)         # [hi|lo][n = 16*(2-ky)+co][k]
+    hi, lo = de[0], de[1]
+    want = torch.zeros(48, katoms * 32)
+    for ky in range(3):
+        want[16 * (2 - ky): 16 * (2 - ky) + cout, :3 * cin] = w[:, :, ky, :].permute(0, 2, 1).reshape(cout, 3 * cin)   # [co][kx*cin+ci]
     assert torch.equal(hi + lo, want)
     assert torch.equal(hi.view(torch.int32) & 0x1FFF, torch.zeros_like(hi, dtype=torch.int32))
-    assert torch.equal(img[6 * mat: 6 * mat + cout], b) and float(img[6 * mat + cout: 6 * mat + 16].abs().sum()) == 0
+    assert torch.equal(img[2 * mat: 2 * mat + cout], b) and float(img[2 * mat + cout: 2 * mat + 16].abs().sum()) == 0

@@ -42,6 +42,18 @@ for cin, cout in cases:
         torch.cuda.synchronize()
         ms = a.elapsed_time(e) / iters
         res[name] = ms
+        if name == "tc" and hasattr(L, "pc_debug_tc_counters"):      # probe build (-DPC_TC_PROBE=1): per-role cycle counters of CTA (0,0)
+            import ctypes
+            buf = (ctypes.c_longlong * 32)()
+            L.pc_debug_tc_counters(buf, 1)
+            run()
+            L.pc_debug_tc_counters(buf, 1)
+            c = list(buf)
+            def per(a, n):
+                return [round(x / max(n, 1)) for x in a]
+            print("   mma thread  rows", c[4], " wait_full_a, wait_d_empty, issue, commit =", per(c[0:4], c[4]))
+            print("   stager w0   rows", c[12], " wait_s_full, wait_empty_a, stage, wait_st+arrive =", per(c[8:12], c[12]))
+            print("   epilogue w8 rows", c[18], " wait_d_full, ld+zero+arrive =", per(c[16:18], c[18]))
         px = H * W
         print(f"cin {cin:2d} cout {cout:2d} {name:4s}: {ms:7.3f} ms  {px / ms / 1e6:7.1f} Gpx/s  {(cin + cout) * 4 * px / ms / 1e6:7.0f} GB/s  "
               f"{2 * 9 * cin * cout * px / ms / 1e9:6.1f} TFLOP/s  clk/row-tile/SM {ms * 1e-3 * 148 * 1.965e9 / (px / 128):7.0f}", flush=True)

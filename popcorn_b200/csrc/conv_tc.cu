@@ -78,7 +78,7 @@ struct TcGeom {
     static constexpr int STAGE_BYTES = CIN * TC_BOXW * 4;       // one input row, all channels
     static constexpr int NS = CIN <= 8 ? 16 : CIN <= 16 ? 8 : 4;   // shared-memory ring depth (~70 KB in flight per SM)
     static constexpr int OFF_STAGE = (IMG_BYTES + 127) / 128 * 128;
-    static constexpr int OFF_BARS = OFF_STAGE + NS * STAGE_BYTES;   // s_full[NS] s_empty[NS] full_a[NA] empty_a[NA] d_full[ND] d_empty[ND]
+    static constexpr int OFF_BARS = OFF_STAGE + NS * STAGE_BYTES;   // s_full[NS] s_empty[NS] full_a[NA/2] empty_a[NA/2] d_full[ND/2] d_empty[ND/2]
     static constexpr int NBARS = 2 * NS + 2 * NA + 2 * ND;
     static constexpr int OFF_TMEM = OFF_BARS + 8 * NBARS;
     static constexpr int SMEM_NEED = OFF_TMEM + 16 + 1024;
@@ -102,8 +102,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
     constexpr int CIN = CIN_A + CIN_B;
     using G = TcGeom<CIN>;
-    constexpr int NA = G::NA, NS = G::NS;
-    constexpr uint32_t IDESC = umma_idesc_tf32(TCM, TCN);
+    constexpr int NA = G::NA, NS = G::NS, NP = NA / 2, NDP = ND / 2;
     constexpr unsigned FULL = 0xffffffffu;
 
     extern __shared__ uint8_t smem_raw[];
@@ -112,12 +111,14 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
     const int tid = threadIdx.x, lane = tid & 31, warp = uniform_warp_idx();
     const float* bias = reinterpret_cast<const float*>(sm + G::OFF_BIAS);
     const uint32_t bars = smem_u32(sm + G::OFF_BARS);
-    auto s_full = [&](int i) { return bars + 8u * (uint32_t)i; };
-    auto s_empty = [&](int i) { return bars + 8u * (uint32_t)(NS + i); };
-    auto full_a = [&](int i) { return bars + 8u * (uint32_t)(2 * NS + i); };
-    auto empty_a = [&](int i) { return bars + 8u * (uint32_t)(2 * NS + NA + i); };
-    auto d_full = [&](int i) { return bars + 8u * (uint32_t)(2 * NS + 2 * NA + i); };
-    auto d_empty = [&](int i) { return bars + 8u * (uint32_t)(2 * NS + 2 * NA + ND + i); };
+    // rows move through the pipeline in PAIRS (input rows 2b-1, 2b of a tile; output rows 2m, 2m+1): one barrier
+    // round trip of the single MMA-issuing thread then covers two rows of UMMAs
+    auto s_full = [&](int i) { return bars + 8u * (uint32_t)i; };                        // TMA -> stagers, per row
+    auto s_empty = [&](int i) { return bars + 8u * (uint32_t)(NS + i); };                // stagers -> TMA, per row
+    auto full_a = [&](int i) { return bars + 8u * (uint32_t)(2 * NS + i); };             // stagers -> MMA, per pair of A buffers
+    auto empty_a = [&](int i) { return bars + 8u * (uint32_t)(2 * NS + NP + i); };       // MMA (commit) -> stagers
+    auto d_full = [&](int i) { return bars + 8u * (uint32_t)(2 * NS + 2 * NP + i); };    // MMA (commit) -> epilogue, per pair of slots
+    auto d_empty = [&](int i) { return bars + 8u * (uint32_t)(2 * NS + 2 * NP + NDP + i); };   // epilogue -> stagers
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + G::OFF_TMEM);
 
     for (int i = tid; i < G::IMG_BYTES / 16; i += WS_THREADS)
@@ -125,8 +126,8 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
     if (warp == W_MMA) tmem_alloc(smem_u32(tmem_slot), TMEM_ALL);
     if (tid == 0) {
         for (int i = 0; i < NS; ++i) { mbar_init(s_full(i), 1); mbar_init(s_empty(i), 4); }     // 4 = the stager warps of a group
-        for (int i = 0; i < NA; ++i) { mbar_init(full_a(i), 4); mbar_init(empty_a(i), 1); }
-        for (int i = 0; i < ND; ++i) { mbar_init(d_full(i), 1); mbar_init(d_empty(i), 4); }     // 4 = the epilogue warps of a group
+        for (int i = 0; i < NP; ++i) { mbar_init(full_a(i), 8); mbar_init(empty_a(i), 1); }     // 8 = both stager groups
+        for (int i = 0; i < NDP; ++i) { mbar_init(d_full(i), 1); mbar_init(d_empty(i), 4); }    // 4 = the epilogue warps of a group
         mbar_init_fence();
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // weights + barriers (generic stores) -> visible to UMMA / TMA
@@ -149,49 +150,63 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
     tc_fence_after();
     const int px = (warp & 3) * 32 + lane;                          // pixel of this thread inside a tile row
 
-    const int H = p.H, W = p.W, TR = p.TR;
+    const int H = p.H, W = p.W, TR = p.TR;                          // TR is even
     const int ntiles = p.tiles_x * p.tiles_y;
-    auto tile_rows = [&](int tile) { const int y0 = (tile / p.tiles_x) * TR; return (H - y0) < TR ? (H - y0) : TR; };
+    // rows of a tile, rounded up to even: an odd last row is computed (from zero-filled input) and never stored
+    auto tile_rows = [&](int tile) {
+        const int y0 = (tile / p.tiles_x) * TR;
+        const int n = (H - y0) < TR ? (H - y0) : TR;
+        return (n + 1) & ~1;
+    };
 
     if (warp < W_EPI0) {
         // =========================== stagers: shared-memory row -> TMEM (A operand) ===========================
-        const int group = warp >> 2;
-        int total = 0;
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) total += tile_rows(t) + 2;
+        const int group = warp >> 2;                                 // group 0 stages input rows 2b-1, group 1 rows 2b
         const float* stage0 = reinterpret_cast<const float*>(sm + G::OFF_STAGE) + px + 3;   // box column 3 = image column x-1
+        int B = 0, P0 = 0;                                           // running batch index / first output pair of the tile
         TCP_DECL;
 #pragma unroll 1
-        for (int i = group; i < total; i += NGROUP) {
-            const int s = i % NS, buf = i & (NA - 1), n = i / NA;
-            TCP_T(t0);
-            mbar_wait_sleep(s_full(s), (uint32_t)(i / NS) & 1u);                       // the row has landed
-            TCP_T(t1);
-            if (n >= 1) mbar_wait_sleep(empty_a(buf), (uint32_t)(n - 1) & 1u);        // UMMAs that read this A buffer are done
-            tc_fence_after();
-            TCP_T(t2);
-            const float* st = stage0 + s * (G::STAGE_BYTES / 4);
-            const uint32_t tA = tbase + (uint32_t)buf * G::A_COLS + lane_off;
-#pragma unroll
-            for (int j = 0; j < G::KSTEPS; ++j) {
-                uint32_t hi[8], lo[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int col = 8 * j + q;                                          // A column = kx * CIN + ci
-                    const float val = (col < 3 * CIN) ? st[(col % CIN) * TC_BOXW + col / CIN] : 0.f;
-                    split_tf32(val, hi[q], lo[q]);
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int nb = tile_rows(tile) / 2 + 1;                  // batches of this tile: (nrows + 2) / 2
+#pragma unroll 1
+            for (int b = 0; b < nb; ++b, ++B) {
+                const int i = 2 * B + group;                         // running input-row index = ring position
+                const int s = i % NS, pb = B & (NP - 1), n = B / NP;
+                TCP_T(t0);
+                mbar_wait_sleep(s_full(s), (uint32_t)(i / NS) & 1u);                    // the row has landed
+                TCP_T(t1);
+                if (n >= 1) mbar_wait_sleep(empty_a(pb), (uint32_t)(n - 1) & 1u);      // UMMAs that read this buffer pair are done
+                if (b < nb - 1) {                                    // this batch opens output pair b: its slots must be drained
+                    const int P = P0 + b;
+                    if (P >= NDP) mbar_wait_sleep(d_empty(P & (NDP - 1)), (uint32_t)(P / NDP - 1) & 1u);
                 }
-                tmem_st8(tA + 8 * j, hi);
-                tmem_st8(tA + G::KROW + 8 * j, lo);
+                tc_fence_after();
+                TCP_T(t2);
+                const float* st = stage0 + s * (G::STAGE_BYTES / 4);
+                const uint32_t tA = tbase + (uint32_t)(2 * pb + group) * G::A_COLS + lane_off;
+#pragma unroll
+                for (int j = 0; j < G::KSTEPS; ++j) {
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int col = 8 * j + q;                                      // A column = kx * CIN + ci
+                        const float val = (col < 3 * CIN) ? st[(col % CIN) * TC_BOXW + col / CIN] : 0.f;
+                        split_tf32(val, hi[q], lo[q]);
+                    }
+                    tmem_st8(tA + 8 * j, hi);
+                    tmem_st8(tA + G::KROW + 8 * j, lo);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(s_empty(s));                               // the ring slot may be refilled
+                TCP_T(t3);
+                tc_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full_a(pb));
+                TCP_T(t4);
+                TCP_ADD(0, t0, t1); TCP_ADD(1, t1, t2); TCP_ADD(2, t2, t3); TCP_ADD(3, t3, t4); TCP_ADD(4, t4 - 1, t4);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(s_empty(s));                                   // the ring slot may be refilled
-            TCP_T(t3);
-            tc_wait_st();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(full_a(buf));
-            TCP_T(t4);
-            TCP_ADD(0, t0, t1); TCP_ADD(1, t1, t2); TCP_ADD(2, t2, t3); TCP_ADD(3, t3, t4); TCP_ADD(4, t4 - 1, t4);
+            P0 += nb - 1;
         }
         if (tid == 0) TCP_FLUSH(8);
     } else if (warp < W_MMA) {
@@ -204,79 +219,83 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
             for (int o = 0; o < 8; ++o) dotw[o] = __ldg(job.dotw + o);
             dotb = __ldg(job.dotw + 8);
         }
-        float prev[EPI == EPI_POOL ? COUT : 1];   // horizontally pooled even row, waiting for the odd row
-        int g0 = 0;
+        int P0 = 0;
         TCP_DECL;
 #pragma unroll 1
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
-            const int y0 = ty * TR, nrows = tile_rows(tile);
+            const int y0 = ty * TR, npairs = tile_rows(tile) / 2;
             const int vx = tx * TCM + px;
             const bool in_x = vx < W;
 #pragma unroll 1
-            for (int y = 0; y < nrows; ++y) {
-                if (((y >> 1) & (NGROUP - 1)) != group) continue;                    // row pairs alternate between the groups
-                const int g = g0 + y, slot = g & (ND - 1);
+            for (int m = group; m < npairs; m += NGROUP) {                           // row pairs alternate between the groups
+                const int P = P0 + m, ps = P & (NDP - 1);
                 TCP_T(t0);
-                mbar_wait_sleep(d_full(slot), (uint32_t)(g / ND) & 1u);
+                mbar_wait_sleep(d_full(ps), (uint32_t)(P / NDP) & 1u);
                 tc_fence_after();
                 TCP_T(t1);
-                uint32_t d[COUT];
-                if (COUT == 16) tmem_ld16(tD + lane_off + TCN * (uint32_t)slot, reinterpret_cast<uint32_t(&)[16]>(d));
-                else tmem_ld8(tD + lane_off + TCN * (uint32_t)slot, reinterpret_cast<uint32_t(&)[8]>(d));
+                uint32_t d[2][COUT];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t ta = tD + lane_off + TCN * (uint32_t)(2 * ps + h);
+                    if (COUT == 16) tmem_ld16(ta, reinterpret_cast<uint32_t(&)[16]>(d[h]));
+                    else tmem_ld8(ta, reinterpret_cast<uint32_t(&)[8]>(d[h]));
+                }
                 tc_wait_ld();
                 {
                     uint32_t z[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) z[i] = 0u;
-                    tmem_st16(tD + lane_off + TCN * (uint32_t)slot, z);              // the next row using the slot accumulates from zero
+                    tmem_st16(tD + lane_off + TCN * (uint32_t)(2 * ps), z);          // the next rows using the slots accumulate from zero
+                    tmem_st16(tD + lane_off + TCN * (uint32_t)(2 * ps + 1), z);
                 }
                 tc_wait_st();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(d_empty(slot));          // the slot may be re-opened by a later row
+                if (lane == 0) mbar_arrive(d_empty(ps));            // the slot pair may be re-opened
                 TCP_T(t2);
                 TCP_ADD(0, t0, t1); TCP_ADD(1, t1, t2); TCP_ADD(2, t2 - 1, t2);
-                float acc[COUT];
+                float acc[2][COUT];
 #pragma unroll
-                for (int o = 0; o < COUT; ++o) acc[o] = fmaxf(__uint_as_float(d[o]) + bias[o], 0.f);
-                const int oy = y0 + y;
-                const int yy = oy - p.crop_y, xx = vx - p.crop_x;
-                const bool inside = in_x && yy >= 0 && yy < p.crop_H && xx >= 0 && xx < p.crop_W;
-                if (EPI == EPI_DOT) {
-                    if (inside) {
-                        float s = 0.f;
+                for (int h = 0; h < 2; ++h)
 #pragma unroll
-                        for (int o = 0; o < 8; ++o) s = fmaf(acc[o], dotw[o], s);
-                        if (job.dot_in) s += job.dot_in[(long long)yy * job.dot_in_rs + xx];
-                        if (job.dot_final) {
-                            s += dotb;
-                            s = 1.f / (1.f + expf(-s));
+                    for (int o = 0; o < COUT; ++o) acc[h][o] = fmaxf(__uint_as_float(d[h][o]) + bias[o], 0.f);
+                const int xx = vx - p.crop_x;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int oy = y0 + 2 * m + h;
+                    const int yy = oy - p.crop_y;
+                    const bool inside = in_x && oy < H && yy >= 0 && yy < p.crop_H && xx >= 0 && xx < p.crop_W;
+                    if (EPI == EPI_DOT) {
+                        if (inside) {
+                            float sacc = 0.f;
+#pragma unroll
+                            for (int o = 0; o < 8; ++o) sacc = fmaf(acc[h][o], dotw[o], sacc);
+                            if (job.dot_in) sacc += job.dot_in[(long long)yy * job.dot_in_rs + xx];
+                            if (job.dot_final) {
+                                sacc += dotb;
+                                sacc = 1.f / (1.f + expf(-sacc));
+                            }
+                            job.dot_out[(long long)yy * job.dot_out_rs + xx] = sacc;
                         }
-                        job.dot_out[(long long)yy * job.dot_out_rs + xx] = s;
-                    }
-                } else {
-                    if (job.out && inside) {
+                    } else if (job.out && inside) {
                         float* dst = job.out + (long long)yy * job.out_rs + xx;
 #pragma unroll
-                        for (int o = 0; o < COUT; ++o) dst[(long long)o * job.out_cs] = acc[o];
+                        for (int o = 0; o < COUT; ++o) dst[(long long)o * job.out_cs] = acc[h][o];
                     }
-                    if (EPI == EPI_POOL) {
-                        const int py = oy >> 1, pxl = vx >> 1;
-                        const bool st = (y & 1) && !(lane & 1) && py < (H >> 1) && pxl < (W >> 1);
+                }
+                if (EPI == EPI_POOL) {                               // 2x2 max over (rows 2m, 2m+1) x (lanes 2k, 2k+1)
+                    const int py = (y0 >> 1) + m, pxl = vx >> 1;
+                    const bool stp = !(lane & 1) && py < (H >> 1) && pxl < (W >> 1);
 #pragma unroll
-                        for (int o = 0; o < COUT; ++o) {
-                            const float hm = fmaxf(acc[o], __shfl_xor_sync(FULL, acc[o], 1));
-                            if (y & 1) {
-                                if (st) job.pool[(long long)o * job.pool_cs + (long long)py * job.pool_rs + pxl] = fmaxf(prev[o], hm);
-                            } else {
-                                prev[o] = hm;
-                            }
-                        }
+                    for (int o = 0; o < COUT; ++o) {
+                        const float vm = fmaxf(acc[0][o], acc[1][o]);
+                        const float hm = fmaxf(vm, __shfl_xor_sync(FULL, vm, 1));
+                        if (stp) job.pool[(long long)o * job.pool_cs + (long long)py * job.pool_rs + pxl] = hm;
                     }
                 }
             }
-            g0 += nrows;
+            P0 += npairs;
         }
         if (tid == W_EPI0 * 32) TCP_FLUSH(16);
     } else if (warp == W_MMA) {
@@ -285,88 +304,69 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
             const uint32_t sW = smem_u32(sm);
             constexpr uint32_t ID48 = umma_idesc_tf32(TCM, 3 * TCN);
             const uint64_t bd_hi = make_bdesc(sW), bd_lo = make_bdesc(sW + G::BMAT);
-            TCP_DECL;
-            // flattened (tile, input row) walk; the mbarrier probes of row i+1 are issued before the UMMAs of row i so that
-            // their round trip through the synchronisation unit is hidden behind the UMMA issue
-            int tile = blockIdx.x;
-            if (tile < ntiles) {
-                int nrows = tile_rows(tile), r = -1, g0 = 0, i = 0;
-                uint32_t ok_full = mbar_test(full_a(0), 0u);
-                uint32_t ok_d = 1u;                                   // rows 0 .. ND-1 open freshly zeroed slots
-#pragma unroll 1
-                for (;;) {
-                    const int buf = i & (NA - 1);
-                    TCP_T(t0);
-                    if (!ok_full) mbar_wait_sleep(full_a(buf), (uint32_t)(i / NA) & 1u);
-                    TCP_T(t1);
-                    if (!ok_d) {                     // this input row opens output row r+1: its accumulator slot must be drained
-                        const int g = g0 + r + 1;
-                        mbar_wait_sleep(d_empty(g & (ND - 1)), (uint32_t)(g / ND - 1) & 1u);
-                    }
-                    tc_fence_after();
-                    TCP_T(t2);
-                    // ---- next row's coordinates and barrier probes ----
-                    int tile_n = tile, r_n = r + 1, nrows_n = nrows, g0_n = g0;
-                    bool more = true;
-                    if (r_n > nrows) {
-                        tile_n += gridDim.x;
-                        more = tile_n < ntiles;
-                        r_n = -1;
-                        g0_n = g0 + nrows;
-                        if (more) nrows_n = tile_rows(tile_n);
-                    }
-                    if (more) {
-                        ok_full = mbar_test(full_a((i + 1) & (NA - 1)), (uint32_t)((i + 1) / NA) & 1u);
-                        ok_d = 1u;
-                        if (r_n + 1 < nrows_n) {
-                            const int g = g0_n + r_n + 1;
-                            if (g >= ND) ok_d = mbar_test(d_empty(g & (ND - 1)), (uint32_t)(g / ND - 1) & 1u);
-                        }
-                    }
-                    const uint32_t tAhi = tbase + (uint32_t)buf * G::A_COLS, tAlo = tAhi + G::KROW;
-                    const int sa3 = (g0 + r - 1) & (ND - 1);
-                    if (r >= 1 && r <= nrows - 2 && sa3 <= ND - 3) {
-                        // common case: three valid output rows r-1, r, r+1 in adjacent slots -> ONE N=48 UMMA per k-step and
-                        // split term, loop-invariant B descriptors
-                        const uint32_t d = tD + TCN * (uint32_t)sa3;
+            // all UMMAs of one input row r (tile-local, -1 .. nrows) whose A operand sits at tA; g0 = running index of the
+            // tile's first output row (even)
+            auto issue_row = [&](int r, int nrows, int g0, uint32_t tAhi) {
+                const uint32_t tAlo = tAhi + G::KROW;
+                const int sa3 = (g0 + r - 1) & (ND - 1);
+                if (r >= 1 && r <= nrows - 2 && sa3 <= ND - 3) {
+                    // common case: three valid output rows r-1, r, r+1 in adjacent slots -> ONE N=48 UMMA per k-step and
+                    // split term, loop-invariant B descriptors
+                    const uint32_t d = tD + TCN * (uint32_t)sa3;
 #pragma unroll
-                        for (int j = 0; j < G::KSTEPS; ++j) {
-                            const uint64_t koff = (uint64_t)(((j >> 2) * G::BATOM + (j & 3) * 32) >> 4);   // address field: 16-byte units
-                            umma_tf32_ts(d, tAhi + 8 * j, bd_hi + koff, ID48, 1u);
-                            umma_tf32_ts(d, tAlo + 8 * j, bd_hi + koff, ID48, 1u);
-                            umma_tf32_ts(d, tAhi + 8 * j, bd_lo + koff, ID48, 1u);
-                        }
-                    } else {
-                        // tile borders and ring wrap: valid output rows [ya, yb] within {r-1, r, r+1}; their accumulators are
-                        // consecutive ring slots -> one UMMA of N = 16 * rows, or two where the ring wraps (slot 7 -> 0)
-                        const int ya = r - 1 < 0 ? 0 : r - 1, yb = r + 1 > nrows - 1 ? nrows - 1 : r + 1;
-                        const int sa = (g0 + ya) & (ND - 1), len = yb - ya + 1;
-                        const int len1 = len < ND - sa ? len : ND - sa, len2 = len - len1;
-                        const int blk = ya - (r - 1);                              // first 16-row block of B: 0 = ky 2, 1 = ky 1, 2 = ky 0
-                        const uint32_t d1 = tD + TCN * (uint32_t)sa, d2 = tD;
-                        const uint32_t id1 = umma_idesc_tf32(TCM, TCN * len1), id2 = umma_idesc_tf32(TCM, TCN * len2);
-                        const uint64_t o1 = (uint64_t)((uint32_t)blk * (TCN * 128) >> 4), o2 = (uint64_t)((uint32_t)(blk + len1) * (TCN * 128) >> 4);
+                    for (int j = 0; j < G::KSTEPS; ++j) {
+                        const uint64_t koff = (uint64_t)(((j >> 2) * G::BATOM + (j & 3) * 32) >> 4);   // address field: 16-byte units
+                        umma_tf32_ts(d, tAhi + 8 * j, bd_hi + koff, ID48, 1u);
+                        umma_tf32_ts(d, tAlo + 8 * j, bd_hi + koff, ID48, 1u);
+                        umma_tf32_ts(d, tAhi + 8 * j, bd_lo + koff, ID48, 1u);
+                    }
+                } else {
+                    // tile borders and ring wrap: valid output rows [ya, yb] within {r-1, r, r+1}; their accumulators are
+                    // consecutive ring slots -> one UMMA of N = 16 * rows, or two where the ring wraps (slot 7 -> 0)
+                    const int ya = r - 1 < 0 ? 0 : r - 1, yb = r + 1 > nrows - 1 ? nrows - 1 : r + 1;
+                    const int sa = (g0 + ya) & (ND - 1), len = yb - ya + 1;
+                    const int len1 = len < ND - sa ? len : ND - sa, len2 = len - len1;
+                    const int blk = ya - (r - 1);                              // first 16-row block of B: 0 = ky 2, 1 = ky 1, 2 = ky 0
+                    const uint32_t d1 = tD + TCN * (uint32_t)sa, d2 = tD;
+                    const uint32_t id1 = umma_idesc_tf32(TCM, TCN * len1), id2 = umma_idesc_tf32(TCM, TCN * len2);
+                    const uint64_t o1 = (uint64_t)((uint32_t)blk * (TCN * 128) >> 4), o2 = (uint64_t)((uint32_t)(blk + len1) * (TCN * 128) >> 4);
 #pragma unroll 1
-                        for (int j = 0; j < G::KSTEPS; ++j) {
-                            const uint64_t koff = (uint64_t)(((j >> 2) * G::BATOM + (j & 3) * 32) >> 4);
-                            umma_tf32_ts(d1, tAhi + 8 * j, bd_hi + o1 + koff, id1, 1u);
-                            umma_tf32_ts(d1, tAlo + 8 * j, bd_hi + o1 + koff, id1, 1u);
-                            umma_tf32_ts(d1, tAhi + 8 * j, bd_lo + o1 + koff, id1, 1u);
-                            if (len2 > 0) {
-                                umma_tf32_ts(d2, tAhi + 8 * j, bd_hi + o2 + koff, id2, 1u);
-                                umma_tf32_ts(d2, tAlo + 8 * j, bd_hi + o2 + koff, id2, 1u);
-                                umma_tf32_ts(d2, tAhi + 8 * j, bd_lo + o2 + koff, id2, 1u);
-                            }
+                    for (int j = 0; j < G::KSTEPS; ++j) {
+                        const uint64_t koff = (uint64_t)(((j >> 2) * G::BATOM + (j & 3) * 32) >> 4);
+                        umma_tf32_ts(d1, tAhi + 8 * j, bd_hi + o1 + koff, id1, 1u);
+                        umma_tf32_ts(d1, tAlo + 8 * j, bd_hi + o1 + koff, id1, 1u);
+                        umma_tf32_ts(d1, tAhi + 8 * j, bd_lo + o1 + koff, id1, 1u);
+                        if (len2 > 0) {
+                            umma_tf32_ts(d2, tAhi + 8 * j, bd_hi + o2 + koff, id2, 1u);
+                            umma_tf32_ts(d2, tAlo + 8 * j, bd_hi + o2 + koff, id2, 1u);
+                            umma_tf32_ts(d2, tAhi + 8 * j, bd_lo + o2 + koff, id2, 1u);
                         }
                     }
+                }
+            };
+            int B = 0, P0 = 0;
+            TCP_DECL;
+#pragma unroll 1
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int nrows = tile_rows(tile), nb = nrows / 2 + 1;
+#pragma unroll 1
+                for (int b = 0; b < nb; ++b, ++B) {
+                    const int pb = B & (NP - 1);
+                    TCP_T(t0);
+                    mbar_wait_sleep(full_a(pb), (uint32_t)(B / NP) & 1u);     // both rows staged (and their new slots drained)
+                    tc_fence_after();
+                    TCP_T(t1);
+                    const uint32_t tA0 = tbase + (uint32_t)(2 * pb) * G::A_COLS;
+                    issue_row(2 * b - 1, nrows, 2 * P0, tA0);
+                    TCP_T(t2);
+                    issue_row(2 * b, nrows, 2 * P0, tA0 + G::A_COLS);
                     TCP_T(t3);
-                    umma_commit(empty_a(buf));                                    // the A buffer may be refilled
-                    if (r >= 1) umma_commit(d_full((g0 + r - 1) & (ND - 1)));      // output row r-1 is final
+                    umma_commit(empty_a(pb));                                  // the A buffer pair may be refilled
+                    if (b >= 1) umma_commit(d_full((P0 + b - 1) & (NDP - 1)));   // output rows 2b-2, 2b-1 are final
                     TCP_T(t4);
                     TCP_ADD(0, t0, t1); TCP_ADD(1, t1, t2); TCP_ADD(2, t2, t3); TCP_ADD(3, t3, t4); TCP_ADD(4, t4 - 1, t4);
-                    if (!more) break;
-                    tile = tile_n; r = r_n; nrows = nrows_n; g0 = g0_n; ++i;
                 }
+                P0 += nb - 1;
             }
             TCP_FLUSH(0);
         }

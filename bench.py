@@ -86,7 +86,7 @@ def synth_ids_slab(H: int, W: int, R: int, lo: int, hi: int, device, seed: int =
 
 # per-kernel algorithmic work: FLOP and HBM bytes per processed pixel of that launch
 def _conv_work(name):
-    ca, cb, co, epi = name[len("conv3x3<"):-1].split(",")
+    ca, cb, co, epi = name[name.index("<") + 1:-1].split(",")
     cin, co = int(ca) + int(cb), int(co)
     flop = 2 * 9 * cin * co
     out_b = {"store": co * 4, "pool": co * 4 + co, "dot": 4 + 4}[epi]
@@ -103,9 +103,14 @@ def kernel_table(prof, ms_total, hbm_peak, tensor_peak):
     for name, (ms, n, units) in prof.items():
         if ms <= 0:
             continue
-        if name.startswith("conv3x3<"):
+        if name.startswith("conv3x3_tc<"):
             flop, byts = _conv_work(name)
-            bound, note = "hbm" if flop / byts < 11 else "tensor", "fp32 FFMA2 stencil (no tensor cores: N<=16, see DESIGN.md §3); " \
+            bound = "hbm"
+            note = ("tcgen05 implicit GEMM, 3xTF32 (3 MMAs per algorithmic MAC at half the bf16 rate -> tensor ceiling = peak/6 = "
+                    f"{tensor_peak / 6:.0f} TFLOP/s): the layer moves (Cin+Cout)*4 B per pixel and is HBM-bound")
+        elif name.startswith("conv3x3<"):
+            flop, byts = _conv_work(name)
+            bound, note = "hbm" if flop / byts < 11 else "tensor", "fp32 FFMA2 stencil (first layer: reflect padding + channel remap, Cin 2|4); " \
                 "compare `tflops` with fp32_simt.peak_tflops_measured_ffma2"
         elif name.startswith("convt2x2<"):
             c = int(name[len("convt2x2<"):-1])
@@ -438,12 +443,18 @@ def main():
         b.record()
         torch.cuda.synchronize()
         fp32_peak = 2 * 32 * iters * nthr / (a.elapsed_time(b) * 1e-3) / 1e12
-        conv_ms = sum(k["ms"] for k in kernels if k["kernel"].startswith("conv3x3"))
-        conv_fl = sum(k["tflops"] * k["ms"] for k in kernels if k["kernel"].startswith("conv3x3"))
+        conv_ms = sum(k["ms"] for k in kernels if k["kernel"].startswith("conv3x3<"))
+        conv_fl = sum(k["tflops"] * k["ms"] for k in kernels if k["kernel"].startswith("conv3x3<"))
+        tc_ms = sum(k["ms"] for k in kernels if k["kernel"].startswith("conv3x3_tc<"))
+        tc_fl = sum(k["tflops"] * k["ms"] for k in kernels if k["kernel"].startswith("conv3x3_tc<"))
+        tc_gb = sum(k["gbs"] * k["ms"] for k in kernels if k["kernel"].startswith("conv3x3_tc<"))
         fp32 = {"peak_tflops_measured_ffma2": fp32_peak,
                 "conv3x3_all_tflops": conv_fl / conv_ms if conv_ms else None,
                 "conv3x3_all_frac_of_fp32_peak": conv_fl / conv_ms / fp32_peak if conv_ms and fp32_peak else None,
-                "note": "register-resident FFMA2 loop (pc_test_fma_peak): the practical ceiling of the fp32 stencil kernels"}
+                "note": "register-resident FFMA2 loop (pc_test_fma_peak): the practical ceiling of the fp32 stencil kernels",
+                "conv3x3_tc_all_tflops_algorithmic": tc_fl / tc_ms if tc_ms else None,
+                "conv3x3_tc_all_gbs_algorithmic": tc_gb / tc_ms if tc_ms else None,
+                "conv3x3_tc_all_frac_of_hbm_peak": tc_gb / tc_ms / hbm_peak if tc_ms else None}
         if world == 1 and not args.skip_cpu_baseline:
             dt, px = cpu_reference_tiles(2)
             cpu_base = {"value": px / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",

@@ -18,8 +18,9 @@
 //                         the source = conv padding / the Up block's F.pad) into an NS-deep shared-memory ring
 //   warps 0-7   stagers : two groups alternate rows: wait s_full -> 3*Cin ld.shared (x-1, x, x+1) -> split ->
 //                         tcgen05.st into one of NA A buffers -> arrive s_empty, full_a
-//   warp 16     MMA     : one lane waits full_a (+ d_empty for the accumulator slot a row opens), issues the row's
-//                         UMMAs, commits to empty_a and, for the output row this input row completes, to d_full
+//   warps 16,17 MMA     : one lane each; issuer q owns the output row pairs with (pair & 1) == q (disjoint accumulators),
+//                         waits full_a, issues its half of the batch's UMMAs, commits to empty_a and, for a finished
+//                         pair, to d_full — while one issuer waits or commits the other keeps the tensor pipe fed
 //   warps 8-15  epilogue: two groups alternate row pairs: wait d_full -> tcgen05.ld -> arrive d_empty -> bias + ReLU
 //                         -> store | 2x2 maxpool | 1x1 logit dot + sigmoid (+ crop)
 // Precision: ~21-bit operands, fp32 accumulation — what the 1e-2 per-pixel bar needs; plain
@@ -43,11 +44,14 @@ namespace pc {
 
 #if PC_TC_PROBE
 __device__ long long g_tc_dbg[32];
+__device__ long long g_tc_trace[4096];   // [role 0..7][batch 0..63][event 0..7] clock64 stamps of CTA (0,0)
+#define TCP_TRACE(role, batch, ev) do { if (blockIdx.x == 0 && blockIdx.y == 0 && (batch) >= 64 && (batch) < 128) g_tc_trace[((role) * 64 + (batch) - 64) * 8 + (ev)] = clock64(); } while (0)
 #define TCP_T(var) const long long var = clock64()
 #define TCP_DECL long long tcp_acc[5] = {0, 0, 0, 0, 0}
 #define TCP_ADD(slot, a, b) tcp_acc[(slot) & 7] += (b) - (a)
 #define TCP_FLUSH(base) do { if (blockIdx.x == 0 && blockIdx.y == 0) for (int q = 0; q < 5; ++q) g_tc_dbg[(base) + q] = tcp_acc[q]; } while (0)
 #else
+#define TCP_TRACE(role, batch, ev)
 #define TCP_T(var)
 #define TCP_DECL
 #define TCP_ADD(slot, a, b)
@@ -58,8 +62,8 @@ constexpr int TCM = 128;           // pixels per UMMA
 constexpr int TCN = 16;            // UMMA N (output channels, zero-padded)
 constexpr int ND = 8;              // accumulator ring (output rows in flight)
 constexpr int NGROUP = 2;          // stager groups / epilogue groups (4 warps each: one per TMEM lane quarter)
-constexpr int WS_THREADS = (4 * NGROUP * 2 + 2) * 32;    // stagers + epilogue + MMA warp + TMA warp
-constexpr int W_EPI0 = 4 * NGROUP, W_MMA = 8 * NGROUP, W_TMA = 8 * NGROUP + 1;
+constexpr int WS_THREADS = (4 * NGROUP * 2 + 3) * 32;    // stagers + epilogue + 2 MMA warps + TMA warp
+constexpr int W_EPI0 = 4 * NGROUP, W_MMA = 8 * NGROUP, W_TMA = 8 * NGROUP + 2;
 constexpr int TMEM_ALL = 512;
 
 template <int CIN>
@@ -126,7 +130,7 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
     if (warp == W_MMA) tmem_alloc(smem_u32(tmem_slot), TMEM_ALL);
     if (tid == 0) {
         for (int i = 0; i < NS; ++i) { mbar_init(s_full(i), 1); mbar_init(s_empty(i), 4); }     // 4 = the stager warps of a group
-        for (int i = 0; i < NP; ++i) { mbar_init(full_a(i), 8); mbar_init(empty_a(i), 1); }     // 8 = both stager groups
+        for (int i = 0; i < NP; ++i) { mbar_init(full_a(i), 8); mbar_init(empty_a(i), 2); }     // 8 = both stager groups, 2 = both MMA issuers
         for (int i = 0; i < NDP; ++i) { mbar_init(d_full(i), 1); mbar_init(d_empty(i), 4); }    // 4 = the epilogue warps of a group
         mbar_init_fence();
     }
@@ -173,15 +177,21 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
                 const int i = 2 * B + group;                         // running input-row index = ring position
                 const int s = i % NS, pb = B & (NP - 1), n = B / NP;
                 TCP_T(t0);
-                mbar_wait_sleep(s_full(s), (uint32_t)(i / NS) & 1u);                    // the row has landed
-                TCP_T(t1);
-                if (n >= 1) mbar_wait_sleep(empty_a(pb), (uint32_t)(n - 1) & 1u);      // UMMAs that read this buffer pair are done
-                if (b < nb - 1) {                                    // this batch opens output pair b: its slots must be drained
+                if ((warp & 3) == 0 && lane == 0) TCP_TRACE(group, B, 0);
+                {
+                    // the row has landed (s_full) + the UMMAs that read this A buffer pair are done (empty_a) + the accumulator
+                    // slots of the output pair this batch opens are drained (d_empty): one merged wait
+                    const uint32_t m1 = s_full(s), p1 = (uint32_t)(i / NS) & 1u;
+                    uint32_t m2 = m1, p2 = p1, m3 = m1, p3 = p1;
+                    if (n >= 1) { m2 = empty_a(pb); p2 = (uint32_t)(n - 1) & 1u; }
                     const int P = P0 + b;
-                    if (P >= NDP) mbar_wait_sleep(d_empty(P & (NDP - 1)), (uint32_t)(P / NDP - 1) & 1u);
+                    if (b < nb - 1 && P >= NDP) { m3 = d_empty(P & (NDP - 1)); p3 = (uint32_t)(P / NDP - 1) & 1u; }
+                    mbar_wait3_sleep(m1, p1, m2, p2, m3, p3);
                 }
+                TCP_T(t1);
                 tc_fence_after();
                 TCP_T(t2);
+                if ((warp & 3) == 0 && lane == 0) TCP_TRACE(group, B, 3);
                 const float* st = stage0 + s * (G::STAGE_BYTES / 4);
                 const uint32_t tA = tbase + (uint32_t)(2 * pb + group) * G::A_COLS + lane_off;
 #pragma unroll
@@ -204,6 +214,7 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(full_a(pb));
                 TCP_T(t4);
+                if ((warp & 3) == 0 && lane == 0) TCP_TRACE(group, B, 4);
                 TCP_ADD(0, t0, t1); TCP_ADD(1, t1, t2); TCP_ADD(2, t2, t3); TCP_ADD(3, t3, t4); TCP_ADD(4, t4 - 1, t4);
             }
             P0 += nb - 1;
@@ -231,9 +242,11 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
             for (int m = group; m < npairs; m += NGROUP) {                           // row pairs alternate between the groups
                 const int P = P0 + m, ps = P & (NDP - 1);
                 TCP_T(t0);
+                if (((warp - W_EPI0) & 3) == 0 && lane == 0) TCP_TRACE(4 + group, P, 0);
                 mbar_wait_sleep(d_full(ps), (uint32_t)(P / NDP) & 1u);
                 tc_fence_after();
                 TCP_T(t1);
+                if (((warp - W_EPI0) & 3) == 0 && lane == 0) TCP_TRACE(4 + group, P, 1);
                 uint32_t d[2][COUT];
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -254,6 +267,7 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(d_empty(ps));            // the slot pair may be re-opened
                 TCP_T(t2);
+                if (((warp - W_EPI0) & 3) == 0 && lane == 0) TCP_TRACE(4 + group, P, 2);
                 TCP_ADD(0, t0, t1); TCP_ADD(1, t1, t2); TCP_ADD(2, t2 - 1, t2);
                 float acc[2][COUT];
 #pragma unroll
@@ -298,77 +312,67 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
             P0 += npairs;
         }
         if (tid == W_EPI0 * 32) TCP_FLUSH(16);
-    } else if (warp == W_MMA) {
+    } else if (warp < W_TMA) {
         if (elect_one()) {
-            // =========================== MMA issuer ===========================
+            // =========================== MMA issuers: one lane each of two warps ===========================
+            // Issuer q owns the output row pairs with (running pair index & 1) == q, i.e. its own accumulator slots, so the two
+            // never accumulate into the same TMEM columns; while one waits on a barrier or commits, the other keeps the tensor
+            // pipe fed.  A batch (input rows 2b-1, 2b) feeds exactly two pairs:
+            //   pair b-1 (rows 2b-2, 2b-1): row 2b-1 -> N=32 with B blocks [ky2, ky1];  row 2b -> N=16 (row 2b-1) with block ky2
+            //   pair b   (rows 2b, 2b+1)  : row 2b-1 -> N=16 (row 2b) with block ky0;   row 2b -> N=32 with B blocks [ky1, ky0]
+            const int q = warp - W_MMA;
             const uint32_t sW = smem_u32(sm);
-            constexpr uint32_t ID48 = umma_idesc_tf32(TCM, 3 * TCN);
+            constexpr uint32_t ID16 = umma_idesc_tf32(TCM, TCN), ID32 = umma_idesc_tf32(TCM, 2 * TCN);
             const uint64_t bd_hi = make_bdesc(sW), bd_lo = make_bdesc(sW + G::BMAT);
-            // all UMMAs of one input row r (tile-local, -1 .. nrows) whose A operand sits at tA; g0 = running index of the
-            // tile's first output row (even)
-            auto issue_row = [&](int r, int nrows, int g0, uint32_t tAhi) {
+            constexpr uint64_t BLK = (uint64_t)((TCN * 128) >> 4);              // one 16-row block of B, in descriptor address units
+            auto issue = [&](uint32_t d, uint32_t tAhi, uint64_t boff, uint32_t idesc) {
                 const uint32_t tAlo = tAhi + G::KROW;
-                const int sa3 = (g0 + r - 1) & (ND - 1);
-                if (r >= 1 && r <= nrows - 2 && sa3 <= ND - 3) {
-                    // common case: three valid output rows r-1, r, r+1 in adjacent slots -> ONE N=48 UMMA per k-step and
-                    // split term, loop-invariant B descriptors
-                    const uint32_t d = tD + TCN * (uint32_t)sa3;
 #pragma unroll
-                    for (int j = 0; j < G::KSTEPS; ++j) {
-                        const uint64_t koff = (uint64_t)(((j >> 2) * G::BATOM + (j & 3) * 32) >> 4);   // address field: 16-byte units
-                        umma_tf32_ts(d, tAhi + 8 * j, bd_hi + koff, ID48, 1u);
-                        umma_tf32_ts(d, tAlo + 8 * j, bd_hi + koff, ID48, 1u);
-                        umma_tf32_ts(d, tAhi + 8 * j, bd_lo + koff, ID48, 1u);
-                    }
-                } else {
-                    // tile borders and ring wrap: valid output rows [ya, yb] within {r-1, r, r+1}; their accumulators are
-                    // consecutive ring slots -> one UMMA of N = 16 * rows, or two where the ring wraps (slot 7 -> 0)
-                    const int ya = r - 1 < 0 ? 0 : r - 1, yb = r + 1 > nrows - 1 ? nrows - 1 : r + 1;
-                    const int sa = (g0 + ya) & (ND - 1), len = yb - ya + 1;
-                    const int len1 = len < ND - sa ? len : ND - sa, len2 = len - len1;
-                    const int blk = ya - (r - 1);                              // first 16-row block of B: 0 = ky 2, 1 = ky 1, 2 = ky 0
-                    const uint32_t d1 = tD + TCN * (uint32_t)sa, d2 = tD;
-                    const uint32_t id1 = umma_idesc_tf32(TCM, TCN * len1), id2 = umma_idesc_tf32(TCM, TCN * len2);
-                    const uint64_t o1 = (uint64_t)((uint32_t)blk * (TCN * 128) >> 4), o2 = (uint64_t)((uint32_t)(blk + len1) * (TCN * 128) >> 4);
-#pragma unroll 1
-                    for (int j = 0; j < G::KSTEPS; ++j) {
-                        const uint64_t koff = (uint64_t)(((j >> 2) * G::BATOM + (j & 3) * 32) >> 4);
-                        umma_tf32_ts(d1, tAhi + 8 * j, bd_hi + o1 + koff, id1, 1u);
-                        umma_tf32_ts(d1, tAlo + 8 * j, bd_hi + o1 + koff, id1, 1u);
-                        umma_tf32_ts(d1, tAhi + 8 * j, bd_lo + o1 + koff, id1, 1u);
-                        if (len2 > 0) {
-                            umma_tf32_ts(d2, tAhi + 8 * j, bd_hi + o2 + koff, id2, 1u);
-                            umma_tf32_ts(d2, tAlo + 8 * j, bd_hi + o2 + koff, id2, 1u);
-                            umma_tf32_ts(d2, tAhi + 8 * j, bd_lo + o2 + koff, id2, 1u);
-                        }
-                    }
+                for (int j = 0; j < G::KSTEPS; ++j) {
+                    const uint64_t koff = boff + (uint64_t)(((j >> 2) * G::BATOM + (j & 3) * 32) >> 4);   // address field: 16-byte units
+                    umma_tf32_ts(d, tAhi + 8 * j, bd_hi + koff, idesc, 1u);
+                    umma_tf32_ts(d, tAlo + 8 * j, bd_hi + koff, idesc, 1u);
+                    umma_tf32_ts(d, tAhi + 8 * j, bd_lo + koff, idesc, 1u);
                 }
             };
             int B = 0, P0 = 0;
             TCP_DECL;
 #pragma unroll 1
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const int nrows = tile_rows(tile), nb = nrows / 2 + 1;
+                const int npairs = tile_rows(tile) / 2, nb = npairs + 1;
 #pragma unroll 1
                 for (int b = 0; b < nb; ++b, ++B) {
                     const int pb = B & (NP - 1);
                     TCP_T(t0);
-                    mbar_wait_sleep(full_a(pb), (uint32_t)(B / NP) & 1u);     // both rows staged (and their new slots drained)
+                    TCP_TRACE(2 + q, B, 0);
+                    mbar_wait_sleep(full_a(pb), (uint32_t)(B / NP) & 1u);     // both rows staged (and the slots they open drained)
                     tc_fence_after();
                     TCP_T(t1);
-                    const uint32_t tA0 = tbase + (uint32_t)(2 * pb) * G::A_COLS;
-                    issue_row(2 * b - 1, nrows, 2 * P0, tA0);
+                    TCP_TRACE(2 + q, B, 1);
+                    const uint32_t tA0 = tbase + (uint32_t)(2 * pb) * G::A_COLS, tA1 = tA0 + G::A_COLS;
+                    const int Pl = P0 + b - 1, Pu = P0 + b;                   // lower / upper pair fed by this batch
+                    if ((Pl & 1) == q) {
+                        if (b >= 1) {
+                            const uint32_t d = tD + TCN * (uint32_t)(2 * (Pl & (NDP - 1)));
+                            issue(d, tA0, 0, ID32);
+                            issue(d + TCN, tA1, 0, ID16);
+                        }
+                    } else if (b < npairs) {
+                        const uint32_t d = tD + TCN * (uint32_t)(2 * (Pu & (NDP - 1)));
+                        issue(d, tA0, 2 * BLK, ID16);
+                        issue(d, tA1, BLK, ID32);
+                    }
                     TCP_T(t2);
-                    issue_row(2 * b, nrows, 2 * P0, tA0 + G::A_COLS);
+                    TCP_TRACE(2 + q, B, 2);
+                    umma_commit(empty_a(pb));                                  // the A buffer pair may be refilled (both issuers commit)
+                    if (b >= 1 && (Pl & 1) == q) umma_commit(d_full(Pl & (NDP - 1)));   // output rows 2b-2, 2b-1 are final
                     TCP_T(t3);
-                    umma_commit(empty_a(pb));                                  // the A buffer pair may be refilled
-                    if (b >= 1) umma_commit(d_full((P0 + b - 1) & (NDP - 1)));   // output rows 2b-2, 2b-1 are final
-                    TCP_T(t4);
-                    TCP_ADD(0, t0, t1); TCP_ADD(1, t1, t2); TCP_ADD(2, t2, t3); TCP_ADD(3, t3, t4); TCP_ADD(4, t4 - 1, t4);
+                    TCP_TRACE(2 + q, B, 3);
+                    TCP_ADD(0, t0, t1); TCP_ADD(1, t1, t2); TCP_ADD(2, t2, t3); TCP_ADD(3, t3 - 1, t3); TCP_ADD(4, t3 - 1, t3);
                 }
-                P0 += nb - 1;
+                P0 += npairs;
             }
-            TCP_FLUSH(0);
+            if (q == 0) TCP_FLUSH(0);
         }
     } else if (elect_one()) {
         // =========================== TMA producer: global rows -> shared-memory ring ===========================
@@ -442,6 +446,7 @@ void conv_tc_pack_layer(const float* flat, int cin, int cout, float* img) {
 extern "C" int pc_debug_tc_counters(long long* out32, int reset) {
     cudaDeviceSynchronize();
     cudaMemcpyFromSymbol(out32, pc::g_tc_dbg, sizeof(long long) * 32);
+    if (reset == 2) cudaMemcpyFromSymbol(out32, pc::g_tc_trace, sizeof(long long) * 4096);
     if (reset) { long long z[32] = {0}; cudaMemcpyToSymbol(pc::g_tc_dbg, z, sizeof(z)); }
     return 0;
 }
@@ -459,9 +464,10 @@ bool conv_tc_enabled() {
 static int conv_tc_rows() {
     static const int tr = [] {
         const char* e = getenv("POPCORN_CONV_TC_ROWS");
-        int v = e ? atoi(e) : 32;
+        int v = e ? atoi(e) : 0;                        // 0 = choose per launch
+        if (v <= 0) return 0;
         if (v < 2) v = 2;
-        return v & ~1;                                  // even: the 2x2 pool pairs rows inside a tile
+        return v & ~1;                                  // even: rows move through the pipeline in pairs
     }();
     return tr;
 }
@@ -476,13 +482,15 @@ static int launch_tc_impl(TcConvParams& p, int njobs, cudaStream_t st) {
     }();
     auto k = conv3x3_tc_kernel<CIN_A, CIN_B, COUT, EPI>;
     PC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
-    p.TR = conv_tc_rows();
+    int per_job = num_sms() / njobs;                                  // persistent CTAs of one job, one CTA per SM
+    if (per_job < 1) per_job = 1;
     p.tiles_x = cdiv(p.W, TCM);
+    p.TR = conv_tc_rows();
+    if (p.TR == 0)                                                    // auto: tall tiles (3 % halo rows) once every CTA still gets >= 8 of them
+        p.TR = ((long long)p.tiles_x * cdiv(p.H, 64) >= 8ll * per_job) ? 64 : 32;
     p.tiles_y = cdiv(p.H, p.TR);
     const int ntiles = p.tiles_x * p.tiles_y;
-    int per_job = num_sms() / njobs;                                  // persistent CTAs of one job, one CTA per SM
     if (per_job > ntiles) per_job = ntiles;
-    if (per_job < 1) per_job = 1;
     {
         ProfScope prof(cat, st, (double)p.H * p.W * njobs);
         k<<<dim3(per_job, njobs), WS_THREADS, G::SMEM_BYTES, st>>>(p);

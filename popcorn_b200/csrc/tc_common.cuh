@@ -124,6 +124,25 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t mbar, uint32_t parity) 
     }
 }
 
+// Wait for THREE barrier phases with one round trip: the probes are issued back to back, so their ~200-cycle latencies
+// through the synchronisation unit overlap instead of adding up (pass a barrier twice when fewer are needed).
+__device__ __forceinline__ void mbar_wait3_sleep(uint32_t m1, uint32_t p1, uint32_t m2, uint32_t p2, uint32_t m3, uint32_t p3) {
+    for (uint32_t spin = 0;; ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred q1, q2, q3;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 q1, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 q2, [%3], %4;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 q3, [%5], %6;\n\t"
+            "and.pred q1, q1, q2;\n\tand.pred q1, q1, q3;\n\tselp.u32 %0, 1, 0, q1;\n\t}"
+            : "=r"(done)
+            : "r"(m1), "r"(p1), "r"(m2), "r"(p2), "r"(m3), "r"(p3)
+            : "memory");
+        if (done) return;
+        if (spin > (1u << 24)) __trap();
+    }
+}
+
 // bounded spin on an mbarrier phase: a descriptor mistake must trap, never hang the GPU
 __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
     for (uint32_t spin = 0;; ++spin) {

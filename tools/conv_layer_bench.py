@@ -51,7 +51,7 @@ for cin, cout in cases:
             c = list(buf)
             def per(a, n):
                 return [round(x / max(n, 1)) for x in a]
-            print("   mma thread  rows", c[4], " wait_full_a, wait_d_empty, issue, commit =", per(c[0:4], c[4]))
+            print("   mma issuer0 batches", c[4], " wait_full_a, issue, commit =", per(c[0:3], c[4]))
             print("   stager w0   rows", c[12], " wait_s_full, wait_empty_a, stage, wait_st+arrive =", per(c[8:12], c[12]))
             print("   epilogue w8 rows", c[18], " wait_d_full, ld+zero+arrive =", per(c[16:18], c[18]))
         px = H * W

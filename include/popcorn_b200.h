@@ -203,6 +203,21 @@ int pc_finalize_map(float* map, float* map_sq, float* smap, float* smap_sq, cons
                     pc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * pc_ingest_normalize — raw bands (on-disk dtypes) -> the normalised fp32 input window [n_s2+n_s1, h, w].
+ * Replaces: the host-side .astype(np.float32) of data/PopulationDataset.py:594-604, to_cuda_inplace
+ *           (utils/utils.py:22) of 24 B/px and apply_normalize + concatenate (utils/utils.py:105-127, 162-171):
+ *           out[c] = (float(band[c]) - mean[c]) / std[c], fp32, bit-identical to the reference tensor.
+ *   s2            DEVICE planes, uint16 (s2_is_u16 = 1) or float32; element strides; output channel c reads plane
+ *                 (s2_plane_map >> 8c) & 0xff  (file order B02,B03,B04,B08 -> R,G,B,NIR is 0x03000102)
+ *   s1            DEVICE float32 planes (VV, VH)
+ *   mean, stdv    HOST arrays of n_s2 + n_s1 floats (data/config/dataset_stats.json)
+ * --------------------------------------------------------------------------------------------- */
+int pc_ingest_normalize(const void* s2, int s2_is_u16, int n_s2, long long s2_cstride, int s2_rstride,
+                        unsigned s2_plane_map, const float* s1, int n_s1, long long s1_cstride, int s1_rstride, int h,
+                        int w, const float* mean, const float* stdv, float* out, long long out_cstride, int out_rstride,
+                        pc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Unit-test hooks (tests/test_gpu_kernels.py): ONE fused conv3x3(+folded BN)+ReLU layer, optionally with a
  * second concatenated source placed at an offset (Up block) and a fused 2x2 max-pool output, and ONE
  * ConvTranspose2d(k2,s2) layer, on plain contiguous tensors.  w uses the packed block layouts above.

@@ -390,6 +390,39 @@ def synthetic_input(H: int, W: int, seed: int = 1610, B: int = 1, coarse: int = 
     return ((val - mean) / std).contiguous()
 
 
+# data/config/dataset_stats.json ("sen2springNIR", "sen1") — the values apply_normalize uses (utils/utils.py:105-127)
+REF_STATS = {
+    "sen2springNIR": {"mean": (1460.4567, 1468.2986, 1383.4556, 2226.6821), "std": (1130.7949, 1129.0261, 1053.3217, 1724.3213)},
+    "sen1": {"mean": (-11.426, -17.753), "std": (5.5983, 5.0076)},
+}
+
+
+def synthetic_raw(H: int, W: int, seed: int = 1610, coarse: int = 64):
+    """Raw bands in their on-disk form: S2 uint16 [4,H,W] in FILE band order (B02,B03,B04,B08 = B,G,R,NIR) and S1
+    float32 [2,H,W] dB (VV,VH) — what utils/01_download_mpc_country.py:108,135-137 writes."""
+    g = torch.Generator().manual_seed(seed)
+    hc, wc = (H + coarse - 1) // coarse + 1, (W + coarse - 1) // coarse + 1
+    low = F.interpolate(torch.randn(1, 6, hc, wc, generator=g), size=(H, W), mode="bilinear", align_corners=True)[0]
+    raw = 0.6 * low + 0.8 * torch.randn(6, H, W, generator=g)
+    mean = torch.tensor(S2_MEAN + S1_MEAN).view(6, 1, 1)
+    std = torch.tensor(S2_STD + S1_STD).view(6, 1, 1)
+    val = raw * std + mean                                     # channels [R,G,B,NIR,VV,VH]
+    s2_rgbn = val[:4].clamp(0, 10000).round().to(torch.int32)
+    s2_file = s2_rgbn[[2, 1, 0, 3]].to(torch.uint16).contiguous()     # file order B,G,R,NIR
+    return s2_file, val[4:6].contiguous()
+
+
+def read_and_normalize(s2_file: Tensor, s1: Tensor) -> Tensor:
+    """Restates the reference's ingest of one window: rasterio read in band order (3,2,1,4) + .astype(float32)
+    (data/PopulationDataset.py:565-567, 594-604), apply_normalize (utils/utils.py:105-127: (x - mean) / std per channel,
+    fp32) and the S2|S1 concatenation (utils/utils.py:162-171).  -> [1,6,H,W]"""
+    s2 = s2_file[[2, 1, 0, 3]].to(torch.float32)               # S2_RGBNIR_channels = (3,2,1,4), 1-based
+    st2, st1 = REF_STATS["sen2springNIR"], REF_STATS["sen1"]
+    s2n = ((s2.permute(1, 2, 0) - torch.tensor(st2["mean"])) / torch.tensor(st2["std"])).permute(2, 0, 1)
+    s1n = ((s1.to(torch.float32).permute(1, 2, 0) - torch.tensor(st1["mean"])) / torch.tensor(st1["std"])).permute(2, 0, 1)
+    return torch.cat([s2n, s1n], 0)[None].contiguous()
+
+
 def synthetic_regions(H: int, W: int, R: int = 400, seed: int = 7):
     """int32 id raster (0 = background frame, 1..R Voronoi cells) + census-style bbox table."""
     g = torch.Generator().manual_seed(seed)

@@ -53,6 +53,7 @@ SIGNATURES = {
     "pc_region_scale": (_i, [_vp, _vp, _ll, _i, _vp, _vp]),
     "pc_accumulate_tile": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "pc_finalize_map": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _vp]),
+    "pc_ingest_normalize": (_i, [_vp, _i, _i, _ll, _i, C.c_uint, _vp, _i, _ll, _i, _i, _i, _vp, _vp, _vp, _ll, _i, _vp]),
     "pc_test_conv3x3": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "pc_test_convt2x2": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "pc_test_fma_peak": (_i, [_i, _i, _i, _vp, _vp]),

@@ -118,6 +118,28 @@ def allreduce_sums(sums: torch.Tensor, group=None) -> torch.Tensor:
     return sums
 
 
+class RawRaster:
+    """A raster frame in its on-disk dtypes: Sentinel-2 [4, rows, W] uint16 (or float32) and Sentinel-1
+    [2, rows, W] float32, both on the device or both in pinned host memory.  ``s2_plane_map`` gives the plane of each
+    output channel R,G,B,NIR (GeoTIFF band order B02,B03,B04,B08 -> ops.S2_FILE_TO_RGBN).  CountryEngine.run uploads
+    16 B/pixel instead of 24 and converts + normalises on the device (csrc/ingest.cu), bit-identical to the reference's
+    .astype(float32) + apply_normalize (data/PopulationDataset.py:594-604, utils/utils.py:105-127)."""
+
+    def __init__(self, s2: torch.Tensor, s1: torch.Tensor, s2_plane_map: int = ops.S2_FILE_TO_RGBN, stats: Optional[dict] = None):
+        if s2.dim() != 3 or s1.dim() != 3 or s2.shape[0] != 4 or s1.shape[0] != 2 or s2.shape[1:] != s1.shape[1:]:
+            raise ValueError("RawRaster needs S2 [4,rows,W] and S1 [2,rows,W] of the same extent")
+        if s2.dtype not in (torch.uint16, torch.float32) or s1.dtype != torch.float32:
+            raise ValueError("RawRaster: S2 must be uint16 or float32, S1 float32")
+        if s2.is_cuda != s1.is_cuda:
+            raise ValueError("RawRaster: S2 and S1 must live on the same side (device, or pinned host)")
+        self.s2, self.s1, self.s2_plane_map, self.stats = s2, s1, s2_plane_map, stats
+        self.is_cuda = s2.is_cuda
+        self.shape = (6,) + tuple(s2.shape[1:])
+
+    def is_pinned(self) -> bool:
+        return self.s2.is_pinned() and self.s1.is_pinned()
+
+
 class CountryEngine:
     """Tiled inference of one raster frame with an ensemble of POPCORN members on the current CUDA device."""
 
@@ -137,6 +159,7 @@ class CountryEngine:
         self.in_rows = input_rows(self.windows)
         self._maps = None
         self._copy_stream = None
+        self._d2h_stream = None
         # ensemble members share the builtup pass when their building_extractor weights are identical
         # (they never receive gradients: model/popcorn.py:112-114) — SURVEY.md §8f N2
         self._bext_shared = len(self.models) > 1 and all(
@@ -169,28 +192,89 @@ class CountryEngine:
                                 self._maps, win.y0 - lo, win.x0)
             del feats, dens, scale
 
+    def _rows_final_after(self, k: int) -> int:
+        """Owned-map rows [0, n) that no window after windows[k] writes again (windows are ordered by strip)."""
+        lo, hi = self.out_rows
+        later = self.windows[k + 1:]
+        if not later:
+            return hi - lo
+        return max(0, min(w.y0 + self.overlap for w in later) - lo)
+
+    def _ship_rows(self, r0: int, r1: int, map_out: torch.Tensor, dev):
+        """Finalise map rows [r0, r1) and start their device->host copy on the download stream."""
+        if r1 <= r0:
+            return
+        ops.finalize_map(self._maps, rows=(r0, r1))
+        if self._d2h_stream is None:
+            self._d2h_stream = torch.cuda.Stream(device=dev)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        self._d2h_stream.wait_event(ev)
+        ops.copy_d2h(map_out[r0:r1], self._maps[0][r0:r1], self._d2h_stream.cuda_stream)
+
     def run(self, raster: torch.Tensor, ids: Optional[torch.Tensor], R: int, row_offset: int = 0,
-            group=None, finalize: bool = True):
-        """raster: [6, rows, W] fp32 holding raster rows [row_offset, row_offset+rows) — a CUDA tensor, or a pinned
-        host tensor (then windows are streamed H2D on a copy stream, overlapped with compute).
+            group=None, finalize: bool = True, map_out: Optional[torch.Tensor] = None):
+        """raster: [6, rows, W] fp32 normalised, holding raster rows [row_offset, row_offset+rows) — a CUDA tensor, or a
+        pinned host tensor (then windows are streamed H2D on a copy stream, overlapped with compute) — or a RawRaster
+        (uint16 S2 + float32 S1 in on-disk form, device or pinned host: converted and normalised on the device).
         ids: int32 [out_hi-out_lo, W] CUDA id raster for this rank's owned rows (or None).
+        map_out: optional pinned host tensor [owned rows, W]: finished strips are finalised and copied out while later
+        strips still compute (replaces the per-tile .cpu() of run_eval.py:127-135); the copies are asynchronous — call
+        engine.wait_download() (or torch.cuda.synchronize()) before reading map_out.
         Returns dict(map, std, scale_map, scale_std, count, sums[R] float64 all-reduced)."""
+        if map_out is not None:
+            if not finalize:
+                raise ValueError("map_out needs finalize=True")
+            if map_out.is_cuda or not map_out.is_pinned() or tuple(map_out.shape) != (self.out_rows[1] - self.out_rows[0], self.W):
+                raise ValueError("map_out must be a pinned host tensor of the owned map shape")
+        self.wait_download()                      # a previous run's download must not race the maps' re-allocation
+        self._map_out, self._shipped = map_out, 0
         dev = torch.device("cuda", torch.cuda.current_device())
         maps = self.alloc_maps(dev)
-        if raster.is_cuda:
-            for win in self.windows:
+        raw = isinstance(raster, RawRaster)
+        if raster.is_cuda and not raw:
+            for k, win in enumerate(self.windows):
                 x = raster[None, :, win.y0 - row_offset: win.y0 - row_offset + win.h, win.x0: win.x0 + win.w]
                 self._forward_window(x, win)
+                self._after_window(k, dev)
+        elif raster.is_cuda:
+            xbuf = None
+            for k, win in enumerate(self.windows):
+                r0 = win.y0 - row_offset
+                if xbuf is None or xbuf.numel() < 6 * win.h * win.w:
+                    xbuf = torch.empty(6 * max(w.h for w in self.windows) * max(w.w for w in self.windows),
+                                       dtype=torch.float32, device=dev)
+                x = xbuf[: 6 * win.h * win.w].view(6, win.h, win.w)
+                ops.ingest_normalize(raster.s2[:, r0: r0 + win.h, win.x0: win.x0 + win.w],
+                                     raster.s1[:, r0: r0 + win.h, win.x0: win.x0 + win.w], x, raster.s2_plane_map, raster.stats)
+                self._forward_window(x[None], win)
+                self._after_window(k, dev)
         else:
             self._run_streamed(raster, row_offset, dev)
         if finalize:
-            ops.finalize_map(maps)
+            if map_out is not None:
+                self._ship_rows(self._shipped, self.out_rows[1] - self.out_rows[0], map_out, dev)
+            else:
+                ops.finalize_map(maps)
         sums = torch.zeros(max(R, 1), dtype=torch.float64, device=dev)
         if ids is not None and maps[0].numel():
             ops.region_sum(maps[0], ids, R, sums)
         allreduce_sums(sums, group)
         return {"map": maps[0], "std": maps[1], "scale_map": maps[2], "scale_std": maps[3], "count": maps[4],
                 "sums": sums, "rows": self.out_rows}
+
+    def _after_window(self, k: int, dev):
+        if self._map_out is None:
+            return
+        n = self._rows_final_after(k)
+        if n > self._shipped:
+            self._ship_rows(self._shipped, n, self._map_out, dev)
+            self._shipped = n
+
+    def wait_download(self):
+        """Block until the map rows shipped through ``map_out`` have landed in host memory."""
+        if self._d2h_stream is not None:
+            self._d2h_stream.synchronize()
 
     def _run_streamed(self, raster: torch.Tensor, row_offset: int, dev):
         """Host raster -> device, one window ahead of the compute (double buffer, copy stream + events)."""
@@ -206,18 +290,31 @@ class CountryEngine:
         # big strip's compute, not just the small right-column window that sits between them
         NB = 3
         mh, mw = max(w.h for w in wins), max(w.w for w in wins)
-        bufs = [torch.empty(6 * mh * mw, dtype=torch.float32, device=dev) for _ in range(NB)]
+        raw = isinstance(raster, RawRaster)
+        if raw:   # raw bands travel in their on-disk dtypes (16 B/px); one fp32 window is produced on the device per forward
+            bufs = [(torch.empty(4 * mh * mw, dtype=raster.s2.dtype, device=dev), torch.empty(2 * mh * mw, dtype=torch.float32, device=dev))
+                    for _ in range(NB)]
+            xnorm = torch.empty(6 * mh * mw, dtype=torch.float32, device=dev)
+        else:
+            bufs = [torch.empty(6 * mh * mw, dtype=torch.float32, device=dev) for _ in range(NB)]
         ready = [torch.cuda.Event() for _ in range(NB)]
         free = [torch.cuda.Event() for _ in range(NB)]
         views = {}
 
         def upload(k):
             w = wins[k]
-            b = bufs[k % NB][: 6 * w.h * w.w].view(6, w.h, w.w)
+            r0 = w.y0 - row_offset
             with torch.cuda.stream(cs):
                 cs.wait_event(free[k % NB])
-                ops.copy_window_h2d(b, raster[:, w.y0 - row_offset: w.y0 - row_offset + w.h, w.x0: w.x0 + w.w],
-                                    cs.cuda_stream)
+                if raw:
+                    b2 = bufs[k % NB][0][: 4 * w.h * w.w].view(4, w.h, w.w)
+                    b1 = bufs[k % NB][1][: 2 * w.h * w.w].view(2, w.h, w.w)
+                    ops.copy_window_h2d(b2, raster.s2[:, r0: r0 + w.h, w.x0: w.x0 + w.w], cs.cuda_stream)
+                    ops.copy_window_h2d(b1, raster.s1[:, r0: r0 + w.h, w.x0: w.x0 + w.w], cs.cuda_stream)
+                    b = (b2, b1)
+                else:
+                    b = bufs[k % NB][: 6 * w.h * w.w].view(6, w.h, w.w)
+                    ops.copy_window_h2d(b, raster[:, r0: r0 + w.h, w.x0: w.x0 + w.w], cs.cuda_stream)
                 ready[k % NB].record(cs)
             views[k] = b
 
@@ -229,9 +326,18 @@ class CountryEngine:
             if k + NB - 1 < len(wins):
                 upload(k + NB - 1)
             main.wait_event(ready[k % NB])
-            self._forward_window(views.pop(k)[None], win)
-            free[k % NB].record(main)
-        self.h2d_bytes = sum(6 * w.h * w.w * 4 for w in wins)
+            b = views.pop(k)
+            if raw:
+                x = xnorm[: 6 * win.h * win.w].view(6, win.h, win.w)
+                ops.ingest_normalize(b[0], b[1], x, raster.s2_plane_map, raster.stats)
+                free[k % NB].record(main)          # the raw buffers are consumed by the ingest kernel
+                self._forward_window(x[None], win)
+            else:
+                self._forward_window(b[None], win)
+                free[k % NB].record(main)
+            self._after_window(k, dev)
+        px = sum(w.h * w.w for w in wins)
+        self.h2d_bytes = px * (4 * raster.s2.element_size() + 2 * 4) if raw else px * 6 * 4
 
 
 def adjust_map_to_census(map_: torch.Tensor, ids: torch.Tensor, sums: torch.Tensor, census_pop: torch.Tensor):

@@ -185,10 +185,62 @@ def accumulate_tile(dens, scale, rows, cols, maps, y0, x0):
                                              m.stride(0), y0, x0, _stream()), "pc_accumulate_tile")
 
 
-def finalize_map(maps):
+def finalize_map(maps, rows=None):
+    """Mean / std where a pixel was visited more than once (run_eval.py:140-154); ``rows`` = (r0, r1) restricts it to a
+    row range of the maps (used to finalise and ship finished strips while later strips still compute)."""
     m, msq, sm, ssq, cnt = maps
+    if rows is not None:
+        r0, r1 = rows
+        if r1 <= r0:
+            return
+        m, cnt = m[r0:r1], cnt[r0:r1]
+        msq = None if msq is None else msq[r0:r1]
+        sm = None if sm is None else sm[r0:r1]
+        ssq = None if ssq is None else ssq[r0:r1]
     _lib.check(_lib.lib().pc_finalize_map(m.data_ptr(), _ptr(msq), _ptr(sm), _ptr(ssq), cnt.data_ptr(), m.numel(),
                                           _stream()), "pc_finalize_map")
+
+
+# per-band normalisation statistics of the reference (data/config/dataset_stats.json: "sen2springNIR", "sen2spring", "sen1"),
+# in the reference's channel order S2 = (R, G, B[, NIR]), S1 = (VV, VH)
+DATASET_STATS = {
+    "sen2springNIR": {"mean": (1460.4567, 1468.2986, 1383.4556, 2226.6821), "std": (1130.7949, 1129.0261, 1053.3217, 1724.3213)},
+    "sen2spring": {"mean": (1460.4567, 1468.2986, 1383.4556), "std": (1130.7949, 1129.0261, 1053.3217)},
+    "sen1": {"mean": (-11.426, -17.753), "std": (5.5983, 5.0076)},
+}
+S2_FILE_TO_RGBN = 0x03000102      # GeoTIFF band order B02,B03,B04,B08 -> R,G,B,NIR (S2_RGBNIR_channels = (3,2,1,4), PopulationDataset.py:566)
+S2_IDENTITY = 0x03020100
+
+
+def ingest_normalize(s2: Optional[torch.Tensor], s1: Optional[torch.Tensor], out: Optional[torch.Tensor] = None,
+                     s2_plane_map: int = S2_IDENTITY, stats: Optional[dict] = None, stream: Optional[int] = None) -> torch.Tensor:
+    """Raw bands on the DEVICE -> normalised fp32 window [n_s2+n_s1, h, w] = cat[(S2-mean)/std, (S1-mean)/std]
+    (utils/utils.py:105-127, 162-171).  s2: [3|4,h,w] uint16 or float32 view (unit column stride); s1: [2,h,w] float32."""
+    import ctypes as C
+    _need_cuda(s2, s1, out)
+    stats = stats or DATASET_STATS
+    n2 = 0 if s2 is None else s2.shape[0]
+    n1 = 0 if s1 is None else s1.shape[0]
+    ref = s2 if s2 is not None else s1
+    h, w = ref.shape[1], ref.shape[2]
+    mean, std = [], []
+    if n2:
+        assert s2.dtype in (torch.uint16, torch.int16, torch.float32) and s2.stride(2) == 1
+        key = "sen2springNIR" if n2 == 4 else "sen2spring"
+        mean += list(stats[key]["mean"]); std += list(stats[key]["std"])
+    if n1:
+        assert s1.dtype == torch.float32 and s1.stride(2) == 1 and s1.shape[1:] == ref.shape[1:]
+        mean += list(stats["sen1"]["mean"]); std += list(stats["sen1"]["std"])
+    if out is None:
+        out = torch.empty(n2 + n1, h, w, dtype=torch.float32, device=ref.device)
+    assert out.shape == (n2 + n1, h, w) and out.stride(2) == 1 and out.dtype == torch.float32
+    m = (C.c_float * 6)(*mean)
+    s = (C.c_float * 6)(*std)
+    _lib.check(_lib.lib().pc_ingest_normalize(
+        _ptr(s2), 1 if (n2 and s2.dtype != torch.float32) else 0, n2, 0 if not n2 else s2.stride(0), 0 if not n2 else s2.stride(1),
+        s2_plane_map, _ptr(s1), n1, 0 if not n1 else s1.stride(0), 0 if not n1 else s1.stride(1), h, w, m, s,
+        out.data_ptr(), out.stride(0), out.stride(1), _stream() if stream is None else stream), "pc_ingest_normalize")
+    return out
 
 
 def launch_count(reset: bool = False) -> int:

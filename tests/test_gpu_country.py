@@ -110,3 +110,57 @@ def test_merging_is_refused_below_the_receptive_field(model):
     """overlap 16 < 24: tile-border padding artefacts reach the written centre, so windows must not be merged."""
     eng = ct.CountryEngine([model], 200, 236, 96, 16, merge=True)
     assert not eng.merged and all(w.h == 96 and w.w == 96 for w in eng.windows)
+
+
+@pytest.mark.parametrize("shape", [(64, 64), (37, 101), (130, 259)])
+def test_raw_ingest_is_bit_identical_to_reference_normalisation(shape):
+    """pc_ingest_normalize (uint16 S2 in file band order + float32 S1) == the reference's .astype(float32) + apply_normalize
+    + concatenate, restated in oracle.read_and_normalize (pinned to utils/utils.py in tests/test_oracle_vs_reference.py)."""
+    s2_file, s1 = po.synthetic_raw(*shape, seed=shape[0])
+    want = po.read_and_normalize(s2_file, s1)[0]
+    got = ops.ingest_normalize(s2_file.cuda(), s1.cuda(), s2_plane_map=ops.S2_FILE_TO_RGBN)
+    assert torch.equal(got.cpu(), want)
+    # a strided window of a bigger raster, float32 S2 variant, identity band order
+    H, W = shape
+    if H > 40 and W > 40:
+        big2 = s2_file[[2, 1, 0, 3]].float().cuda()
+        got = ops.ingest_normalize(big2[:, 3:H - 5, 7:W - 2], s1.cuda()[:, 3:H - 5, 7:W - 2], s2_plane_map=ops.S2_IDENTITY)
+        assert torch.equal(got.cpu(), want[:, 3:H - 5, 7:W - 2])
+
+
+@pytest.mark.parametrize("streamed", [False, True])
+def test_country_engine_on_raw_rasters_equals_normalised_input(model, streamed):
+    """RawRaster path (16 B/px upload + device-side normalisation) gives exactly the map of the fp32 path fed with the
+    reference-normalised raster."""
+    H, W, ps, ov = 520, 456, 128, 32
+    s2_file, s1 = po.synthetic_raw(H, W, seed=33)
+    norm = po.read_and_normalize(s2_file, s1)[0]
+    ids = po.synthetic_regions(H, W, 30).cuda()
+    eng = ct.CountryEngine([model], H, W, ps, ov, merge=True, rows_per_strip=2)
+    lo, hi = eng.out_rows
+    with torch.no_grad():
+        a = eng.run(norm.cuda(), ids[lo:hi].contiguous(), 31)
+        a = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in a.items()}
+        raw = ct.RawRaster(s2_file.pin_memory(), s1.pin_memory()) if streamed else ct.RawRaster(s2_file.cuda(), s1.cuda())
+        b = eng.run(raw, ids[lo:hi].contiguous(), 31)
+    assert torch.equal(a["map"], b["map"]) and torch.equal(a["count"], b["count"])
+    assert torch.allclose(a["sums"], b["sums"], rtol=1e-6)
+    if streamed:
+        assert eng.h2d_bytes == sum(w.h * w.w for w in eng.windows) * 16
+
+
+def test_map_out_streams_the_finalised_map_to_the_host(model):
+    """run(map_out=pinned) ships finished strips while later strips compute; the host copy equals the device map."""
+    H, W, ps, ov = 700, 456, 128, 32
+    raster = po.synthetic_input(H, W, seed=5)[0]
+    ids = po.synthetic_regions(H, W, 30).cuda()
+    eng = ct.CountryEngine([model], H, W, ps, ov, merge=True, rows_per_strip=2)
+    lo, hi = eng.out_rows
+    with torch.no_grad():
+        ref = eng.run(raster.cuda(), ids[lo:hi].contiguous(), 31)
+        ref_map, ref_sums = ref["map"].cpu(), ref["sums"].cpu()
+        host = torch.full((hi - lo, W), float("nan")).pin_memory()
+        out = eng.run(raster.pin_memory(), ids[lo:hi].contiguous(), 31, map_out=host)
+        eng.wait_download()
+    assert torch.equal(host, ref_map) and torch.equal(out["map"].cpu(), ref_map)
+    assert torch.allclose(out["sums"].cpu(), ref_sums, rtol=1e-6)

@@ -36,3 +36,28 @@ def test_sparse_mask_is_region(ref_model):
     with torch.no_grad():
         out = po.forward(sd, inp, padding=False, sparse=True)
     assert torch.equal(out["mask"], admin == 3)
+
+
+def test_read_and_normalize_matches_reference_apply_normalize():
+    """oracle.read_and_normalize == the reference's own apply_normalize + concatenation (utils/utils.py:105-127, 162-171)
+    on the band-reordered float32 cast of the raw window (PopulationDataset.py:565-567, 594-604), with the reference's
+    dataset_stats.json.  (Tensor.cuda is a no-op here: apply_normalize calls .cuda() on the statistics.)"""
+    import json
+    import os
+    rs.load_reference()
+    import utils.utils as ru                      # the reference module (sys.path set by the shim)
+    with open(os.path.join(rs.REF_ROOT, "data", "config", "dataset_stats.json")) as f:
+        stats = json.load(f)
+    for k in stats:
+        for kk in stats[k]:
+            stats[k][kk] = torch.tensor(stats[k][kk])
+    assert tuple(float("%.4f" % v) for v in stats["sen2springNIR"]["mean"]) == po.REF_STATS["sen2springNIR"]["mean"]
+    s2_file, s1 = po.synthetic_raw(40, 56, seed=3)
+    sample = {"S2": s2_file[[2, 1, 0, 3]].float()[None], "S1": s1.float()[None]}
+    orig = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        ref = ru.apply_transformations_and_normalize(sample, None, stats)["input"]
+    finally:
+        torch.Tensor.cuda = orig
+    assert torch.equal(po.read_and_normalize(s2_file, s1), ref)

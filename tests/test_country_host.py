@@ -118,3 +118,43 @@ def test_two_rank_partial_sums_allreduce_gloo():
     covered = _count_reference(H, W, 96, 16) > 0
     ref = po.region_sums(full_map * covered, ids, R + 1)
     assert torch.allclose(res[0], ref, rtol=1e-12) and torch.equal(res[0], res[1])
+
+
+def _ts_worker(rank, world, port, q):
+    """Season totals of row-sharded frames: each rank holds its rows of T frame maps; totals are all-reduced (gloo)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        T, H, W = 4, 64, 40
+        g = torch.Generator().manual_seed(11)
+        frames = torch.rand(T, H, W, generator=g, dtype=torch.float64)
+        lo, hi = (0, 40) if rank == 0 else (40, 64)
+        totals = torch.zeros(T + 1, dtype=torch.float64)
+        season = torch.zeros(hi - lo, W, dtype=torch.float64)
+        for t in range(T):
+            totals[t] = frames[t, lo:hi].sum()
+            season += frames[t, lo:hi]
+        season /= T
+        totals[T] = season.sum()
+        ct.allreduce_sums(totals)
+        q.put((rank, totals))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_time_series_totals_allreduce_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ts_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    g = torch.Generator().manual_seed(11)
+    frames = torch.rand(4, 64, 40, generator=g, dtype=torch.float64)
+    want = torch.cat([frames.sum((1, 2)), frames.mean(0).sum()[None]])
+    assert torch.allclose(res[0], want, rtol=1e-12) and torch.equal(res[0], res[1])

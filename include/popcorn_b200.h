@@ -169,6 +169,8 @@ int pc_head_sparse_forward(const float* hpack, int head_in, const float* feats, 
  *   grad_pack            : device float[pc_head_pack_floats(head_in)] gradient in hpack layout (w4/b4 slots =
  *                          row 0 of head.6; row 1 has zero gradient), overwritten
  *   workspace            : pc_head_bwd_workspace_bytes(head_in)
+ *   g_feats              : NULL, or device float [B, head_in, H, W] with the strides of feats, ZEROED by the caller:
+ *                          dL/dfeats is scattered to the selected pixels (needed when unetmodel is fine-tuned, N4)
  *  Deterministic: fixed grid, fixed tile->CTA assignment, two-stage fixed-order reduction, no float atomics.
  */
 size_t pc_head_bwd_workspace_bytes(int head_in);
@@ -176,7 +178,7 @@ int pc_head_sparse_backward(const float* hpack, int head_in, const float* feats,
                             long long f_cstride, const float* builtup, const int32_t* idx, const int32_t* n_dev,
                             long long n_max, long long HW, const float* g_popcount, float g_scale_coef,
                             const float* g_scale_sel, float* grad_pack, void* workspace, size_t workspace_bytes,
-                            pc_stream_t stream);
+                            float* g_feats, pc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Census aggregation.
@@ -216,6 +218,44 @@ int pc_ingest_normalize(const void* s2, int s2_is_u16, int n_s2, long long s2_cs
                         unsigned s2_plane_map, const float* s1, int n_s1, long long s1_cstride, int s1_rstride, int h,
                         int w, const float* mean, const float* stdv, float* out, long long out_cstride, int out_rstride,
                         pc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * UNet fine-tuning (the reference's default for batches < 9 M px, run_train.py:191-202).
+ * The training path runs the DDA UNet LAYER BY LAYER so that autograd (popcorn_b200/model/unet_train.py) can keep
+ * every activation.  All planes are fp32 with explicit element strides (cs = plane, rs = row).
+ *   pc_conv3x3_layer   one Conv2d 3x3 pad 1 + folded BN (+ReLU if relu) [+ fused 2x2 max-pool output]; source A
+ *                      (optional reflect folding / plane map), optional concatenated source B at an offset, weights
+ *                      in the packed block layout (w) and optionally as tcgen05 image (wtc).  With relu = 0 and the
+ *                      transposed, tap-flipped weights this is also the DGRAD of the layer.      networks.py:258-267
+ *   pc_convt2x2_layer  ConvTranspose2d k2 s2 forward                                              networks.py:302
+ *   pc_conv3x3_wgrad   dW[cin][tap][cout], db[cout] of the folded conv from its input (A | B) and the ReLU-masked output
+ *                      gradient g; deterministic two-stage reduction; accumulate != 0 adds to grad_pack
+ *   pc_relu_backward   out = (act > 0) ? g (+ add) : 0                                            (ReLU backward)
+ *   pc_maxpool2x2_relu_backward  out = (act > 0) ? skip + [act is the first max of its window] * gpool : 0
+ *                      (MaxPool2d(2) backward + the skip-connection sum + ReLU backward, networks.py:289, 318)
+ *   pc_convt2x2_dgrad / pc_convt2x2_wgrad   backward of the transposed conv (packed layout [cin][dy*2+dx][cout], bias)
+ * --------------------------------------------------------------------------------------------- */
+int pc_conv3x3_layer(const float* a, int cin_a, long long a_cs, int a_rs, int a_H, int a_W, int a_oy, int a_ox,
+                     int a_reflect, unsigned a_chmap, const float* b, int cin_b, long long b_cs, int b_rs, int b_H, int b_W,
+                     int b_oy, int b_ox, const float* w, const float* wtc, int cout, int relu, int H, int W, float* out,
+                     long long out_cs, int out_rs, float* pool, long long pool_cs, int pool_rs, pc_stream_t stream);
+int pc_convt2x2_layer(const float* in, int C, long long in_cs, int in_rs, int Hl, int Wl, const float* w, float* out,
+                      long long out_cs, int out_rs, pc_stream_t stream);
+size_t pc_conv_wgrad_workspace_bytes(int cin, int cout, int H, int W);
+int pc_conv3x3_wgrad(const float* a, int cin_a, long long a_cs, int a_rs, int a_H, int a_W, int a_oy, int a_ox,
+                     int a_reflect, unsigned a_chmap, const float* b, int cin_b, long long b_cs, int b_rs, int b_H, int b_W,
+                     int b_oy, int b_ox, const float* g, long long g_cs, int g_rs, int cout, int H, int W, float* grad_pack,
+                     int accumulate, void* workspace, size_t workspace_bytes, pc_stream_t stream);
+int pc_relu_backward(const float* g, long long g_cs, int g_rs, const float* act, long long a_cs, int a_rs, const float* add,
+                     long long d_cs, int d_rs, float* out, long long o_cs, int o_rs, int C, int H, int W, pc_stream_t stream);
+int pc_maxpool2x2_relu_backward(const float* skip, long long s_cs, int s_rs, const float* gpool, long long p_cs, int p_rs,
+                                const float* act, long long a_cs, int a_rs, float* out, long long o_cs, int o_rs, int C,
+                                int H, int W, pc_stream_t stream);
+int pc_convt2x2_dgrad(const float* gu, long long gu_cs, int gu_rs, const float* w, int C, int Hl, int Wl, float* gin,
+                      long long gi_cs, int gi_rs, pc_stream_t stream);
+size_t pc_convt_wgrad_workspace_bytes(int C, int Hl, int Wl);
+int pc_convt2x2_wgrad(const float* in, long long in_cs, int in_rs, const float* gu, long long gu_cs, int gu_rs, int C, int Hl,
+                      int Wl, float* grad_pack, int accumulate, void* workspace, size_t workspace_bytes, pc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Unit-test hooks (tests/test_gpu_kernels.py): ONE fused conv3x3(+folded BN)+ReLU layer, optionally with a

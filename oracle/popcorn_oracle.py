@@ -54,22 +54,24 @@ def _up(sd, pfx, x1, x2):
     return _double_conv(sd, f"{pfx}.conv.conv", torch.cat([x2, x1], dim=1))
 
 
-def unet_stream(sd: Dict[str, Tensor], pfx: str, z: Tensor) -> Tensor:
-    """UNet.forward with TOPOLOGY [8,16], enable_outc=False; networks.py:121-151, utils/constants.py:173."""
-    a = _double_conv(sd, f"{pfx}.inc.conv.conv", z)
-    b = _double_conv(sd, f"{pfx}.down_seq.down1.mpconv.1.conv", F.max_pool2d(a, 2))
-    c = _double_conv(sd, f"{pfx}.down_seq.down2.mpconv.1.conv", F.max_pool2d(b, 2))
+def unet_stream(sd: Dict[str, Tensor], pfx: str, z: Tensor, encoder_no_grad: bool = False) -> Tensor:
+    """UNet.forward with TOPOLOGY [8,16], enable_outc=False; networks.py:121-151, utils/constants.py:173.
+    encoder_no_grad: inc / down1 / down2 run under torch.no_grad() (networks.py:124-131)."""
+    with torch.set_grad_enabled(torch.is_grad_enabled() and not encoder_no_grad):
+        a = _double_conv(sd, f"{pfx}.inc.conv.conv", z)
+        b = _double_conv(sd, f"{pfx}.down_seq.down1.mpconv.1.conv", F.max_pool2d(a, 2))
+        c = _double_conv(sd, f"{pfx}.down_seq.down2.mpconv.1.conv", F.max_pool2d(b, 2))
     u = _up(sd, f"{pfx}.up_seq.up2", c, b)
     return _up(sd, f"{pfx}.up_seq.up1", u, a)
 
 
-def dual_stream_features(sd, copy: str, x_fusion: Tensor, S1=True, S2=True) -> Tensor:
+def dual_stream_features(sd, copy: str, x_fusion: Tensor, S1=True, S2=True, encoder_no_grad: bool = False) -> Tensor:
     """DualStreamUNet.forward(..., return_features=True); networks.py:192-211."""
     feats = []
     if S1:
-        feats.append(unet_stream(sd, f"{copy}.sar_stream", x_fusion[:, :2]))
+        feats.append(unet_stream(sd, f"{copy}.sar_stream", x_fusion[:, :2], encoder_no_grad))
     if S2:
-        feats.append(unet_stream(sd, f"{copy}.optical_stream", x_fusion[:, 2:]))
+        feats.append(unet_stream(sd, f"{copy}.optical_stream", x_fusion[:, 2:], encoder_no_grad))
     return torch.cat(feats, dim=1)
 
 
@@ -140,12 +142,12 @@ def building_score(sd, x: Tensor, S1=True, S2=True) -> Tensor:
     return torch.sigmoid(logits)[:, :, p:-p, p:-p]
 
 
-def unet_features(sd, x: Tensor, padding: bool, S1=True, S2=True) -> Tensor:
+def unet_features(sd, x: Tensor, padding: bool, S1=True, S2=True, encoder_no_grad: bool = False) -> Tensor:
     """model/popcorn.py:126-158."""
     H, W = x.shape[2:]
     top, bot, left, right = feature_padding(H, W, force=padding)
     xq = _reflect_pad(x, top, bot, left, right)
-    f = dual_stream_features(sd, "unetmodel", to_fusion_order(xq, S1, S2), S1, S2)
+    f = dual_stream_features(sd, "unetmodel", to_fusion_order(xq, S1, S2), S1, S2, encoder_no_grad)
     return f[:, :, top:top + H, left:left + W]
 
 
@@ -178,7 +180,8 @@ def sparsity_mask(builtup: Tensor, admin_mask: Tensor, census_idx: Tensor, occup
 
 
 def forward(sd: Dict[str, Tensor], inputs: dict, padding: bool = True, sparse: bool = False,
-            occupancymodel: bool = True, sentinelbuildings: bool = True, grid=None) -> dict:
+            occupancymodel: bool = True, sentinelbuildings: bool = True, grid=None, encoder_no_grad: bool = False,
+            unet_no_grad: bool = False) -> dict:
     """POPCORN.forward, model/popcorn.py:100-193 (eval-mode BN everywhere, :128, :288-289)."""
     x = inputs["input"]
     S1, S2 = modality_flags(x.shape[1])
@@ -186,7 +189,8 @@ def forward(sd: Dict[str, Tensor], inputs: dict, padding: bool = True, sparse: b
         with torch.no_grad():
             inputs["building_counts"] = building_score(sd, x, S1, S2)
     builtup = inputs["building_counts"]
-    feats = unet_features(sd, x, padding, S1, S2)
+    with torch.set_grad_enabled(torch.is_grad_enabled() and not unet_no_grad):   # popcorn.py:147-152
+        feats = unet_features(sd, x, padding, S1, S2, encoder_no_grad)
     B, C, H, W = feats.shape
     aux = {}
     if sparse:

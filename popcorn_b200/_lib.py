@@ -47,13 +47,24 @@ SIGNATURES = {
     "pc_sparse_mask_compact": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pc_head_sparse_forward": (_i, [_vp, _i, _vp, _ll, _ll, _vp, _vp, _vp, _ll, _ll, _vp, _vp, _vp, _vp]),
     "pc_head_bwd_workspace_bytes": (_sz, [_i]),
-    "pc_head_sparse_backward": (_i, [_vp, _i, _vp, _ll, _ll, _vp, _vp, _vp, _ll, _ll, _vp, _f, _vp, _vp, _vp, _sz, _vp]),
+    "pc_head_sparse_backward": (_i, [_vp, _i, _vp, _ll, _ll, _vp, _vp, _vp, _ll, _ll, _vp, _f, _vp, _vp, _vp, _sz, _vp, _vp]),
     "pc_region_sum": (_i, [_vp, _vp, _ll, _i, _vp, _vp]),
     "pc_region_sum_backward": (_i, [_vp, _vp, _ll, _i, _vp, _vp]),
     "pc_region_scale": (_i, [_vp, _vp, _ll, _i, _vp, _vp]),
     "pc_accumulate_tile": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "pc_finalize_map": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _vp]),
     "pc_ingest_normalize": (_i, [_vp, _i, _i, _ll, _i, C.c_uint, _vp, _i, _ll, _i, _i, _i, _vp, _vp, _vp, _ll, _i, _vp]),
+    "pc_conv3x3_layer": (_i, [_vp, _i, _ll, _i, _i, _i, _i, _i, _i, C.c_uint, _vp, _i, _ll, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _i,
+                               _vp, _ll, _i, _vp, _ll, _i, _vp]),
+    "pc_convt2x2_layer": (_i, [_vp, _i, _ll, _i, _i, _i, _vp, _vp, _ll, _i, _vp]),
+    "pc_conv_wgrad_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "pc_conv3x3_wgrad": (_i, [_vp, _i, _ll, _i, _i, _i, _i, _i, _i, C.c_uint, _vp, _i, _ll, _i, _i, _i, _i, _i, _vp, _ll, _i, _i, _i, _i,
+                               _vp, _i, _vp, _sz, _vp]),
+    "pc_relu_backward": (_i, [_vp, _ll, _i, _vp, _ll, _i, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _vp]),
+    "pc_maxpool2x2_relu_backward": (_i, [_vp, _ll, _i, _vp, _ll, _i, _vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _vp]),
+    "pc_convt2x2_dgrad": (_i, [_vp, _ll, _i, _vp, _i, _i, _i, _vp, _ll, _i, _vp]),
+    "pc_convt_wgrad_workspace_bytes": (_sz, [_i, _i, _i]),
+    "pc_convt2x2_wgrad": (_i, [_vp, _ll, _i, _vp, _ll, _i, _i, _i, _i, _vp, _i, _vp, _sz, _vp]),
     "pc_test_conv3x3": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "pc_test_convt2x2": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "pc_test_fma_peak": (_i, [_i, _i, _i, _vp, _vp]),

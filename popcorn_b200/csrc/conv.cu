@@ -262,7 +262,7 @@ conv3x3_kernel(const __grid_constant__ ConvParams p) {
                 for (int o = 0; o < 4; ++o) unpack2(acc2[r][q][o], acc[r][q][2 * o], acc[r][q][2 * o + 1]);
             }
 #pragma unroll
-            for (int o = 0; o < 8; ++o) acc[r][q][o] = fmaxf(acc[r][q][o] + bias[o], 0.f);
+            for (int o = 0; o < 8; ++o) { const float t = acc[r][q][o] + bias[o]; acc[r][q][o] = job.linear ? t : fmaxf(t, 0.f); }
         }
 
     const int oy = y0 + 2 * ty, ox = x0 + 4 * tx;
@@ -789,6 +789,66 @@ extern "C" int pc_test_conv3x3(const float* a, int cin_a, int a_H, int a_W, int 
         case 80808: return launch_conv<8, 8, 8, EPI_STORE>(p, 1, st);
     }
     PC_CHECK_ARG(false, "no instantiation for this (cin_a, cin_b, cout)");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Layer-level entry points with explicit strides (the training path drives the UNet layer by layer from
+// Python so that autograd can keep every activation: popcorn_b200/model/unet_train.py).
+// ---------------------------------------------------------------------------------------------------
+extern "C" int pc_conv3x3_layer(const float* a, int cin_a, long long a_cs, int a_rs, int a_H, int a_W, int a_oy, int a_ox,
+                                int a_reflect, unsigned a_chmap, const float* b, int cin_b, long long b_cs, int b_rs, int b_H,
+                                int b_W, int b_oy, int b_ox, const float* w, const float* wtc, int cout, int relu, int H,
+                                int W, float* out, long long out_cs, int out_rs, float* pool, long long pool_cs, int pool_rs,
+                                pc_stream_t stream) {
+    PC_CHECK_ARG(a && w && out, "null pointer");
+    PC_CHECK_ARG(H >= 1 && W >= 1, "bad shape");
+    ConvParams p;
+    memset(&p, 0, sizeof(p));
+    p.H = H; p.W = W; p.crop_H = H; p.crop_W = W;
+    ConvJob& J = p.jobs[0];
+    J.a = a; J.a_cs = a_cs; J.a_rs = a_rs; J.a_H = a_H; J.a_W = a_W; J.a_oy = a_oy; J.a_ox = a_ox;
+    J.a_reflect = a_reflect; J.a_chmap = a_chmap;
+    J.b = b; J.b_cs = b_cs; J.b_rs = b_rs; J.b_H = b_H; J.b_W = b_W; J.b_oy = b_oy; J.b_ox = b_ox;
+    J.w = w; J.wtc = wtc; J.linear = relu ? 0 : 1;
+    J.out = out; J.out_cs = out_cs; J.out_rs = out_rs;
+    J.out_vec = (out_rs % 4 == 0) && (out_cs % 4 == 0) && (((uintptr_t)out) % 16 == 0);
+    J.pool = pool; J.pool_cs = pool_cs; J.pool_rs = pool_rs;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int key = cin_a * 10000 + cin_b * 100 + cout;
+    if (pool) {
+        PC_CHECK_ARG(pool_rs % 2 == 0 && pool_cs % 2 == 0 && (((uintptr_t)pool) % 8 == 0), "pooled planes must be 8-byte aligned with even strides");
+        if (key == 80008) return launch_conv<8, 0, 8, EPI_POOL>(p, 1, st);
+        if (key == 160016) return launch_conv<16, 0, 16, EPI_POOL>(p, 1, st);
+        PC_CHECK_ARG(false, "no pooled instantiation for this shape");
+    }
+    switch (key) {
+        case 20008: return launch_conv<2, 0, 8, EPI_STORE>(p, 1, st);
+        case 40008: return launch_conv<4, 0, 8, EPI_STORE>(p, 1, st);
+        case 80008: return launch_conv<8, 0, 8, EPI_STORE>(p, 1, st);
+        case 80016: return launch_conv<8, 0, 16, EPI_STORE>(p, 1, st);
+        case 160016: return launch_conv<16, 0, 16, EPI_STORE>(p, 1, st);
+        case 161608: return launch_conv<16, 16, 8, EPI_STORE>(p, 1, st);
+        case 80808: return launch_conv<8, 8, 8, EPI_STORE>(p, 1, st);
+    }
+    PC_CHECK_ARG(false, "no instantiation for this (cin_a, cin_b, cout)");
+}
+
+extern "C" int pc_convt2x2_layer(const float* in, int C, long long in_cs, int in_rs, int Hl, int Wl, const float* w, float* out,
+                                 long long out_cs, int out_rs, pc_stream_t stream) {
+    PC_CHECK_ARG(in && w && out, "null pointer");
+    PC_CHECK_ARG(C == 8 || C == 16, "C must be 8 or 16");
+    PC_CHECK_ARG(out_rs % 2 == 0 && out_cs % 2 == 0 && (((uintptr_t)out) % 8 == 0), "output planes must be 8-byte aligned with even strides");
+    if (Hl <= 0 || Wl <= 0) return 0;
+    ConvTParams pt;
+    memset(&pt, 0, sizeof(pt));
+    pt.Hl = Hl; pt.Wl = Wl;
+    ConvTJob& J = pt.jobs[0];
+    J.in = in; J.in_cs = in_cs; J.in_rs = in_rs; J.w = w; J.out = out; J.out_cs = out_cs; J.out_rs = out_rs;
+    dim3 grid(cdiv(Wl, 32), cdiv(Hl, 4), 1), block(32, 4);
+    if (C == 8) convt2x2_kernel<8><<<grid, block, 0, (cudaStream_t)stream>>>(pt);
+    else convt2x2_kernel<16><<<grid, block, 0, (cudaStream_t)stream>>>(pt);
+    PC_LAUNCH_CHECK();
+    return 0;
 }
 
 extern "C" int pc_test_convt2x2(const float* in, int C, int Hl, int Wl, const float* w, float* out, pc_stream_t stream) {

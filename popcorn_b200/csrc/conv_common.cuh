@@ -20,6 +20,7 @@ struct ConvJob {
     const float* w;                      // SIMT: [CIN][9][COUT] then bias[COUT]
     const float* wtc;                    // tcgen05: pre-split, pre-swizzled image of the layer (conv_tc.cu), or null
     float* out; long long out_cs; int out_rs; int out_vec;
+    int linear;                          // 1: no ReLU in the epilogue (the dgrad convolutions of the UNet backward)
     float* pool; long long pool_cs; int pool_rs;
     const float* dotw;                   // [8] weights + [1] bias of the 1x1 out conv slice (EPI_DOT)
     const float* dot_in; int dot_in_rs;  // partial logits of the other stream (or null)

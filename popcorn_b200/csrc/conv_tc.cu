@@ -273,7 +273,7 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h)
 #pragma unroll
-                    for (int o = 0; o < COUT; ++o) acc[h][o] = fmaxf(__uint_as_float(d[h][o]) + bias[o], 0.f);
+                    for (int o = 0; o < COUT; ++o) { const float t = __uint_as_float(d[h][o]) + bias[o]; acc[h][o] = job.linear ? t : fmaxf(t, 0.f); }
                 const int xx = vx - p.crop_x;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {

@@ -19,6 +19,7 @@ struct HeadBwdArgs {
     const int32_t* idx; const int32_t* n_dev; long long HW;
     const float* g_pop; float g_coef; const float* g_sel;
     float* partial;   // [gridDim.x][PF]
+    float* g_feats;   // optional dL/dfeats, same strides as feats (zeroed by the caller)
 };
 
 // dst[n][m] = epilogue( sum_k src[k][m] * Wk[k][n] ),  n < 64, m < 128; thread: 4 pixels x 8 outputs.
@@ -190,6 +191,26 @@ __global__ void __launch_bounds__(256, 1) head_backward_kernel(const __grid_cons
         tile_wgrad<4>(A2, A1, g2, gb2, wa, wb);                 // dW2 += dz2 (x) h1
         tile_gemm<BN, false>(A2, A1, W2n, nullptr, lane, warp); // dz1 = (W2^T dz2) * [h1 > 0]
         if (wb < K1) tile_wgrad<1>(A1, A0, g1, gb1, wa, wb);    // dW1 += dz1 (x) h0
+        if (a.g_feats) {                                         // dfeats[ch][m] = sum_n W1t[ch][n] * dz1[n][m], scattered
+            const int m = tid & 127, half = tid >> 7;
+            const long long i = base + m;
+            if (i < total) {
+                const long long p = (long long)__ldg(a.idx + i);
+                const int b = (int)(p / a.HW);
+                const long long foff = b * a.f_bs + (p - (long long)b * a.HW);
+                float acc[K1 / 2];
+#pragma unroll
+                for (int c = 0; c < K1 / 2; ++c) acc[c] = 0.f;
+#pragma unroll 4
+                for (int n = 0; n < BN; ++n) {
+                    const float dz = A1[n * BP + m];
+#pragma unroll
+                    for (int c = 0; c < K1 / 2; ++c) acc[c] = fmaf(W1t[(half * (K1 / 2) + c) * BN + n], dz, acc[c]);
+                }
+#pragma unroll
+                for (int c = 0; c < K1 / 2; ++c) a.g_feats[foff + (half * (K1 / 2) + c) * a.f_cs] = acc[c];
+            }
+        }
         __syncthreads();
     }
 
@@ -247,7 +268,7 @@ extern "C" int pc_head_sparse_backward(const float* hpack, int head_in, const fl
                                        long long f_cstride, const float* builtup, const int32_t* idx,
                                        const int32_t* n_dev, long long n_max, long long HW, const float* g_popcount,
                                        float g_scale_coef, const float* g_scale_sel, float* grad_pack, void* workspace,
-                                       size_t workspace_bytes, pc_stream_t stream) {
+                                       size_t workspace_bytes, float* g_feats, pc_stream_t stream) {
     PC_CHECK_ARG(hpack && feats && idx && n_dev && g_popcount && grad_pack && workspace, "null pointer");
     PC_CHECK_ARG(head_in == 16 || head_in == 8, "head_in must be 16 or 8");
     PC_CHECK_ARG(HW >= 1 && n_max >= 0, "bad shape");
@@ -259,6 +280,7 @@ extern "C" int pc_head_sparse_backward(const float* hpack, int head_in, const fl
     a.pack = hpack; a.feats = feats; a.f_bs = f_bstride; a.f_cs = f_cstride; a.builtup = builtup;
     a.idx = idx; a.n_dev = n_dev; a.HW = HW; a.g_pop = g_popcount; a.g_coef = g_scale_coef; a.g_sel = g_scale_sel;
     a.partial = reinterpret_cast<float*>(round_up((long long)(uintptr_t)workspace, 256));
+    a.g_feats = g_feats;
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = bwd_grid(n_max);
     const int PF = bwd_pack_floats(head_in);

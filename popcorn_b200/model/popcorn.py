@@ -15,6 +15,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops, weights
+from . import unet_train
 from .dda import STAGE1_FEATS, load_checkpoint
 
 # forward head on tcgen05 (3xTF32, csrc/head_tc.cu) unless POPCORN_HEAD_TC=0 selects the fp32 SIMT kernel (csrc/head.cu)
@@ -58,10 +59,14 @@ class _SparseHeadFn(torch.autograd.Function):
             if builtup is not None:
                 gd = gd * builtup.reshape(-1)[sel]
             g_sel = gd if g_sel is None else g_sel + gd
-        gpack = ops.head_sparse_backward(hpack, feats, builtup, idx, n_dev, ctx.n, g_pop, 0.0, g_sel)
+        g_feats = None
+        if ctx.needs_input_grad[0]:      # unetmodel is being fine-tuned: dL/dfeats at the selected pixels
+            gpack, g_feats = ops.head_sparse_backward(hpack, feats, builtup, idx, n_dev, ctx.n, g_pop, 0.0, g_sel, want_g_feats=True)
+        else:
+            gpack = ops.head_sparse_backward(hpack, feats, builtup, idx, n_dev, ctx.n, g_pop, 0.0, g_sel)
         g = weights.unpack_head_grad(gpack, ctx.head_in)
         grads = tuple(g[f"head.{i}.{t}"] for i in (0, 2, 4, 6) for t in ("weight", "bias"))
-        return (None, None, None, None, None, None) + grads
+        return (g_feats, None, None, None, None, None) + grads
 
 
 class POPCORN(nn.Module):
@@ -222,17 +227,18 @@ class POPCORN(nn.Module):
         # feature pass (popcorn.py:126-158); BN is frozen / eval on every call (:128)
         self.unetmodel.freeze_bn_layers()
         unet_trainable = any(p.requires_grad for p in self.unetmodel.parameters())
-        if torch.is_grad_enabled() and not unet_no_grad and unet_trainable and self.training:
-            raise NotImplementedError(
-                "popcorn_b200: back-propagation into unetmodel (SURVEY.md §8f row N4) is not built yet — call with "
-                "unet_no_grad=True (the census-supervised configuration of BASELINE.json) or freeze unetmodel")
         B, _, H, W = X.shape
         pads = self.feature_padding(H, W, force=bool(padding))
-        with torch.no_grad():
-            feats = ops.dda_forward(self._dda_pack("unetmodel"), X, pads, ops.PC_DDA_FEATURES)
+        if torch.is_grad_enabled() and not unet_no_grad and unet_trainable:
+            # fine-tuning path (run_train.py:191-202 for batches < 9 M px): layer-by-layer forward that keeps the
+            # activations, hand-written backward (model/unet_train.py, csrc/unet_bwd.cu)
+            feats = unet_train.unet_features(self.unetmodel, X, pads, encoder_no_grad, self.S1, self.S2)
+        else:
+            with torch.no_grad():
+                feats = ops.dda_forward(self._dda_pack("unetmodel"), X, pads, ops.PC_DDA_FEATURES)
 
         bu = builtup if self.occupancymodel else None
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.head.parameters())
+        need_grad = torch.is_grad_enabled() and (feats.requires_grad or any(p.requires_grad for p in self.head.parameters()))
         has_admin = "admin_mask" in inputs.keys()
 
         if sparse or need_grad:

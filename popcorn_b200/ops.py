@@ -129,8 +129,8 @@ def head_sparse_forward(hpack, feats, builtup, idx, n_dev, n_max, tc=False):
     return dens, scale_sel, pop
 
 
-def head_sparse_backward(hpack, feats, builtup, idx, n_dev, n_max, g_pop, g_coef, g_sel=None):
-    """-> gradient buffer in hpack layout (fp32)."""
+def head_sparse_backward(hpack, feats, builtup, idx, n_dev, n_max, g_pop, g_coef, g_sel=None, want_g_feats=False):
+    """-> gradient buffer in hpack layout (fp32) [, dL/dfeats [B,Cin,H,W] when want_g_feats]."""
     _need_cuda(hpack, feats, builtup, idx, n_dev, g_pop, g_sel)
     L = _lib.lib()
     B, Cin, H, W = feats.shape
@@ -141,11 +141,12 @@ def head_sparse_backward(hpack, feats, builtup, idx, n_dev, n_max, g_pop, g_coef
     g_pop = g_pop.float().contiguous()
     if g_sel is not None:
         g_sel = g_sel.float().contiguous()
+    g_feats = torch.zeros_like(feats) if want_g_feats else None
     _lib.check(L.pc_head_sparse_backward(hpack.data_ptr(), Cin, feats.data_ptr(), feats.stride(0), feats.stride(1),
                                          _ptr(bu), idx.data_ptr(), n_dev.data_ptr(), int(n_max), H * W,
                                          g_pop.data_ptr(), float(g_coef), _ptr(g_sel), grad.data_ptr(),
-                                         buf.data_ptr(), buf.numel(), _stream()), "pc_head_sparse_backward")
-    return grad
+                                         buf.data_ptr(), buf.numel(), _ptr(g_feats), _stream()), "pc_head_sparse_backward")
+    return (grad, g_feats) if want_g_feats else grad
 
 
 def region_sum(dens: torch.Tensor, ids: torch.Tensor, R: int, sums: Optional[torch.Tensor] = None) -> torch.Tensor:

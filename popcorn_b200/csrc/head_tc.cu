@@ -62,167 +62,215 @@ __device__ __forceinline__ void epilogue_hidden(uint32_t tD, uint32_t tAhi, uint
     }
 }
 
+// Kernel structure: ONE persistent CTA per SM, 17 warps.  Two tile contexts (each: accumulator D, A_hi, A_lo = 192 TMEM
+// columns) are worked on by their own 8 worker warps; warp 16 is the only UMMA issuer and serves the contexts in strict
+// alternation (ctx0 layer 1, ctx1 layer 1, ctx0 layer 2, ...), so one context's epilogue always runs under the other
+// context's UMMAs instead of the two drifting into the same phase.  Hand-offs are mbarriers: workers -> issuer a_ready[c]
+// (8 warp arrivals), issuer -> workers d_ready[c] (tcgen05.commit).
+constexpr int HWORK = 256;                       // worker threads per context
+constexpr int HTHREADS = 2 * HWORK + 32;
+constexpr int OFF_BARS2 = OFF_MBAR;              // a_ready[2], d_ready[2]
+constexpr int OFF_TMEM2 = OFF_BARS2 + 32;
+constexpr int OFF_PART2 = OFF_TMEM2 + 16;        // float[2][128]
+constexpr int TC2_SMEM_BYTES = (OFF_PART2 + 1024 + 1024) > 116 * 1024 ? (OFF_PART2 + 1024 + 1024) : 116 * 1024;   // > half an SM: one CTA per SM
+
 template <int K1, bool SPARSE>
-__global__ void __launch_bounds__(HT, 2) head_tc_kernel(const __grid_constant__ HeadArgs a) {
+__global__ void __launch_bounds__(HTHREADS, 1) head_tc_kernel(const __grid_constant__ HeadArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const float* vec = reinterpret_cast<const float*>(sm + OFF_VEC);
     const float* b1 = vec, *b2 = vec + 64, *b3 = vec + 128, *w4 = vec + 192, *b4 = vec + 256;
-    const uint32_t mbar = smem_u32(sm + OFF_MBAR);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + OFF_TMEM);
-    float* part = reinterpret_cast<float*>(sm + OFF_PART);
+    const uint32_t bars = smem_u32(sm + OFF_BARS2);
+    auto a_ready = [&](int c) { return bars + 8u * (uint32_t)c; };
+    auto d_ready = [&](int c) { return bars + 16u + 8u * (uint32_t)c; };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + OFF_TMEM2);
     const int tid = threadIdx.x, warp = uniform_warp_idx();
-    const int px = tid & (TM - 1);                   // pixel (= TMEM lane) of this thread inside a tile
-    const int half = warp >> 2;                      // which half of the columns this thread works on
-    constexpr int CH = K1 >= 16 ? K1 / 2 : K1;       // layer-1 feature channels per thread (K1 = 8: lower half stages all)
-    const bool stager = K1 >= 16 || half == 0;
-    const int c_lo = K1 >= 16 ? half * CH : 0;
 
-    for (int i = tid; i < TC_PACK_BYTES / 16; i += HT)
+    for (int i = tid; i < TC_PACK_BYTES / 16; i += HTHREADS)
         reinterpret_cast<int4*>(sm)[i] = __ldg(reinterpret_cast<const int4*>(a.pack) + i);
-    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 256);
-    if (tid == 0) mbar_init1(mbar);
+    if (warp == 16) tmem_alloc(smem_u32(tmem_slot), 512);
+    if (tid == 0) {
+        mbar_init(a_ready(0), 8); mbar_init(a_ready(1), 8);
+        mbar_init(d_ready(0), 1); mbar_init(d_ready(1), 1);
+        mbar_init_fence();
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // weight image (generic stores) -> visible to UMMA
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tbase = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
-    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;    // a warp may touch TMEM lanes 32*(warp%4) .. +31
-    const uint32_t tD = tbase, tAhi = tbase + 64, tAlo = tbase + 128;  // column offsets inside the 256-col block
-    const uint32_t col_off = (uint32_t)(32 * half);                  // this thread's 32 hidden units
     const uint32_t sW = smem_u32(sm);
-    uint32_t phase = 0;
 
     const long long HW = SPARSE ? a.HW : (long long)a.H * a.W;
     const long long total = SPARSE ? (long long)__ldg(a.n_dev) : HW * a.B;
+    const long long ntiles = (total + TM - 1) / TM;
+    const long long stride = 2ll * gridDim.x;                       // tiles are dealt to (CTA, context) round-robin
 
-    // pixel bookkeeping + feature fetch of one tile; the NEXT tile's features are fetched while the current tile
-    // runs its MMAs / epilogues, so the global-load latency is off the critical path
-    struct Px { long long i; bool valid; int b; long long boff, ooff, ioff; };
-    auto locate = [&](long long base, long long& foff) {
-        Px q;
-        q.i = base + px;
-        q.valid = q.i < total;
-        q.b = 0; q.boff = 0; q.ooff = 0; q.ioff = 0; foff = 0;
-        if (q.valid) {
-            const long long p = SPARSE ? (long long)__ldg(a.idx + q.i) : q.i;
-            q.b = (int)(p / HW);
-            const long long r = p - (long long)q.b * HW;
-            if (SPARSE) {
-                foff = q.b * a.f_bs + r; q.boff = p; q.ooff = p;
-            } else {
-                const int y = (int)(r / a.W), x = (int)(r - (long long)y * a.W);
-                foff = q.b * a.f_bs + (long long)y * a.f_rs + x;
-                q.boff = q.b * a.bu_bs + (long long)y * a.bu_rs + x;
-                q.ooff = q.b * a.o_bs + (long long)y * a.o_rs + x;
-                q.ioff = q.b * a.id_bs + (long long)y * a.id_rs + x;
-            }
-        }
-        return q;
-    };
-    float fcur[CH], fnext[CH];
-    long long foff0;
-    Px cur = locate((long long)blockIdx.x * TM, foff0);
-#pragma unroll
-    for (int c = 0; c < CH; ++c) fcur[c] = (cur.valid && stager) ? __ldg(a.feats + foff0 + (long long)(c_lo + c) * a.f_cs) : 0.f;
+    if (warp < 16) {
+        // =========================== workers of context c ===========================
+        const int c = warp >> 3;
+        const int wl = warp & 7, lane = tid & 31;
+        const int px = (wl & 3) * 32 + lane;            // pixel (= TMEM lane) of this thread inside a tile
+        const int half = wl >> 2;                       // which half of the columns this thread works on
+        constexpr int CH = K1 >= 16 ? K1 / 2 : K1;      // layer-1 feature channels per thread (K1 = 8: lower half stages all)
+        const bool stager = K1 >= 16 || half == 0;
+        const int c_lo = K1 >= 16 ? half * CH : 0;
+        const uint32_t lane_off = (uint32_t)((wl & 3) * 32) << 16;     // a warp may touch TMEM lanes 32*(warp%4) .. +31
+        const uint32_t tD = tbase + 256u * c, tAhi = tD + 64, tAlo = tD + 128;
+        const uint32_t col_off = (uint32_t)(32 * half);
+        float* part = reinterpret_cast<float*>(sm + OFF_PART2) + 128 * c;
+        uint32_t ph = 0;                                 // phase counter of both barriers of this context
 
-    for (long long base = (long long)blockIdx.x * TM; base < total; base += (long long)gridDim.x * TM) {
-        const long long i = cur.i;
-        const bool valid = cur.valid;
-        const int b = cur.b;
-        const long long boff = cur.boff, ooff = cur.ooff, ioff = cur.ioff;
-        // ---- layer-1 A operand: this pixel's features (this thread's channel half), split, into TMEM ----
-        if (stager) {
-#pragma unroll
-            for (int c0 = 0; c0 < CH; c0 += 8) {
-                uint32_t hi[8], lo[8];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) split_tf32(fcur[c0 + c], hi[c], lo[c]);
-                tmem_st8(tAhi + lane_off + c_lo + c0, hi);
-                tmem_st8(tAlo + lane_off + c_lo + c0, lo);
-            }
-        }
-        // ---- prefetch the next tile's features (consumed at the top of the next iteration) ----
-        long long foffn;
-        const Px nxt = locate(base + (long long)gridDim.x * TM, foffn);
-#pragma unroll
-        for (int c = 0; c < CH; ++c) fnext[c] = (nxt.valid && stager) ? __ldg(a.feats + foffn + (long long)(c_lo + c) * a.f_cs) : 0.f;
-        tc_wait_st();
-        tc_fence_before();
-        __syncthreads();
-        if (warp == 0 && elect_one()) { tc_fence_after(); issue_layer<K1>(tD, tAhi, tAlo, sW + OFF_W1HI, sW + OFF_W1LO, mbar); }
-        mbar_wait_sleep(mbar, phase); phase ^= 1;
-        tc_fence_after();
-        epilogue_hidden(tD + lane_off + col_off, tAhi + lane_off + col_off, tAlo + lane_off + col_off, b1 + col_off);
-        tc_wait_st();
-        tc_fence_before();
-        __syncthreads();
-        if (warp == 0 && elect_one()) { tc_fence_after(); issue_layer<HN>(tD, tAhi, tAlo, sW + OFF_W2HI, sW + OFF_W2LO, mbar); }
-        mbar_wait_sleep(mbar, phase); phase ^= 1;
-        tc_fence_after();
-        epilogue_hidden(tD + lane_off + col_off, tAhi + lane_off + col_off, tAlo + lane_off + col_off, b2 + col_off);
-        tc_wait_st();
-        tc_fence_before();
-        __syncthreads();
-        if (warp == 0 && elect_one()) { tc_fence_after(); issue_layer<HN>(tD, tAhi, tAlo, sW + OFF_W3HI, sW + OFF_W3LO, mbar); }
-        mbar_wait_sleep(mbar, phase); phase ^= 1;
-        tc_fence_after();
-        // ---- output layer on the CUDA cores: o = b4 + sum_n relu(D3[n] + b3[n]) * w4[n]; each thread sums its 32 hidden
-        //      units, the upper half hands its partial sum over through shared memory ----
-        float o = 0.f;
-        {
-            uint32_t v[2][16];
-            tmem_ld16(tD + lane_off + col_off, v[0]);
-            tmem_ld16(tD + lane_off + col_off + 16, v[1]);
-            tc_wait_ld();
-#pragma unroll
-            for (int q = 0; q < 2; ++q)
-#pragma unroll
-                for (int k = 0; k < 16; ++k)
-                    o = fmaf(fmaxf(__uint_as_float(v[q][k]) + b3[col_off + 16 * q + k], 0.f), w4[col_off + 16 * q + k], o);
-        }
-        tc_fence_before();   // D is overwritten by the next tile's first UMMA after the next __syncthreads
-        if (half == 1) part[px] = o;
-        __syncthreads();
-        if (half == 0) {
-            const float s = fmaxf(b4[0] + o + part[px], 0.f);
-            float d = 0.f; int bin = -1;
-            if (valid) {
-                d = a.builtup ? s * __ldg(a.builtup + boff) : s;
-                a.dens[ooff] = d;
-                if (SPARSE) { if (a.scale_sel) a.scale_sel[i] = s; }
-                else if (a.scale) a.scale[ooff] = s;
-                if (a.sums) {
-                    if (SPARSE) bin = b;
-                    else if (a.census_idx) bin = (a.ids == nullptr || __ldg(a.ids + ioff) == __ldg(a.census_idx + b)) ? b : -1;
-                    else if (a.ids) { const int id = __ldg(a.ids + ioff); bin = (id >= 0 && id < a.R) ? id : -1; }
-                    else bin = b;
+        struct Px { long long i; bool valid; int b; long long boff, ooff, ioff; };
+        auto locate = [&](long long tile, long long& foff) {
+            Px q;
+            q.i = tile * TM + px;
+            q.valid = tile < ntiles && q.i < total;
+            q.b = 0; q.boff = 0; q.ooff = 0; q.ioff = 0; foff = 0;
+            if (q.valid) {
+                const long long p = SPARSE ? (long long)__ldg(a.idx + q.i) : q.i;
+                q.b = (int)(p / HW);
+                const long long r = p - (long long)q.b * HW;
+                if (SPARSE) {
+                    foff = q.b * a.f_bs + r; q.boff = p; q.ooff = p;
+                } else {
+                    const int y = (int)(r / a.W), x = (int)(r - (long long)y * a.W);
+                    foff = q.b * a.f_bs + (long long)y * a.f_rs + x;
+                    q.boff = q.b * a.bu_bs + (long long)y * a.bu_rs + x;
+                    q.ooff = q.b * a.o_bs + (long long)y * a.o_rs + x;
+                    q.ioff = q.b * a.id_bs + (long long)y * a.id_rs + x;
                 }
             }
-            if (a.sums) bin_add(a.sums, bin, d);
-        }
-        cur = nxt;
+            return q;
+        };
+        auto hand_over = [&]() {                         // TMEM writes of this warp are done -> one arrival on a_ready[c]
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_ready(c));
+        };
+        auto wait_d = [&]() { mbar_wait_sleep(d_ready(c), ph & 1u); ++ph; tc_fence_after(); };
+
+        float fcur[CH], fnext[CH];
+        long long foff0;
+        long long tile = 2ll * blockIdx.x + c;
+        Px cur = locate(tile, foff0);
 #pragma unroll
-        for (int c = 0; c < CH; ++c) fcur[c] = fnext[c];
+        for (int k = 0; k < CH; ++k) fcur[k] = (cur.valid && stager) ? __ldg(a.feats + foff0 + (long long)(c_lo + k) * a.f_cs) : 0.f;
+
+#pragma unroll 1
+        for (; tile < ntiles; tile += stride) {
+            const long long i = cur.i;
+            const bool valid = cur.valid;
+            const int b = cur.b;
+            const long long boff = cur.boff, ooff = cur.ooff, ioff = cur.ioff;
+            // ---- layer-1 A operand: this pixel's features (this thread's channel half), split, into TMEM ----
+            if (stager) {
+#pragma unroll
+                for (int c0 = 0; c0 < CH; c0 += 8) {
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) split_tf32(fcur[c0 + k], hi[k], lo[k]);
+                    tmem_st8(tAhi + lane_off + c_lo + c0, hi);
+                    tmem_st8(tAlo + lane_off + c_lo + c0, lo);
+                }
+            }
+            hand_over();                                 // -> issuer: layer 1 of this tile may run
+            // ---- prefetch the next tile's features while the UMMAs run ----
+            long long foffn;
+            const Px nxt = locate(tile + stride, foffn);
+#pragma unroll
+            for (int k = 0; k < CH; ++k) fnext[k] = (nxt.valid && stager) ? __ldg(a.feats + foffn + (long long)(c_lo + k) * a.f_cs) : 0.f;
+            wait_d();
+            epilogue_hidden(tD + lane_off + col_off, tAhi + lane_off + col_off, tAlo + lane_off + col_off, b1 + col_off);
+            hand_over();
+            wait_d();
+            epilogue_hidden(tD + lane_off + col_off, tAhi + lane_off + col_off, tAlo + lane_off + col_off, b2 + col_off);
+            hand_over();
+            wait_d();
+            // ---- output layer on the CUDA cores: o = b4 + sum_n relu(D3[n] + b3[n]) * w4[n]; each thread sums its 32 hidden
+            //      units, the upper half hands its partial sum over through shared memory ----
+            float o = 0.f;
+            {
+                uint32_t v[2][16];
+                tmem_ld16(tD + lane_off + col_off, v[0]);
+                tmem_ld16(tD + lane_off + col_off + 16, v[1]);
+                tc_wait_ld();
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+#pragma unroll
+                    for (int k = 0; k < 16; ++k)
+                        o = fmaf(fmaxf(__uint_as_float(v[q][k]) + b3[col_off + 16 * q + k], 0.f), w4[col_off + 16 * q + k], o);
+            }
+            tc_fence_before();   // D is overwritten by the next tile's layer-1 UMMAs, which follow this context's next hand_over
+            if (half == 1) part[px] = o;
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + c), "r"(HWORK) : "memory");      // the 8 warps of this context only
+            if (half == 0) {
+                const float s = fmaxf(b4[0] + o + part[px], 0.f);
+                float d = 0.f; int bin = -1;
+                if (valid) {
+                    d = a.builtup ? s * __ldg(a.builtup + boff) : s;
+                    a.dens[ooff] = d;
+                    if (SPARSE) { if (a.scale_sel) a.scale_sel[i] = s; }
+                    else if (a.scale) a.scale[ooff] = s;
+                    if (a.sums) {
+                        if (SPARSE) bin = b;
+                        else if (a.census_idx) bin = (a.ids == nullptr || __ldg(a.ids + ioff) == __ldg(a.census_idx + b)) ? b : -1;
+                        else if (a.ids) { const int id = __ldg(a.ids + ioff); bin = (id >= 0 && id < a.R) ? id : -1; }
+                        else bin = b;
+                    }
+                }
+                if (a.sums) bin_add(a.sums, bin, d);
+            }
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + c), "r"(HWORK) : "memory");      // part[] may be rewritten by the next tile
+            cur = nxt;
+#pragma unroll
+            for (int k = 0; k < CH; ++k) fcur[k] = fnext[k];
+        }
+    } else if (elect_one()) {
+        // =========================== UMMA issuer: strict alternation between the two contexts ===========================
+        long long n[2];
+        for (int c = 0; c < 2; ++c) {
+            const long long first = 2ll * blockIdx.x + c;
+            n[c] = first < ntiles ? (ntiles - first + stride - 1) / stride : 0;
+        }
+        const long long rounds = n[0] > n[1] ? n[0] : n[1];
+        uint32_t ph[2] = {0, 0};
+#pragma unroll 1
+        for (long long k = 0; k < rounds; ++k) {
+#pragma unroll
+            for (int layer = 0; layer < 3; ++layer) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    if (k >= n[c]) continue;
+                    const uint32_t tD = tbase + 256u * c, tAhi = tD + 64, tAlo = tD + 128;
+                    mbar_wait_sleep(a_ready(c), ph[c] & 1u); ++ph[c];
+                    tc_fence_after();
+                    if (layer == 0) issue_layer<K1>(tD, tAhi, tAlo, sW + OFF_W1HI, sW + OFF_W1LO, d_ready(c));
+                    else if (layer == 1) issue_layer<HN>(tD, tAhi, tAlo, sW + OFF_W2HI, sW + OFF_W2LO, d_ready(c));
+                    else issue_layer<HN>(tD, tAhi, tAlo, sW + OFF_W3HI, sW + OFF_W3LO, d_ready(c));
+                }
+            }
+        }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tbase, 256);
+    if (warp == 16) tmem_dealloc(tbase, 512);
 }
 
 template <int K1, bool SPARSE>
 static int launch_head_tc(const HeadArgs& a, long long total_bound, cudaStream_t st) {
     auto k = head_tc_kernel<K1, SPARSE>;
-    PC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    PC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES));
     long long tiles = (total_bound + TM - 1) / TM;
-    const int maxg = num_sms() * 2;          // persistent: 2 CTAs per SM, each walks tiles grid-stride
-    int grid = (int)(tiles < maxg ? tiles : maxg);
+    const int maxg = num_sms();              // persistent: one CTA per SM (it owns all 512 TMEM columns), two tile contexts each
+    int grid = (int)((tiles + 1) / 2 < maxg ? (tiles + 1) / 2 : maxg);
     if (grid < 1) grid = 1;
     {
         static const int cat = prof_register(SPARSE ? "head_tc<sparse>" : "head_tc<dense>");
         ProfScope prof(cat, st, (double)total_bound);
-        k<<<grid, HT, TC_SMEM_BYTES, st>>>(a);
+        k<<<grid, HTHREADS, TC2_SMEM_BYTES, st>>>(a);
     }
     PC_LAUNCH_CHECK();
     return 0;

@@ -359,7 +359,8 @@ def main():
     model.load_state_dict(sd)
     model.eval()
 
-    eng = ct.CountryEngine([model], H, W, merge=not args.no_merge, rows_per_strip=args.rows_per_strip, rank=rank, world=world)
+    eng = ct.CountryEngine([model], H, W, merge=not args.no_merge, rows_per_strip=args.rows_per_strip, rank=rank, world=world,
+                           first_strip_rows=1)     # short first strip: a streamed run starts computing after a small upload
     i0, i1 = eng.in_rows
     lo, hi = eng.out_rows
     raster = synth_raster_slab(i1 - i0, W, i0, dev)

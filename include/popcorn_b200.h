@@ -74,7 +74,7 @@ int pc_dda_pack_offset(int stream, int layer);
 int pc_dda_tc_pack_base(void);
 int pc_dda_tc_pack_floats(void);
 int pc_dda_tc_pack(const float* flat_host, float* img_host);
-int pc_conv_tc_layer_floats(int cin);
+int pc_conv_tc_layer_floats(int cin, int cout);
 int pc_conv_tc_pack_layer(const float* flat_host, int cin, int cout, float* img_host);
 
 /* Head pack: W1t[k=Cin][64], b1[64], W2t[64][64], b2[64], W3t[64][64], b3[64], w4[64] (row 0 of

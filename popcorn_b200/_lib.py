@@ -34,7 +34,7 @@ SIGNATURES = {
     "pc_dda_tc_pack_base": (_i, []),
     "pc_dda_tc_pack_floats": (_i, []),
     "pc_dda_tc_pack": (_i, [_vp, _vp]),
-    "pc_conv_tc_layer_floats": (_i, [_i]),
+    "pc_conv_tc_layer_floats": (_i, [_i, _i]),
     "pc_conv_tc_pack_layer": (_i, [_vp, _i, _i, _vp]),
     "pc_dda_forward": (_i, [_vp, _ll, _vp, _i, _i, _i, _i, _ll, _ll, _i, _i, _i, _i, _i, _i, _vp, _ll, _ll, _i, _vp, _sz, _vp]),
     "pc_head_dense_forward": (_i, [_vp, _i, _vp, _ll, _ll, _i, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _ll, _i, _vp, _ll, _i,

@@ -54,8 +54,10 @@ def grid_origins(n: int, patch: int = PATCH, overlap: int = OVERLAP) -> List[int
 
 
 def plan_windows(H: int, W: int, patch: int = PATCH, overlap: int = OVERLAP, merge: bool = True,
-                 rows_per_strip: int = 2) -> List[Window]:
-    """All windows covering the raster the way get_patch_indices does (PopulationDataset.py:294-316)."""
+                 rows_per_strip: int = 2, first_strip_rows: Optional[int] = None) -> List[Window]:
+    """All windows covering the raster the way get_patch_indices does (PopulationDataset.py:294-316).
+    first_strip_rows: tile-rows of the FIRST merged strip (default rows_per_strip) — a short first strip lets a streamed
+    run start computing after a small upload instead of waiting for a whole strip."""
     if H < patch or W < patch:
         raise ValueError(f"raster {H}x{W} is smaller than the inference patch {patch}")
     xs, ys = grid_origins(H, patch, overlap), grid_origins(W, patch, overlap)
@@ -72,8 +74,12 @@ def plan_windows(H: int, W: int, patch: int = PATCH, overlap: int = OVERLAP, mer
         wins.append(Window(max_x, max_y, patch, patch, -1, 1))                   # corner
         return wins
     width = (ys[-1] + patch) if ys else 0
-    for i0 in range(0, len(xs), rows_per_strip):
-        k = min(rows_per_strip, len(xs) - i0)
+    starts, i0 = [], 0
+    while i0 < len(xs):
+        k = min(first_strip_rows if (i0 == 0 and first_strip_rows) else rows_per_strip, len(xs) - i0)
+        starts.append((i0, k))
+        i0 += k
+    for i0, k in starts:
         height = stride * (k - 1) + patch
         if ys:
             wins.append(Window(xs[i0], 0, height, width, i0, k * len(ys)))
@@ -145,14 +151,14 @@ class CountryEngine:
 
     def __init__(self, models, H: int, W: int, patch: int = PATCH, overlap: int = OVERLAP, merge: bool = True,
                  rows_per_strip: int = 2, rank: int = 0, world: int = 1, want_scale: bool = True,
-                 want_std: bool = True):
+                 want_std: bool = True, first_strip_rows: Optional[int] = None):
         self.models = list(models) if isinstance(models, (list, tuple)) else [models]
         self.H, self.W, self.patch, self.overlap = H, W, patch, overlap
         self.rank, self.world = rank, world
         self.want_scale, self.want_std = want_scale, want_std
         merge = merge and can_merge(patch, overlap)      # otherwise fall back to the reference tile grid
         self.merged = merge
-        all_w = plan_windows(H, W, patch, overlap, merge, rows_per_strip if merge else 1)
+        all_w = plan_windows(H, W, patch, overlap, merge, rows_per_strip if merge else 1, first_strip_rows if merge else None)
         n_rows = len(grid_origins(H, patch, overlap))
         self.windows = shard_windows(all_w, n_rows, rank, world, rows_per_strip if merge else 1) if world > 1 else all_w
         self.out_rows = owned_rows(self.windows, H, overlap)

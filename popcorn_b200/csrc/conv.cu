@@ -413,7 +413,7 @@ static int tc_pack_offset(int stream, int layer) {     // floats from the start 
             if (s == stream && l == layer) return off;
             if (kLayers[l].is_t) continue;
             const int cin = kLayers[l].cin < 0 ? (s == 0 ? 2 : 4) : kLayers[l].cin;
-            off += conv_tc_layer_floats(cin);
+            off += conv_tc_layer_floats(cin, kLayers[l].cout);
         }
     return off;
 }
@@ -578,7 +578,7 @@ extern "C" int pc_dda_tc_pack(const float* flat_host, float* img_host) {
         }
     return 0;
 }
-extern "C" int pc_conv_tc_layer_floats(int cin) { return conv_tc_layer_floats(cin); }
+extern "C" int pc_conv_tc_layer_floats(int cin, int cout) { return conv_tc_layer_floats(cin, cout); }
 extern "C" int pc_conv_tc_pack_layer(const float* flat_host, int cin, int cout, float* img_host) {
     PC_CHECK_ARG(flat_host && img_host && cin >= 1 && cin <= 32 && (cout == 8 || cout == 16), "bad argument");
     conv_tc_pack_layer(flat_host, cin, cout, img_host);

@@ -42,7 +42,7 @@ struct alignas(64) TcConvParams {
 bool make_tmap3d(CUtensorMap* tm, const float* ptr, int C, int H, int W, int rs, long long cs, int boxw, int boxh, int boxc);
 
 // conv_tc.cu
-int conv_tc_layer_floats(int cin);                                              // floats of one layer image
+int conv_tc_layer_floats(int cin, int cout);                                    // floats of one layer image
 void conv_tc_pack_layer(const float* flat, int cin, int cout, float* img);       // host: [cin][9][cout]+bias -> image
 bool conv_tc_enabled();
 int launch_conv_tc(int cin_a, int cin_b, int cout, int epi, TcConvParams& p, int njobs, cudaStream_t st);

@@ -66,17 +66,19 @@ constexpr int WS_THREADS = (4 * NGROUP * 2 + 3) * 32;    // stagers + epilogue +
 constexpr int W_EPI0 = 4 * NGROUP, W_MMA = 8 * NGROUP, W_TMA = 8 * NGROUP + 2;
 constexpr int TMEM_ALL = 512;
 
-template <int CIN>
+template <int CIN, int COUT>
 struct TcGeom {
+    static constexpr int SLOTW = COUT == 8 ? 8 : 16;            // accumulator columns per output row
+    static constexpr int BROWS = COUT == 8 ? 64 : 48;           // rows of a B matrix (see conv_tc_pack_layer)
     static constexpr int KROW = (3 * CIN + 7) / 8 * 8;          // A columns per half (hi | lo) of one input row
     static constexpr int KSTEPS = KROW / 8;
     static constexpr int KATOMS = (KROW + 31) / 32;             // 32-float swizzle atoms along K
-    static constexpr int BATOM = 3 * TCN * 128;                 // bytes of one K-atom: 48 rows = [W_ky2 | W_ky1 | W_ky0] x 128 B
-    static constexpr int BMAT = KATOMS * BATOM;                 // bytes of one swizzled [48 x KROW] matrix
+    static constexpr int BATOM = BROWS * 128;                   // bytes of one K-atom
+    static constexpr int BMAT = KATOMS * BATOM;                 // bytes of one swizzled [BROWS x KROW] matrix
     static constexpr int OFF_BIAS = 2 * BMAT;                   // matrices: [hi, lo]
     static constexpr int IMG_BYTES = OFF_BIAS + 64;             // + bias[16]
     static constexpr int A_COLS = 2 * KROW;                     // one A buffer: hi at [0, KROW), lo at [KROW, 2*KROW)
-    static constexpr int NA_FIT = (TMEM_ALL - ND * TCN) / A_COLS;
+    static constexpr int NA_FIT = (TMEM_ALL - ND * SLOTW) / A_COLS;
     static constexpr int NA = NA_FIT >= 4 ? 4 : 2;              // A buffers (power of two)
     static constexpr int D_COL0 = NA * A_COLS;                  // accumulator slots of 16 columns
     static constexpr int STAGE_BYTES = CIN * TC_BOXW * 4;       // one input row, all channels
@@ -89,7 +91,7 @@ struct TcGeom {
     // > half of the SM's shared memory: exactly one CTA per SM (it owns all 512 TMEM columns)
     static constexpr int SMEM_BYTES = SMEM_NEED > 116 * 1024 ? SMEM_NEED : 116 * 1024;
     static_assert(NA_FIT >= 2, "TMEM budget");
-    static_assert(D_COL0 % 16 == 0 && D_COL0 + ND * TCN <= TMEM_ALL, "accumulator ring placement");
+    static_assert(D_COL0 % 16 == 0 && D_COL0 + ND * SLOTW <= TMEM_ALL, "accumulator ring placement");
     static_assert(STAGE_BYTES % 128 == 0 && SMEM_BYTES <= 227 * 1024, "shared memory layout");
 };
 
@@ -105,7 +107,7 @@ template <int CIN_A, int CIN_B, int COUT, int EPI>
 __global__ void __launch_bounds__(WS_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
     constexpr int CIN = CIN_A + CIN_B;
-    using G = TcGeom<CIN>;
+    using G = TcGeom<CIN, COUT>;
     constexpr int NA = G::NA, NS = G::NS, NP = NA / 2, NDP = ND / 2;
     constexpr unsigned FULL = 0xffffffffu;
 
@@ -146,7 +148,7 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) z[i] = 0u;
 #pragma unroll
-        for (int i = 0; i < ND; ++i) tmem_st16(tD + lane_off + TCN * i, z);
+        for (int i = 0; i < ND * G::SLOTW / 16; ++i) tmem_st16(tD + lane_off + 16 * i, z);
         tc_wait_st();
     }
     tc_fence_before();
@@ -248,19 +250,20 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
                 TCP_T(t1);
                 if (((warp - W_EPI0) & 3) == 0 && lane == 0) TCP_TRACE(4 + group, P, 1);
                 uint32_t d[2][COUT];
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const uint32_t ta = tD + lane_off + TCN * (uint32_t)(2 * ps + h);
-                    if (COUT == 16) tmem_ld16(ta, reinterpret_cast<uint32_t(&)[16]>(d[h]));
-                    else tmem_ld8(ta, reinterpret_cast<uint32_t(&)[8]>(d[h]));
+                const uint32_t tpair = tD + lane_off + 2 * G::SLOTW * (uint32_t)ps;      // the pair's two slots are adjacent
+                if (COUT == 16) {
+                    tmem_ld16(tpair, reinterpret_cast<uint32_t(&)[16]>(d[0]));
+                    tmem_ld16(tpair + 16, reinterpret_cast<uint32_t(&)[16]>(d[1]));
+                } else {
+                    tmem_ld16(tpair, reinterpret_cast<uint32_t(&)[16]>(d[0]));             // d[0][0..7] = row 2m, d[1][0..7] = row 2m+1
                 }
                 tc_wait_ld();
                 {
                     uint32_t z[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) z[i] = 0u;
-                    tmem_st16(tD + lane_off + TCN * (uint32_t)(2 * ps), z);          // the next rows using the slots accumulate from zero
-                    tmem_st16(tD + lane_off + TCN * (uint32_t)(2 * ps + 1), z);
+                    tmem_st16(tpair, z);                                                   // the next rows using the slots accumulate from zero
+                    if (COUT == 16) tmem_st16(tpair + 16, z);
                 }
                 tc_wait_st();
                 tc_fence_before();
@@ -351,16 +354,33 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
                     TCP_TRACE(2 + q, B, 1);
                     const uint32_t tA0 = tbase + (uint32_t)(2 * pb) * G::A_COLS, tA1 = tA0 + G::A_COLS;
                     const int Pl = P0 + b - 1, Pu = P0 + b;                   // lower / upper pair fed by this batch
-                    if ((Pl & 1) == q) {
-                        if (b >= 1) {
-                            const uint32_t d = tD + TCN * (uint32_t)(2 * (Pl & (NDP - 1)));
-                            issue(d, tA0, 0, ID32);
-                            issue(d + TCN, tA1, 0, ID16);
+                    if (COUT == 16) {
+                        // B rows [W_ky2 | W_ky1 | W_ky0] (16 each): two adjacent rows of a pair = one N=32 UMMA
+                        if ((Pl & 1) == q) {
+                            if (b >= 1) {
+                                const uint32_t d = tD + 32 * (uint32_t)(Pl & (NDP - 1));
+                                issue(d, tA0, 0, ID32);                        // rows 2b-2 (ky2), 2b-1 (ky1)
+                                issue(d + 16, tA1, 0, ID16);                   // row 2b-1 (ky2)
+                            }
+                        } else if (b < npairs) {
+                            const uint32_t d = tD + 32 * (uint32_t)(Pu & (NDP - 1));
+                            issue(d, tA0, 2 * BLK, ID16);                      // row 2b (ky0)
+                            issue(d, tA1, BLK, ID32);                          // rows 2b (ky1), 2b+1 (ky0)
                         }
-                    } else if (b < npairs) {
-                        const uint32_t d = tD + TCN * (uint32_t)(2 * (Pu & (NDP - 1)));
-                        issue(d, tA0, 2 * BLK, ID16);
-                        issue(d, tA1, BLK, ID32);
+                    } else {
+                        // Cout 8: 8-column slots, a pair = 16 columns = one N=16 UMMA; B blocks of 16 rows:
+                        // X0 = [W_ky2 | W_ky1], X1 = [0 | W_ky2], X2 = [W_ky0 | 0], X3 = [W_ky1 | W_ky0]
+                        if ((Pl & 1) == q) {
+                            if (b >= 1) {
+                                const uint32_t d = tD + 16 * (uint32_t)(Pl & (NDP - 1));
+                                issue(d, tA0, 0, ID16);                        // X0: rows 2b-2 (ky2), 2b-1 (ky1)
+                                issue(d, tA1, BLK, ID16);                      // X1: row 2b-1 (ky2)
+                            }
+                        } else if (b < npairs) {
+                            const uint32_t d = tD + 16 * (uint32_t)(Pu & (NDP - 1));
+                            issue(d, tA0, 2 * BLK, ID16);                      // X2: row 2b (ky0)
+                            issue(d, tA1, 3 * BLK, ID16);                      // X3: rows 2b (ky1), 2b+1 (ky0)
+                        }
                     }
                     TCP_T(t2);
                     TCP_TRACE(2 + q, B, 2);
@@ -404,22 +424,36 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
-static int tc_geom_img_floats(int cin) {
+static int tc_brows(int cout) { return cout == 8 ? 64 : 48; }
+
+static int tc_geom_img_floats(int cin, int cout) {
     const int krow = (3 * cin + 7) / 8 * 8, katoms = (krow + 31) / 32;
-    return (2 * katoms * 3 * TCN * 128 + 64) / 4;
+    return (2 * katoms * tc_brows(cout) * 128 + 64) / 4;
 }
 
-int conv_tc_layer_floats(int cin) { return (int)round_up(tc_geom_img_floats(cin), 64); }   // 256-B multiple
+int conv_tc_layer_floats(int cin, int cout) { return (int)round_up(tc_geom_img_floats(cin, cout), 64); }   // 256-B multiple
 
-// flat = [cin][ky][kx][cout] + bias[cout] (the SIMT pack)  ->  [hi|lo][katom][48 rows][32 floats] swizzled + bias[16];
-// row 16*b + co of a matrix holds W_ky[co][k = kx*cin + ci] with ky = 2 - b (the block order of three adjacent output rows)
+// flat = [cin][ky][kx][cout] + bias[cout] (the SIMT pack)  ->  [hi|lo][katom][rows][32 floats] swizzled + bias[16], k = kx*cin + ci.
+//   cout 16: 48 rows [W_ky2 | W_ky1 | W_ky0]                         (row 16*(2-ky) + co)
+//   cout  8: 64 rows X0 = [W_ky2 | W_ky1], X1 = [0 | W_ky2], X2 = [W_ky0 | 0], X3 = [W_ky1 | W_ky0]   (8 + 8 rows each)
+// — the 16-row windows the issuers address for one or two adjacent output rows of a pair (conv3x3_tc_kernel).
 void conv_tc_pack_layer(const float* flat, int cin, int cout, float* img) {
     const int krow = (3 * cin + 7) / 8 * 8, katoms = (krow + 31) / 32;
-    const int rows = 3 * TCN;
+    const int rows = tc_brows(cout);
     const int mat = katoms * rows * 32;                 // floats per matrix
-    const int total = conv_tc_layer_floats(cin);
+    const int total = conv_tc_layer_floats(cin, cout);
     memset(img, 0, sizeof(float) * total);
-    for (int ky = 0; ky < 3; ++ky)
+    // (row offset, ky) placements of the 8/16-row weight blocks
+    int place[6][2], nplace = 0;
+    if (cout == 16) {
+        for (int ky = 0; ky < 3; ++ky) { place[nplace][0] = (2 - ky) * 16; place[nplace][1] = ky; ++nplace; }
+    } else {
+        const int p[6][2] = {{0, 2}, {8, 1}, {24, 2}, {32, 0}, {48, 1}, {56, 0}};
+        for (int i = 0; i < 6; ++i) { place[i][0] = p[i][0]; place[i][1] = p[i][1]; }
+        nplace = 6;
+    }
+    for (int pi = 0; pi < nplace; ++pi) {
+        const int r0 = place[pi][0], ky = place[pi][1];
         for (int co = 0; co < cout; ++co)
             for (int kx = 0; kx < 3; ++kx)
                 for (int ci = 0; ci < cin; ++ci) {
@@ -430,7 +464,7 @@ void conv_tc_pack_layer(const float* flat, int cin, int cout, float* img) {
                     float hi;
                     memcpy(&hi, &bits, 4);
                     const float lo = w - hi;
-                    const int n = (2 - ky) * TCN + co;
+                    const int n = r0 + co;
                     const int k = kx * cin + ci;
                     const int atom = k / 32, kk = k % 32;
                     const int pos = (((kk / 4) ^ (n % 8)) * 4) + kk % 4;      // Swizzle<3,4,3>: 16-B chunk ^= row % 8
@@ -438,6 +472,7 @@ void conv_tc_pack_layer(const float* flat, int cin, int cout, float* img) {
                     img[idx] = hi;
                     img[mat + idx] = lo;
                 }
+    }
     for (int n = 0; n < cout; ++n) img[2 * mat + n] = flat[cin * 9 * cout + n];
 }
 
@@ -474,7 +509,7 @@ static int conv_tc_rows() {
 
 template <int CIN_A, int CIN_B, int COUT, int EPI>
 static int launch_tc_impl(TcConvParams& p, int njobs, cudaStream_t st) {
-    using G = TcGeom<CIN_A + CIN_B>;
+    using G = TcGeom<CIN_A + CIN_B, COUT>;
     static const int cat = [] {
         char nm[64];
         snprintf(nm, sizeof(nm), "conv3x3_tc<%d,%d,%d,%s>", CIN_A, CIN_B, COUT, EPI == EPI_STORE ? "store" : EPI == EPI_POOL ? "pool" : "dot");

@@ -158,3 +158,19 @@ def test_time_series_totals_allreduce_gloo():
     frames = torch.rand(4, 64, 40, generator=g, dtype=torch.float64)
     want = torch.cat([frames.sum((1, 2)), frames.mean(0).sum()[None]])
     assert torch.allclose(res[0], want, rtol=1e-12) and torch.equal(res[0], res[1])
+
+
+@pytest.mark.parametrize("H,W", [(4 * 1792 + 300, 3 * 1792 + 500), (9000, 5000)])
+def test_short_first_strip_covers_the_same_pixels(H, W):
+    """first_strip_rows only regroups main-grid tile rows: the union of written centres is unchanged."""
+    a = ct.plan_windows(H, W, merge=True, rows_per_strip=3)
+    b = ct.plan_windows(H, W, merge=True, rows_per_strip=3, first_strip_rows=1)
+    assert b[0].h == ct.PATCH and sum(w.ntiles for w in a) == sum(w.ntiles for w in b)
+
+    def cover(wins):
+        m = torch.zeros(H // 8 + 1, W // 8 + 1, dtype=torch.int16)
+        for w in wins:
+            ov = ct.OVERLAP
+            m[(w.y0 + ov) // 8:(w.y0 + w.h - ov) // 8, (w.x0 + ov) // 8:(w.x0 + w.w - ov) // 8] += 1
+        return m
+    assert torch.equal(cover(a), cover(b))

@@ -26,7 +26,7 @@ def _pack_conv_tc(w, b, tc):
     L = _lib.lib()
     cout, cin = w.shape[:2]
     flat = _pack_conv(w, b).cpu()
-    img = torch.zeros(L.pc_conv_tc_layer_floats(cin), dtype=torch.float32)
+    img = torch.zeros(L.pc_conv_tc_layer_floats(cin, cout), dtype=torch.float32)
     _lib.check(L.pc_conv_tc_pack_layer(flat.data_ptr(), cin, cout, img.data_ptr()))
     return img.cuda()
 

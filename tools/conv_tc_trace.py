@@ -17,7 +17,7 @@ x = torch.randn(cin, H, W, device="cuda")
 w = torch.randn(cout, cin, 3, 3) * 0.2
 b = torch.randn(cout)
 flat = torch.cat([w.permute(1, 2, 3, 0).reshape(-1), b]).contiguous()
-img = torch.zeros(L.pc_conv_tc_layer_floats(cin))
+img = torch.zeros(L.pc_conv_tc_layer_floats(cin, cout))
 _lib.check(L.pc_conv_tc_pack_layer(flat.data_ptr(), cin, cout, img.data_ptr()))
 flat_d, img_d = flat.cuda(), img.cuda()
 out = torch.empty(cout, H, W, device="cuda")

@@ -174,3 +174,31 @@ def test_short_first_strip_covers_the_same_pixels(H, W):
             m[(w.y0 + ov) // 8:(w.y0 + w.h - ov) // 8, (w.x0 + ov) // 8:(w.x0 + w.w - ov) // 8] += 1
         return m
     assert torch.equal(cover(a), cover(b))
+
+
+def test_random_rasters_plan_and_shard_invariants():
+    """Property test (hypothesis): for random raster sizes, tile geometry, strip heights and world sizes the merged plan
+    visits every pixel exactly as often as the reference tile grid, and the rank shards partition the windows with disjoint
+    owned row ranges."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.integers(0, 3), st.integers(1, 9), st.integers(1, 9), st.integers(0, 500), st.integers(0, 500),
+           st.integers(1, 4), st.integers(1, 5), st.booleans())
+    def check(ovi, ny, nx, dy, dx, rps, world, short_first):
+        ps = 96
+        ov = (12, 16, 20, 24)[ovi]
+        stride = ps - 2 * ov
+        H, W = ps + ny * stride + dy % stride, ps + nx * stride + dx % stride
+        ref = _count_reference(H, W, ps, ov)
+        wins = ct.plan_windows(H, W, ps, ov, True, rps, 1 if short_first else None)
+        cnt = torch.zeros(H, W, dtype=torch.int16)
+        for w in wins:
+            cnt[w.y0 + ov: w.y0 + w.h - ov, w.x0 + ov: w.x0 + w.w - ov] += 1
+        assert torch.equal(cnt, ref)
+        parts = [ct.shard_windows(wins, len(ct.grid_origins(H, ps, ov)), r, world, rps) for r in range(world)]
+        assert sorted((w.y0, w.x0, w.h, w.w) for p in parts for w in p) == sorted((w.y0, w.x0, w.h, w.w) for w in wins)
+        ranges = sorted(ct.owned_rows(p, H, ov) for p in parts if p)
+        assert all(a[1] <= b[0] for a, b in zip(ranges, ranges[1:]))
+
+    check()

@@ -177,3 +177,34 @@ def test_conv_tc_weight_image_layout(cin, cout):
     assert torch.equal(hi + lo, want)
     assert torch.equal(hi.view(torch.int32) & 0x1FFF, torch.zeros_like(hi, dtype=torch.int32))
     assert torch.equal(img[2 * mat: 2 * mat + cout], b) and float(img[2 * mat + cout: 2 * mat + 16].abs().sum()) == 0
+
+
+def test_raw_raster_validation_and_no_cpu_path():
+    """RawRaster checks shapes / dtypes / placement up front; the ingest op refuses host tensors (no CPU fallback)."""
+    from popcorn_b200 import country as ct
+    from popcorn_b200 import ops
+    s2 = torch.zeros(4, 8, 8, dtype=torch.uint16)
+    s1 = torch.zeros(2, 8, 8)
+    r = ct.RawRaster(s2, s1)
+    assert r.shape == (6, 8, 8) and not r.is_cuda and r.s2_plane_map == ops.S2_FILE_TO_RGBN
+    with pytest.raises(ValueError):
+        ct.RawRaster(torch.zeros(3, 8, 8, dtype=torch.uint16), s1)
+    with pytest.raises(ValueError):
+        ct.RawRaster(s2, torch.zeros(2, 8, 9))
+    with pytest.raises(ValueError):
+        ct.RawRaster(s2.to(torch.int32), s1)
+    with pytest.raises(RuntimeError):
+        ops.ingest_normalize(s2, s1)
+    # the statistics the product uses are the reference's (data/config/dataset_stats.json), restated in the oracle
+    assert ops.DATASET_STATS["sen2springNIR"] == po.REF_STATS["sen2springNIR"] and ops.DATASET_STATS["sen1"] == po.REF_STATS["sen1"]
+
+
+def test_unet_trainable_keys_are_the_conv_and_convt_parameters(sd):
+    """The fine-tuning path (N4) differentiates exactly the Conv2d / ConvTranspose2d weights and biases of the two streams
+    (BN affine parameters are frozen by freeze_bn_layers, networks.py:184-189; the out convs are unused on this path)."""
+    from popcorn_b200.model import unet_train
+    keys = unet_train.trainable_keys()
+    assert len(keys) == 48 and len(set(keys)) == 48
+    assert all(("unetmodel." + k) in sd for k in keys)
+    assert not any(k.split(".")[-2] in ("1", "4") for k in keys) and not any("out" in k for k in keys)
+    assert len(unet_train.trainable_keys(S1=True, S2=False)) == 24

@@ -168,7 +168,7 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
     if (warp < W_EPI0) {
         // =========================== stagers: shared-memory row -> TMEM (A operand) ===========================
         const int group = warp >> 2;                                 // group 0 stages input rows 2b-1, group 1 rows 2b
-        const uint32_t stage0 = smem_u32(sm + G::OFF_STAGE) + 4u * (uint32_t)(px + 3);     // box column 3 = image column x-1
+        const float* stage0 = reinterpret_cast<const float*>(sm + G::OFF_STAGE) + px + 3;   // box column 3 = image column x-1
         int B = 0, P0 = 0;                                           // running batch index / first output pair of the tile
         TCP_DECL;
 #pragma unroll 1
@@ -194,7 +194,7 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
                 tc_fence_after();
                 TCP_T(t2);
                 if ((warp & 3) == 0 && lane == 0) TCP_TRACE(group, B, 3);
-                const uint32_t st = stage0 + (uint32_t)s * G::STAGE_BYTES;
+                const float* st = stage0 + s * (G::STAGE_BYTES / 4);
                 const uint32_t tA = tbase + (uint32_t)(2 * pb + group) * G::A_COLS + lane_off;
 #pragma unroll
                 for (int j = 0; j < G::KSTEPS; ++j) {
@@ -202,7 +202,7 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         const int col = 8 * j + q;                                      // A column = kx * CIN + ci
-                        const float val = (col < 3 * CIN) ? lds_f32(st + 4u * (uint32_t)((col % CIN) * TC_BOXW + col / CIN)) : 0.f;
+                        const float val = (col < 3 * CIN) ? st[(col % CIN) * TC_BOXW + col / CIN] : 0.f;
                         split_tf32(val, hi[q], lo[q]);
                     }
                     tmem_st8(tA + 8 * j, hi);

@@ -13,14 +13,6 @@ namespace pc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// explicit shared-space load: pointers derived from the aligned dynamic-smem base lose their address space and would
-// compile to generic LD.E; volatile keeps it after the preceding mbarrier wait
-__device__ __forceinline__ float lds_f32(uint32_t saddr) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
-    return v;
-}
-
 // One lane of a fully converged warp.  UMMAs must be issued under elect.sync: ptxas then knows the region is
 // single-lane and feeds UTCHMMA from uniform registers directly; under a plain `tid == 0` branch it wraps EVERY
 // tcgen05.mma in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop (~10 instructions, ~50 cycles per MMA).

@@ -73,3 +73,32 @@ def test_random_state_dict_has_reference_keys(sd):
     assert sorted(r.keys()) == sorted(sd.keys())
     for k in sd:
         assert tuple(r[k].shape) == tuple(sd[k].shape), k
+
+
+@pytest.mark.parametrize("enc", [False, True])
+def test_finetune_gradients_match_reference_golden(sd, enc):
+    """N4 pin: torch.autograd through the oracle == the gradients the imported reference produced for the fine-tuning
+    step (unet_no_grad=False, encoder_no_grad=enc; oracle/make_golden_finetune.py): same set of tensors (conv / convT
+    weights and biases of unetmodel + head; BN frozen; with encoder_no_grad the encoder gets none) and same values."""
+    g = golden("finetune")
+    tag = "enc1" if enc else "enc0"
+    gkeys = sorted(k[len(tag) + 6:] for k in g if k.startswith(tag + ".grad."))
+    assert len(gkeys) == (32 if enc else 56)
+    x, admin, cidx, y = g["input"], g["admin_mask"], g["census_idx"], g["y"]
+    is_param = lambda k, v: (k.startswith("head.") or k.startswith("unetmodel.")) and v.is_floating_point() and "running_" not in k
+    sdg = {k: (v.clone().requires_grad_(True) if is_param(k, v) else v) for k, v in sd.items()}
+    out = po.forward(sdg, {"input": x, "admin_mask": admin, "census_idx": cidx}, padding=False, sparse=True,
+                     grid=(g[tag + ".grid_x"], g[tag + ".grid_y"]), encoder_no_grad=enc)
+    loss = po.train_loss(out, y)
+    loss.backward()
+    assert abs(float(loss) - float(g[tag + ".loss"])) < 1e-5 * abs(float(g[tag + ".loss"]))
+    for k in gkeys:
+        ref = g[f"{tag}.grad.{k}"]
+        got = sdg[k].grad
+        assert got is not None, k
+        assert float((got - ref).abs().max()) <= 1e-4 * float(ref.abs().max()) + 1e-12, k
+    # nothing else of unetmodel receives a gradient in the reference (BN affine frozen; encoder under no_grad if enc)
+    extra = [k for k, v in sdg.items() if k.startswith("unetmodel.") and v.is_floating_point() and v.requires_grad
+             and v.grad is not None and float(v.grad.abs().max()) > 0 and k not in gkeys]
+    bn_or_stats = lambda k: k.split(".")[-2] in ("1", "4") or "out" in k
+    assert all(bn_or_stats(k) for k in extra), [k for k in extra if not bn_or_stats(k)]

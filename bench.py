@@ -144,6 +144,9 @@ def kernel_table(prof, ms_total, hbm_peak, tensor_peak):
                      "tflops": tfl, "gbs": gbs, "bound": bound, "achieved": ach, "peak": peak, "unit": unit,
                      "frac": ach / peak if peak else None,
                      "traffic": None if tpp is None else tpp * units / n, "note": note})
+        if name.startswith("head_tc"):   # fp32-accurate tensor-core arithmetic costs 3 tf32 MMAs (= 6 bf16-rate slots) per MAC
+            rows[-1]["ceiling_3xtf32"] = tensor_peak / 6
+            rows[-1]["frac_of_3xtf32_ceiling"] = tfl / (tensor_peak / 6) if tensor_peak else None
     rows.sort(key=lambda r: -r["ms"])
     return rows
 
@@ -255,7 +258,7 @@ def run_reference_arm(args):
 # ---------------------------------------------------------------------------------------------------
 def train_step_ms(model, device, iters: int = 5):
     """BASELINE config 3: census-supervised step B=2, 896x960, sparse head, log-L1 loss, clip 0.01, Adam (run_train.py)."""
-    from oracle import popcorn_oracle as po
+    from popcorn_b200 import synthetic as sy
     B, H, W = 2, 896, 960
     x = synth_raster_slab(B * H, W, 12345, device).view(6, B, H, W).permute(1, 0, 2, 3).contiguous()
     yy, xx = torch.meshgrid(torch.arange(H, device=device), torch.arange(W, device=device), indexing="ij")
@@ -274,7 +277,7 @@ def train_step_ms(model, device, iters: int = 5):
         t0 = time.perf_counter()
         inp = {"input": x, "admin_mask": admin, "census_idx": cidx}
         out = model(inp, train=True, padding=False, encoder_no_grad=True, unet_no_grad=True, sparse=True)
-        loss = po.train_loss(out, y)
+        loss = sy.census_loss(out, y)
         loss.backward()
         torch.nn.utils.clip_grad_norm_(params, 0.01)
         opt.step()
@@ -295,7 +298,7 @@ def train_step_ms(model, device, iters: int = 5):
             t0 = time.perf_counter()
             inp = {"input": x, "admin_mask": admin, "census_idx": cidx}
             out = model(inp, train=True, padding=False, encoder_no_grad=False, unet_no_grad=False, sparse=True)
-            po.train_loss(out, y).backward()
+            sy.census_loss(out, y).backward()
             torch.nn.utils.clip_grad_norm_([p for p in params_ft if p.requires_grad], 0.01)
             opt2.step()
             opt2.zero_grad()
@@ -304,7 +307,7 @@ def train_step_ms(model, device, iters: int = 5):
                 ft.append(1e3 * (time.perf_counter() - t0))
         res["finetune_ms"] = sorted(ft)[len(ft) // 2]
         res["finetune_includes"] = "builtup pass + layer-by-layer unetmodel forward (activations kept) + sparse head fwd/bwd + full UNet backward + clip + Adam"
-        model.load_state_dict(po.random_state_dict(seed=1600))      # undo the updates: the timed inference uses the benchmark weights
+        model.load_state_dict(sy.random_state_dict(seed=1600))      # undo the updates: the timed inference uses the benchmark weights
     except Exception as ex:
         res["finetune_error"] = repr(ex)[:200]
     model.eval()
@@ -324,6 +327,8 @@ def main():
     ap.add_argument("--skip-train", action="store_true")
     ap.add_argument("--skip-timeseries", action="store_true")
     ap.add_argument("--timeseries-multi", action="store_true", help="also run the time-series section when world > 1")
+    ap.add_argument("--balance", action="store_true",
+                    help="N>1: shard the main grid at 256-row granularity (country.plan_balanced_shards) instead of whole strips")
     ap.add_argument("--height", type=int, default=0, help="override raster rows (debug)")
     ap.add_argument("--width", type=int, default=0, help="override raster cols (debug)")
     args = ap.parse_args()
@@ -348,12 +353,12 @@ def main():
     import popcorn_b200 as pb
     from popcorn_b200 import country as ct
     from popcorn_b200 import ops
-    from oracle import popcorn_oracle as po   # only for the synthetic state_dict + the cpu_baseline leg
+    from popcorn_b200 import synthetic as sy   # benchmark weights; the oracle is imported by the cpu_baseline leg only
 
     H, W, name = workload(world)
     if args.height and args.width:
         H, W, name = args.height, args.width, f"debug_{args.height}x{args.width}"
-    sd = po.random_state_dict(seed=1600)
+    sd = sy.random_state_dict(seed=1600)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         model = pb.POPCORN(6, occupancymodel=True, pretrained=False, biasinit=0.9407, sentinelbuildings=True, device=dev)
@@ -361,7 +366,7 @@ def main():
     model.eval()
 
     eng = ct.CountryEngine([model], H, W, merge=not args.no_merge, rows_per_strip=args.rows_per_strip, rank=rank, world=world,
-                           first_strip_rows=1)     # short first strip: a streamed run starts computing after a small upload
+                           first_strip_rows=1, balance=args.balance)     # short first strip: a streamed run starts computing after a small upload
     i0, i1 = eng.in_rows
     lo, hi = eng.out_rows
     raster = synth_raster_slab(i1 - i0, W, i0, dev)
@@ -411,6 +416,9 @@ def main():
                     "unit": dom["unit"], "frac": dom["frac"], "traffic": dom.get("traffic"),
                     "launches": dom["launches"], "avg_launch_ms": dom["ms"] / dom["launches"],
                     "share_of_step": dom["share_of_step"], "note": dom["note"], "peak_source": peak_src}
+        for k in ("ceiling_3xtf32", "frac_of_3xtf32_ceiling"):
+            if k in dom:
+                roofline[k] = dom[k]
     head = next((k for k in kernels if k["kernel"].startswith("head_")), None)
     head_tflops = head["tflops"] if head else 0.0
 
@@ -541,9 +549,9 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": name, "H": H, "W": W, "regions": R_REGIONS, "patch": 2048, "overlap": 128,
                            "windows": "merged_row_strips" if not args.no_merge else "reference_tiles",
-                           "rows_per_strip": args.rows_per_strip, "ensemble": 1, "head": "dense",
+                           "rows_per_strip": args.rows_per_strip, "sharding": "balanced_256_row_units" if (args.balance and world > 1) else "strips", "ensemble": 1, "head": "dense",
                            "l2": "inputs (>=6 GB per GPU) far larger than the 126 MB L2; no flush needed",
-                           "weights": "random-init DDA x2 + head (oracle.random_state_dict seed 1600)"},
+                           "weights": "random-init DDA x2 + head (popcorn_b200.synthetic.random_state_dict seed 1600)"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kernels,
                 "fp32_simt": fp32,
                 "cpu_baseline": cpu_base, "train_step": train, "time_series": tseries,

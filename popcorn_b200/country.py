@@ -103,6 +103,66 @@ def shard_windows(wins: Sequence[Window], n_tile_rows: int, rank: int, world: in
     return [w for w in wins if (w.tile_row in mine) or (w.tile_row < 0 and rank == last_owner)]
 
 
+def plan_balanced_shards(H: int, W: int, world: int, patch: int = PATCH, overlap: int = OVERLAP, rows_per_strip: int = 2,
+                         unit: int = 256, first_strip_rows: Optional[int] = None) -> List[List[Window]]:
+    """Per-rank windows with the main grid split at ``unit``-row granularity instead of whole tile-rows.
+
+    ``shard_windows`` hands out whole strips, so with 27 tile-rows on 8 GPUs (Uganda) the busiest rank computes 4 tile-rows
+    where 3.4 would do.  Here the rows the main grid writes, [overlap, overlap + stride * n_tile_rows), are cut into units of
+    ``unit`` rows (stride % unit == 0, unit % 4 == 0: every window origin stays on the reference grid's pool phase, and with
+    unit a multiple of the kernels' 64-row CTA tiles also on their tiling), and each rank gets a contiguous run of units
+    chosen so that the *input rows it computes* (units + 2*overlap of halo per window + the 2048-row bottom edge windows on
+    the last rank) are as equal as possible.  The last rank always owns the rows the bottom edge tiles overlap, so both
+    contributors of a doubly covered pixel stay on one GPU.  Written pixels, visit counts and values are those of the
+    reference tile grid (tests/test_country_host.py); ``Window.ntiles`` is 0 for these windows (they are not unions of tiles).
+    """
+    if H < patch or W < patch:
+        raise ValueError(f"raster {H}x{W} is smaller than the inference patch {patch}")
+    stride = patch - 2 * overlap
+    if not can_merge(patch, overlap) or stride % unit or unit % 4:
+        raise ValueError(f"balanced sharding needs mergeable tiles and stride {stride} % unit {unit} == 0 (unit % 4 == 0)")
+    xs, ys = grid_origins(H, patch, overlap), grid_origins(W, patch, overlap)
+    max_x, max_y = H - patch, W - patch
+    width = (ys[-1] + patch) if ys else 0
+    edge = ([Window(max_x, 0, patch, width, -1, len(ys))] if ys else []) + [Window(max_x, max_y, patch, patch, -1, 1)]
+    if not xs:
+        return [edge if r == 0 else [] for r in range(world)]
+    n_units = len(xs) * stride // unit
+    max_u = max(1, rows_per_strip * stride // unit)               # units per window (bounds the activation workspace)
+    halo = 2.0 * overlap / unit                                    # recomputed rows per window, in units
+    need_last = max(0, -(-(stride * len(xs) - max_x) // unit))     # rows shared with the bottom edge tiles -> last rank
+    units = [0] * world
+    units[-1] = min(n_units, need_last)
+
+    def cost(r: int, u: int) -> float:
+        c = u + halo * (-(-u // max_u)) if u else 0.0
+        return c + (patch / unit if r == world - 1 else 0.0)
+
+    for _ in range(n_units - units[-1]):                           # hand out unit by unit to the least loaded rank
+        r = min(range(world), key=lambda q: (cost(q, units[q] + 1), q))
+        units[r] += 1
+    shards: List[List[Window]] = []
+    a = overlap
+    for r in range(world):
+        wins: List[Window] = []
+        end = a + units[r] * unit
+        first = True
+        while a < end:
+            k = max_u
+            if first and r == 0 and first_strip_rows:
+                k = max(1, first_strip_rows * stride // unit)
+            b = min(end, a + k * unit)
+            y0, h = a - overlap, b - a + 2 * overlap
+            if ys:
+                wins.append(Window(y0, 0, h, width, y0 // stride, 0))
+            wins.append(Window(y0, max_y, h, patch, y0 // stride, 0))          # right column of these rows
+            a, first = b, False
+        if r == world - 1:
+            wins += edge
+        shards.append(wins)
+    return shards
+
+
 def owned_rows(wins: Sequence[Window], H: int, overlap: int = OVERLAP) -> Tuple[int, int]:
     """Raster rows [lo, hi) this rank writes (centre rows of its windows)."""
     if not wins:
@@ -151,7 +211,8 @@ class CountryEngine:
 
     def __init__(self, models, H: int, W: int, patch: int = PATCH, overlap: int = OVERLAP, merge: bool = True,
                  rows_per_strip: int = 2, rank: int = 0, world: int = 1, want_scale: bool = True,
-                 want_std: bool = True, first_strip_rows: Optional[int] = None):
+                 want_std: bool = True, first_strip_rows: Optional[int] = None, balance: bool = False,
+                 balance_unit: int = 256):
         self.models = list(models) if isinstance(models, (list, tuple)) else [models]
         self.H, self.W, self.patch, self.overlap = H, W, patch, overlap
         self.rank, self.world = rank, world
@@ -160,7 +221,13 @@ class CountryEngine:
         self.merged = merge
         all_w = plan_windows(H, W, patch, overlap, merge, rows_per_strip if merge else 1, first_strip_rows if merge else None)
         n_rows = len(grid_origins(H, patch, overlap))
-        self.windows = shard_windows(all_w, n_rows, rank, world, rows_per_strip if merge else 1) if world > 1 else all_w
+        if balance and world > 1:     # opt-in: unit-row granularity instead of whole strips (plan_balanced_shards)
+            if not merge:
+                raise ValueError("balance=True needs merged windows")
+            self.windows = plan_balanced_shards(H, W, world, patch, overlap, rows_per_strip, balance_unit,
+                                                first_strip_rows)[rank]
+        else:
+            self.windows = shard_windows(all_w, n_rows, rank, world, rows_per_strip if merge else 1) if world > 1 else all_w
         self.out_rows = owned_rows(self.windows, H, overlap)
         self.in_rows = input_rows(self.windows)
         self._maps = None
@@ -231,14 +298,16 @@ class CountryEngine:
         if map_out is not None:
             if not finalize:
                 raise ValueError("map_out needs finalize=True")
-            if map_out.is_cuda or not map_out.is_pinned() or tuple(map_out.shape) != (self.out_rows[1] - self.out_rows[0], self.W):
+            if map_out.is_cuda or (map_out.numel() and not map_out.is_pinned()) or tuple(map_out.shape) != (self.out_rows[1] - self.out_rows[0], self.W):
                 raise ValueError("map_out must be a pinned host tensor of the owned map shape")
         self.wait_download()                      # a previous run's download must not race the maps' re-allocation
         self._map_out, self._shipped = map_out, 0
         dev = torch.device("cuda", torch.cuda.current_device())
         maps = self.alloc_maps(dev)
         raw = isinstance(raster, RawRaster)
-        if raster.is_cuda and not raw:
+        if not self.windows:
+            pass                                  # this rank owns no rows (more ranks than strips): only the all-reduce below
+        elif raster.is_cuda and not raw:
             for k, win in enumerate(self.windows):
                 x = raster[None, :, win.y0 - row_offset: win.y0 - row_offset + win.h, win.x0: win.x0 + win.w]
                 self._forward_window(x, win)

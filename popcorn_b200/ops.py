@@ -156,6 +156,8 @@ def region_sum(dens: torch.Tensor, ids: torch.Tensor, R: int, sums: Optional[tor
     assert dens.numel() == ids.numel()
     if sums is None:
         sums = torch.zeros(R, dtype=torch.float64, device=dens.device)
+    if dens.numel() == 0:
+        return sums
     _lib.check(_lib.lib().pc_region_sum(dens.data_ptr(), ids.data_ptr(), dens.numel(), R, sums.data_ptr(), _stream()),
                "pc_region_sum")
     return sums
@@ -190,6 +192,8 @@ def finalize_map(maps, rows=None):
     """Mean / std where a pixel was visited more than once (run_eval.py:140-154); ``rows`` = (r0, r1) restricts it to a
     row range of the maps (used to finalise and ship finished strips while later strips still compute)."""
     m, msq, sm, ssq, cnt = maps
+    if m.numel() == 0:          # a rank that owns no rows (more ranks than row strips): nothing to finalise
+        return
     if rows is not None:
         r0, r1 = rows
         if r1 <= r0:

@@ -202,3 +202,61 @@ def test_random_rasters_plan_and_shard_invariants():
         assert all(a[1] <= b[0] for a, b in zip(ranges, ranges[1:]))
 
     check()
+
+
+def test_more_ranks_than_strips_leaves_empty_ranks_consistent():
+    """Switzerland-shaped raster (config 5) on 8 ranks: 4 strips -> ranks 4..7 own nothing; their row ranges are empty, the
+    non-empty shards still partition the plan (the engine then skips finalise / region sums on the empty ranks but joins the
+    all-reduce)."""
+    H, W = 13408, 30592
+    wins = ct.plan_windows(H, W, merge=True, rows_per_strip=2)
+    n_rows = len(ct.grid_origins(H))
+    parts = [ct.shard_windows(wins, n_rows, r, 8, 2) for r in range(8)]
+    assert [bool(p) for p in parts] == [True] * 4 + [False] * 4
+    assert all(ct.owned_rows(p, H) == (0, 0) and ct.input_rows(p) == (0, 0) for p in parts[4:])
+    assert sorted((w.y0, w.x0) for p in parts for w in p) == sorted((w.y0, w.x0) for w in wins)
+    assert any(w.tile_row < 0 for w in parts[3]) and not any(w.tile_row < 0 for p in parts[:3] for w in p)
+
+
+@pytest.mark.parametrize("H,W,ps,ov,unit", [(1900, 700, 256, 32, 64), (15104 // 8, 17216 // 8, 256, 32, 64), (1000, 1100, 320, 32, 128),
+                                            (256, 300, 256, 32, 64), (448, 256, 256, 32, 64)])
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("rps,short_first", [(1, False), (2, True)])
+def test_balanced_shards_cover_exactly_like_the_reference_tile_grid(H, W, ps, ov, unit, world, rps, short_first):
+    shards = ct.plan_balanced_shards(H, W, world, ps, ov, rps, unit, 1 if short_first else None)
+    assert len(shards) == world
+    cnt = torch.zeros(H, W, dtype=torch.int16)
+    owner = torch.full((H,), -1, dtype=torch.int16)
+    stride = ps - 2 * ov
+    for r, part in enumerate(shards):
+        cnt += _count_from_windows(part, H, W, ov)
+        for w in part:
+            rows = owner[w.y0 + ov: w.y0 + w.h - ov]
+            assert bool(((rows == -1) | (rows == r)).all()), "a raster row would be accumulated on two ranks"
+            rows.fill_(r)
+            if w.tile_row >= 0:       # pool phase / CTA tiling of the reference grid, bounded window height
+                assert w.y0 % unit == 0 and (w.h - 2 * ov) % unit == 0 and w.h - 2 * ov <= max(rps * stride, unit)
+            else:
+                assert w.y0 == H - ps and r == (world - 1 if H > ps else 0)
+            assert w.x0 == 0 or w.x0 == W - ps
+    assert torch.equal(cnt, _count_reference(H, W, ps, ov))
+    ranges = [ct.owned_rows(p, H, ov) for p in shards if p]
+    assert all(a[1] <= b[0] for a, b in zip(ranges, ranges[1:]))            # contiguous, in rank order
+
+
+def test_balanced_shards_are_better_balanced_than_strips_on_the_bench_rasters():
+    for world, H in ((8, 50048), (4, 25024), (2, 12512)):
+        W = 47952
+        work = lambda wins: sum(w.h * w.w for w in wins)
+        bal = [work(p) for p in ct.plan_balanced_shards(H, W, world, first_strip_rows=1)]
+        plan = ct.plan_windows(H, W, merge=True, rows_per_strip=2, first_strip_rows=1)
+        strips = [work(ct.shard_windows(plan, 0, r, world, 2)) for r in range(world)]
+        assert max(bal) < 0.95 * max(strips)
+        assert max(bal) < 1.06 * sum(bal) / world
+
+
+def test_balanced_shards_reject_unaligned_units():
+    with pytest.raises(ValueError):
+        ct.plan_balanced_shards(4000, 4000, 2, unit=100)         # 1792 % 100 != 0
+    with pytest.raises(ValueError):
+        ct.plan_balanced_shards(1000, 4000, 2)                    # smaller than the patch

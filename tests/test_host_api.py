@@ -208,3 +208,24 @@ def test_unet_trainable_keys_are_the_conv_and_convt_parameters(sd):
     assert all(("unetmodel." + k) in sd for k in keys)
     assert not any(k.split(".")[-2] in ("1", "4") for k in keys) and not any("out" in k for k in keys)
     assert len(unet_train.trainable_keys(S1=True, S2=False)) == 24
+
+
+def test_benchmark_weights_equal_the_oracles_copy():
+    """bench.py draws its weights with popcorn_b200.synthetic (the product never imports oracle/); the oracle's generator must
+    produce the same 324 tensors so that tests, fixtures and bench runs talk about the same model."""
+    from popcorn_b200 import synthetic as sy
+    for seed, head_in in ((1600, 16), (3, 8)):
+        a, b = sy.random_state_dict(seed, head_in=head_in), po.random_state_dict(seed, head_in=head_in)
+        assert list(a) == list(b)
+        assert all(torch.equal(a[k], b[k]) for k in a)
+    out = {"popcount": torch.tensor([10.0, 100.0]), "scale": torch.tensor([1.0, -3.0])}
+    y = torch.tensor([20.0, 50.0])
+    assert torch.equal(sy.census_loss(out, y), po.train_loss(out, y))
+
+
+def test_product_package_never_imports_the_oracle():
+    import pathlib
+    root = pathlib.Path(__file__).resolve().parents[1] / "popcorn_b200"
+    for f in root.rglob("*.py"):
+        src = f.read_text()
+        assert "import oracle" not in src and "from oracle" not in src, f

@@ -1,0 +1,62 @@
+"""GPU: checks of paths that were written after this round's GPU budget was spent (opt-in features, empty ranks).  The file
+sorts last on purpose: with `pytest -x` a surprise here cannot hide the validated parity suites that run before it."""
+import pytest
+import torch
+
+from popcorn_b200 import country as ct
+from popcorn_b200 import timeseries as ts
+from oracle import popcorn_oracle as po
+from util import build_model, golden_state_dict, max_rel
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def model():
+    return build_model(golden_state_dict()).eval()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_balanced_row_shards_are_bit_identical_to_the_unsharded_run(model, world):
+    """plan_balanced_shards cuts the main grid at unit-row granularity (origins stay on the pool phase and on the kernels'
+    64-row CTA tiling): every written pixel must equal the single-GPU result bit for bit, sums add up."""
+    H, W, ps, ov = 1220, 300, 192, 32         # stride 128, unit 64: cuts fall inside tile-rows
+    raster = po.synthetic_input(H, W, seed=31)[0].cuda()
+    ids = po.synthetic_regions(H, W, 20).cuda()
+    with torch.no_grad():
+        e0 = ct.CountryEngine([model], H, W, ps, ov, merge=True, rows_per_strip=2)
+        flo, fhi = e0.out_rows
+        full = e0.run(raster, ids[flo:fhi].contiguous(), 21)
+        total = torch.zeros_like(full["sums"])
+        seen = 0
+        for r in range(world):
+            eng = ct.CountryEngine([model], H, W, ps, ov, merge=True, rows_per_strip=2, rank=r, world=world, balance=True,
+                                   balance_unit=64)
+            lo, hi = eng.out_rows
+            i0, i1 = eng.in_rows
+            o = eng.run(raster[:, i0:i1].contiguous(), ids[lo:hi].contiguous(), 21, row_offset=i0)
+            assert torch.equal(o["map"], full["map"][lo - flo:hi - flo])
+            assert torch.equal(o["count"], full["count"][lo - flo:hi - flo])
+            total += o["sums"]
+            seen += hi - lo
+    assert seen == fhi - flo
+    assert max_rel(total, full["sums"], floor_frac=1.0) < 1e-6
+
+
+def test_rank_without_rows_runs_and_contributes_zero(model):
+    """More ranks than row strips (config 5 on 8 GPUs): a rank that owns no rows must get through run() — empty maps, zero
+    partial sums — so that it still joins the all-reduce instead of raising while its peers wait."""
+    H, W, ps, ov = 300, 300, 128, 32          # 3 tile-rows -> ranks 3.. of 8 own nothing
+    eng = ct.CountryEngine([model], H, W, ps, ov, merge=True, rows_per_strip=1, rank=6, world=8)
+    assert eng.windows == [] and eng.out_rows == (0, 0) and eng.in_rows == (0, 0)
+    empty = torch.empty(6, 0, W, device="cuda")
+    ids = torch.empty(0, W, dtype=torch.int32, device="cuda")
+    with torch.no_grad():
+        out = eng.run(empty, ids, 5)
+        assert out["map"].shape == (0, W) and float(out["sums"].abs().sum()) == 0.0
+        host_map = torch.empty(0, W).pin_memory()
+        out = eng.run(empty.cpu().pin_memory(), ids, 5, map_out=host_map)
+        eng.wait_download()
+        tse = ts.TimeSeriesEngine([model], H, W, rank=6, world=8, patch=ps, overlap=ov, merge=True, rows_per_strip=1)
+        o = tse.run([empty, empty], None, 0)
+    assert float(o["season_total"]) == 0.0 and o["season_map"].shape == (0, W)

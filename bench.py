@@ -404,8 +404,11 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
     value = H * W / (ms_step * 1e-3)
-    sums_check = float(out["sums"].sum().item())
-    map_total = float(out["map"].double().sum().item())
+    sums_check = float(out["sums"].sum().item())          # all-reduced census sums (every id incl. background 0)
+    mt = out["map"].double().sum().reshape(1)               # this rank's rows of the map -> all ranks
+    if world > 1:
+        dist.all_reduce(mt)
+    map_total = float(mt.item())
 
     hbm_peak, bf16_peak, bf16_sust, peak_src = measured_peaks()
     kernels = kernel_table(prof, ms_total, hbm_peak, bf16_sust)

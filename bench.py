@@ -329,6 +329,8 @@ def main():
     ap.add_argument("--timeseries-multi", action="store_true", help="also run the time-series section when world > 1")
     ap.add_argument("--balance", action="store_true",
                     help="N>1: shard the main grid at 256-row granularity (country.plan_balanced_shards) instead of whole strips")
+    ap.add_argument("--upload-once", action="store_true",
+                    help="e2e: copy every raw input row to the device once (CountryEngine(upload_once=True)) instead of per window")
     ap.add_argument("--height", type=int, default=0, help="override raster rows (debug)")
     ap.add_argument("--width", type=int, default=0, help="override raster cols (debug)")
     args = ap.parse_args()
@@ -366,7 +368,7 @@ def main():
     model.eval()
 
     eng = ct.CountryEngine([model], H, W, merge=not args.no_merge, rows_per_strip=args.rows_per_strip, rank=rank, world=world,
-                           first_strip_rows=1, balance=args.balance)     # short first strip: a streamed run starts computing after a small upload
+                           first_strip_rows=1, balance=args.balance, upload_once=args.upload_once)     # short first strip: a streamed run starts computing after a small upload
     i0, i1 = eng.in_rows
     lo, hi = eng.out_rows
     raster = synth_raster_slab(i1 - i0, W, i0, dev)
@@ -471,6 +473,7 @@ def main():
         e2e = {"value": H * W / (float(tt.item()) / k_e2e), "unit": UNIT, "h2d_bytes_per_step": int(h2d.item()),
                "d2h_bytes_per_step": int(d2h.item()), "steps": k_e2e,
                "api": "popcorn_b200.country.CountryEngine.run(RawRaster(pinned uint16 S2 + float32 S1), map_out=pinned host map) + sums.cpu()",
+               "upload": "once_per_row" if args.upload_once else "per_window",
                "host_input": "raw on-disk dtypes: S2 uint16 x4 (file band order) + S1 float32 x2 = 16 B/px; converted + normalised on the device"}
 
     train = None

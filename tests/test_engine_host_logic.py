@@ -1,0 +1,120 @@
+"""CPU: the country / time-series engines' host logic (row offsets of sharded rasters, upload ring, upload-once slabs, strip
+shipping to map_out, balanced shards, empty ranks) on a stand-in device (tests/fake_device.py: torch-CPU `ops` with a 3x3-local
+fake network, no-op streams).  Expected values come from applying the same fake network to the WHOLE raster at once and the
+reference tile grid's visit counts (oracle.get_patch_indices / centre_mask) — i.e. what the tiling must be invisible to."""
+import pytest
+import torch
+
+import fake_device as fd
+from popcorn_b200 import country as ct
+from popcorn_b200 import timeseries as ts
+from oracle import popcorn_oracle as po
+
+
+class Pinned(torch.Tensor):
+    def is_pinned(self):
+        return True
+
+
+class OnDevice(torch.Tensor):
+    is_cuda = property(lambda self: True)
+
+
+def _expected(norm, ids, H, W, ps, ov, R):
+    dens, scale = fd.fake_density(norm[None])
+    cnt = torch.zeros(H, W, dtype=torch.int16)
+    m = po.centre_mask(ps, ps, ov)
+    for xl, yl in po.get_patch_indices(H, W, ps, ov).tolist():
+        cnt[xl:xl + ps, yl:yl + ps][m] += 1
+    dmap = torch.where(cnt > 0, dens[0], torch.zeros(()))
+    sums = torch.zeros(R, dtype=torch.float64).index_add_(0, ids.reshape(-1).long(), dmap.reshape(-1).double())
+    return dmap, torch.where(cnt > 0, scale[0], torch.zeros(())), cnt, sums
+
+
+@pytest.fixture()
+def world_data():
+    H, W, ps, ov, R = 1220, 300, 192, 32, 21
+    s2_file, s1 = po.synthetic_raw(H, W, seed=41)
+    norm = fd.normalise(s2_file, s1)
+    ids = po.synthetic_regions(H, W, R - 1)
+    return H, W, ps, ov, R, s2_file, s1, norm, ids, _expected(norm, ids, H, W, ps, ov, R)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+@pytest.mark.parametrize("mode", ["device", "host_fp32", "raw_windows", "raw_once", "raw_device"])
+@pytest.mark.parametrize("balance", [False, True])
+def test_sharded_engine_reassembles_the_whole_raster_result(monkeypatch, world_data, world, mode, balance):
+    H, W, ps, ov, R, s2_file, s1, norm, ids, (want_map, want_scale, want_cnt, want_sums) = world_data
+    if balance and world == 1:
+        pytest.skip("nothing to balance")
+    log = fd.install(monkeypatch)
+    got_map = torch.zeros(H, W)
+    got_cnt = torch.zeros(H, W, dtype=torch.int16)
+    host_full = torch.zeros(H, W)
+    total = torch.zeros(R, dtype=torch.float64)
+    seen = []
+    for rank in range(world):
+        eng = ct.CountryEngine([fd.FakeModel()], H, W, ps, ov, merge=True, rows_per_strip=2, rank=rank, world=world,
+                               first_strip_rows=1, balance=balance, balance_unit=64, upload_once=(mode == "raw_once"))
+        lo, hi = eng.out_rows
+        i0, i1 = eng.in_rows
+        if mode == "device":
+            raster = norm[:, i0:i1].contiguous().as_subclass(OnDevice)
+        elif mode == "host_fp32":
+            raster = norm[:, i0:i1].contiguous().as_subclass(Pinned)
+        else:
+            raster = ct.RawRaster(s2_file[:, i0:i1].contiguous(), s1[:, i0:i1].contiguous())
+            if mode == "raw_device":
+                raster.is_cuda = True
+        map_out = torch.full((hi - lo, W), float("nan")).as_subclass(Pinned) if mode != "device" else None
+        del log[:]
+        out = eng.run(raster, ids[lo:hi].contiguous(), R, row_offset=i0, map_out=map_out)
+        eng.wait_download()
+        if not eng.windows:
+            assert (lo, hi) == (0, 0) and float(out["sums"].abs().sum()) == 0.0 and out["map"].numel() == 0
+            continue
+        seen.append((lo, hi))
+        got_map[lo:hi] = out["map"]
+        got_cnt[lo:hi] = out["count"]
+        total += out["sums"]
+        if map_out is not None:
+            assert torch.equal(torch.Tensor(map_out), out["map"]), "rows shipped to the host differ from the device map"
+            host_full[lo:hi] = map_out
+            shipped = sorted((e[1], e[2]) for e in log if e[0] == "finalize")
+            assert shipped[0][0] == 0 and shipped[-1][1] == hi - lo
+            assert all(a[1] == b[0] for a, b in zip(shipped, shipped[1:])), "every owned row is finalised exactly once"
+        h2d = sum(e[1] for e in log if e[0] == "h2d")
+        if mode == "raw_once":
+            assert h2d == eng.h2d_bytes == (i1 - i0) * W * 16
+        elif mode == "raw_windows":
+            assert h2d == eng.h2d_bytes == sum(w.h * w.w for w in eng.windows) * 16 >= (i1 - i0) * W * 16
+        elif mode == "host_fp32":
+            assert h2d == eng.h2d_bytes == sum(w.h * w.w for w in eng.windows) * 24
+    assert all(a[1] <= b[0] for a, b in zip(seen, seen[1:]))
+    assert torch.equal(got_cnt, want_cnt)
+    assert torch.allclose(got_map, want_map, rtol=1e-6, atol=1e-6)
+    assert torch.allclose(total, want_sums, rtol=1e-9)
+    if mode != "device":
+        assert torch.equal(host_full, got_map)
+
+
+def test_time_series_engine_on_sharded_frames(monkeypatch, world_data):
+    H, W, ps, ov, R, s2_file, s1, norm, ids, (want_map, _, _, want_sums) = world_data
+    fd.install(monkeypatch)
+    frames_full = [norm, norm * 0.5, norm + 0.25]
+    wants = [_expected(f, ids, H, W, ps, ov, R) for f in frames_full]
+    season = sum(w[0] for w in wants) / 3
+    world = 4
+    tot = torch.zeros(4, dtype=torch.float64)
+    for rank in range(world):
+        eng = ts.TimeSeriesEngine([fd.FakeModel()], H, W, rank=rank, world=world, patch=ps, overlap=ov, merge=True, rows_per_strip=2)
+        lo, hi = eng.out_rows
+        i0, i1 = eng.in_rows
+        frames = [f[:, i0:i1].contiguous().as_subclass(OnDevice) for f in frames_full]
+        o = eng.run(frames, ids[lo:hi].contiguous(), R, row_offset=i0)
+        assert torch.allclose(o["season_map"], season[lo:hi], rtol=1e-5, atol=1e-6)
+        tot[:3] += o["totals"]
+        tot[3] += o["season_total"]
+    for t in range(3):
+        assert abs(float(tot[t]) - float(wants[t][0].double().sum())) < 1e-6 * float(wants[t][0].double().sum())
+    assert abs(float(tot[3]) - float(season.double().sum())) < 1e-6 * float(season.double().sum())

@@ -60,3 +60,29 @@ def test_rank_without_rows_runs_and_contributes_zero(model):
         tse = ts.TimeSeriesEngine([model], H, W, rank=6, world=8, patch=ps, overlap=ov, merge=True, rows_per_strip=1)
         o = tse.run([empty, empty], None, 0)
     assert float(o["season_total"]) == 0.0 and o["season_map"].shape == (0, W)
+
+
+@pytest.mark.parametrize("world,rank", [(1, 0), (2, 1)])
+def test_upload_once_equals_the_per_window_upload(model, world, rank):
+    """CountryEngine(upload_once=True): every raw input row crosses PCIe once into device slabs (chunked, copy stream) and the
+    windows are normalised from the slabs — same maps, sums and host download as the window-by-window streamed upload."""
+    H, W, ps, ov = 900, 456, 128, 32
+    s2_file, s1 = po.synthetic_raw(H, W, seed=35)
+    ids = po.synthetic_regions(H, W, 30).cuda()
+    outs = []
+    for once in (False, True):
+        eng = ct.CountryEngine([model], H, W, ps, ov, merge=True, rows_per_strip=2, rank=rank, world=world, upload_once=once)
+        lo, hi = eng.out_rows
+        i0, i1 = eng.in_rows
+        raw = ct.RawRaster(s2_file[:, i0:i1].contiguous().pin_memory(), s1[:, i0:i1].contiguous().pin_memory())
+        host = torch.full((hi - lo, W), float("nan")).pin_memory()
+        with torch.no_grad():
+            o = eng.run(raw, ids[lo:hi].contiguous(), 31, row_offset=i0, map_out=host)
+            eng.wait_download()
+        torch.cuda.synchronize()
+        outs.append((o["map"].clone(), o["count"].clone(), o["sums"].clone(), host.clone(), eng.h2d_bytes))
+    a, b = outs
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[3], b[3])
+    assert torch.equal(b[3], b[0].cpu())
+    assert torch.allclose(a[2], b[2], rtol=1e-6)
+    assert b[4] == (i1 - i0) * W * 16 and b[4] < a[4]

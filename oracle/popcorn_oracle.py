@@ -9,7 +9,9 @@ Parity pin: the reference ships no tests or golden vectors.
 restatement is pinned against the *imported, unmodified* reference model in this
 container by ``oracle/make_golden.py`` (max |diff| printed there, fixtures committed to
 ``tests/golden/``) and re-checked by ``tests/test_oracle_vs_reference.py`` whenever
-``/root/reference`` is present.
+``/root/reference`` is present — model forward / backward, and bit-exactly the reference's own
+``Population_Dataset`` tiling / census methods, ``run_eval.Trainer.test_target`` loop,
+``apply_transformations_and_normalize`` and ``utils/losses.get_loss``.
 
 Every function cites the reference lines it follows (paths relative to /root/reference).
 """
@@ -253,10 +255,10 @@ def centre_mask(ps_x: int, ps_y: int, overlap: int) -> Tensor:
     return m
 
 
-def tiled_eval(sd_list, raster: Tensor, patchsize: int = 2048, overlap: int = 128, forward_fn=None):
+def tiled_eval(sd_list, raster: Tensor, patchsize: int = 2048, overlap: int = 128, forward_fn=None, with_scale_std: bool = False):
     """Restated run_eval.Trainer.test_target accumulate loop, run_eval.py:83-154, for one frame.
 
-    raster [6,H,W] normalised fp32.  Returns (mean popdensemap [H,W], std map, mean scale map, count).
+    raster [6,H,W] normalised fp32.  Returns (mean popdensemap [H,W], std map, mean scale map, count[, scale std map]).
     ``forward_fn(member, inputs)`` defaults to this module's ``forward(sd, inputs, padding=False)``;
     make_golden.py passes the imported reference model's forward instead.
     """
@@ -266,6 +268,7 @@ def tiled_eval(sd_list, raster: Tensor, patchsize: int = 2048, overlap: int = 12
     out = torch.zeros(h, w)
     out_sq = torch.zeros(h, w)
     out_scale = torch.zeros(h, w)
+    out_scale_sq = torch.zeros(h, w)
     count = torch.zeros(h, w, dtype=torch.int16)
     mask = centre_mask(patchsize, patchsize, overlap)
     for xl, yl in get_patch_indices(h, w, patchsize, overlap).tolist():
@@ -273,20 +276,26 @@ def tiled_eval(sd_list, raster: Tensor, patchsize: int = 2048, overlap: int = 12
         dens = torch.zeros(patchsize, patchsize)
         dens_sq = torch.zeros(patchsize, patchsize)
         scale = torch.zeros(patchsize, patchsize)
+        scale_sq = torch.zeros(patchsize, patchsize)
         for sd in sd_list:
             o = forward_fn(sd, {"input": tile})
             dens += o["popdensemap"][0]
             dens_sq += o["popdensemap"][0] ** 2
             scale += o["scale"][0]
+            scale_sq += o["scale"][0] ** 2
         out[xl:xl + patchsize, yl:yl + patchsize][mask] += dens[mask]
         out_sq[xl:xl + patchsize, yl:yl + patchsize][mask] += dens_sq[mask]
         out_scale[xl:xl + patchsize, yl:yl + patchsize][mask] += scale[mask]
+        out_scale_sq[xl:xl + patchsize, yl:yl + patchsize][mask] += scale_sq[mask]
         count[xl:xl + patchsize, yl:yl + patchsize][mask] += len(sd_list)
     div = count > 1                                                   # run_eval.py:140-154
     cf = count[div].to(torch.float32)
     out[div] = out[div] / cf
     out_sq[div] = torch.sqrt((out_sq[div] - out[div] ** 2 * cf) / (cf - 1))
     out_scale[div] = out_scale[div] / cf
+    out_scale_sq[div] = torch.sqrt((out_scale_sq[div] - out_scale[div] ** 2 * cf) / (cf - 1))
+    if with_scale_std:
+        return out, out_sq, out_scale, count, out_scale_sq
     return out, out_sq, out_scale, count
 
 

@@ -125,3 +125,70 @@ def build_reference_model(input_channels=6, occupancymodel=True, pretrained=Fals
 def reference_forward(model, inputs, **kw):
     with reference_cwd():
         return model(inputs, **kw)
+
+
+def load_reference_dataset_class(boundaries: dict):
+    """The reference's ``Population_Dataset`` class (data/PopulationDataset.py) with a stub ``rasterio`` whose
+    ``open(path).read(1)`` serves the numpy boundary rasters in ``boundaries`` (path -> array).  Instances are made with
+    ``object.__new__`` (the real __init__ needs the on-disk dataset); only methods that are pure functions of a few
+    attributes are called: get_patch_indices (:294-334), _create_mask (:656-672), convert_popmap_to_census (:675-729),
+    adjust_map_to_census (:823-852)."""
+    load_reference()
+
+    class _Src:
+        def __init__(self, arr):
+            self.arr = arr
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+        def read(self, band, window=None):
+            return self.arr
+
+    rio = _stub("rasterio")
+    rio.open = lambda path, mode="r", **kw: _Src(boundaries[path])
+    cwd = os.getcwd()
+    os.chdir(REF_ROOT)
+    real_isdir = os.path.isdir
+    os.path.isdir = lambda p: True if str(p) == "/scratch/metzgern/HAC/data" else real_isdir(p)
+    try:
+        import data.PopulationDataset as pds
+    finally:
+        os.chdir(cwd)
+        os.path.isdir = real_isdir
+    pds.rasterio = rio
+    return pds.Population_Dataset
+
+
+def load_reference_run_eval():
+    """The reference's ``run_eval`` module (its ``Trainer.test_target`` is the evaluation loop, run_eval.py:83-203).
+    Needs: a stub ``configargparse`` (absent here; arguments/eval.py parses at import, so sys.argv is emptied meanwhile),
+    the rasterio stub of load_reference_dataset_class, cwd = reference root.  The caller patches ``run_eval.torch`` /
+    ``run_eval.ips`` / ``run_eval.wandb`` for a CPU run at small tile sizes (tests/test_oracle_vs_reference.py)."""
+    import argparse
+    load_reference_dataset_class({})
+
+    class _AP(argparse.ArgumentParser):
+        def add_argument(self, *a, **k):
+            k.pop("is_config_file", None)
+            return super().add_argument(*a, **k)
+
+        def format_values(self):
+            return ""
+
+    cap = _stub("configargparse")
+    cap.ArgumentParser = _AP
+    argv, cwd, real_isdir = sys.argv, os.getcwd(), os.path.isdir
+    sys.argv = ["run_eval.py"]
+    os.chdir(REF_ROOT)
+    os.path.isdir = lambda p: True if str(p) == "/scratch/metzgern/HAC/data" else real_isdir(p)
+    try:
+        import run_eval
+    finally:
+        sys.argv = argv
+        os.chdir(cwd)
+        os.path.isdir = real_isdir
+    return run_eval

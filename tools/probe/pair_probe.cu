@@ -17,7 +17,11 @@
 //   3. what does an SS-form N = 48 / 96 UMMA cost when A (4 KB per instruction) comes from shared memory?   -> clk per MMA.
 //
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I popcorn_b200/csrc -o tools/probe/pair_probe tools/probe/pair_probe.cu -lcuda
-//   pair_probe [swap_lbo_sbo]     (run each variant in its own process: a faulting descriptor poisons the context)
+//   pair_probe [swap_lbo_sbo] [variant]     (run each variant in its own process: a faulting descriptor poisons the context)
+//     variant 0: SS form, two N = 48 UMMAs per (tap, 8 channels) — weight images w1 and w2 into the same accumulator
+//     variant 1: SS form, ONE N = 96 UMMA per (tap, 8 channels) — [B(w1) | B(w2)] side by side, the read-out adds the halves
+//                (A is fetched from shared memory once instead of twice)
+//     variant 2: tcgen05.cp.128x256b copies each 128 x K16 slice of A from shared memory into TMEM, then two TS-form N = 48 UMMAs
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
@@ -56,13 +60,25 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t adesc, ui
         : "memory");
 }
 
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}\n"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
+        : "memory");
+}
+// 128 lanes x 256 bits (= one K = 16 slice of a 16-bit A operand = 8 TMEM columns) from shared memory (matrix descriptor) to TMEM
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t sdesc) {
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
+
 struct Args {
     const uint32_t* act;      // [CQ][H][W][4] pair words
     const uint8_t* wimg;      // two weight images (w1, w2), B_IMG bytes each
     float* out;               // [128][N]
     long long* clk;           // [4]
     int mode;                 // 0: threads copy the row, 1: TMA
-    int y, x0, swap, reps;
+    int y, x0, swap, reps, variant;
 };
 
 __global__ void __launch_bounds__(128) probe(const __grid_constant__ CUtensorMap tm, Args a) {
@@ -74,7 +90,7 @@ __global__ void __launch_bounds__(128) probe(const __grid_constant__ CUtensorMap
     __shared__ uint32_t slot;
     const int tid = threadIdx.x, warp = uniform_warp_idx();
     for (int i = tid; i < 2 * B_IMG / 16; i += 128) reinterpret_cast<int4*>(sB)[i] = reinterpret_cast<const int4*>(a.wimg)[i];
-    if (warp == 0) tmem_alloc(smem_u32(&slot), 128);
+    if (warp == 0) tmem_alloc(smem_u32(&slot), 256);
     if (tid == 0) { mbar_init(smem_u32(&bar_tma), 1); mbar_init(smem_u32(&bar_mma), 1); mbar_init_fence(); }
     if (a.mode == 0) {                                  // the layout the TMA box is expected to produce, written by hand
         for (int i = tid; i < CQ * BOXW; i += 128) {
@@ -106,16 +122,27 @@ __global__ void __launch_bounds__(128) probe(const __grid_constant__ CUtensorMap
         const uint32_t lboB = a.swap ? 128u : (uint32_t)LBO_B, sboB = a.swap ? (uint32_t)LBO_B : 128u;
         const uint32_t id = idesc_bf16(128, N);
         t2 = clock64();
+        const uint32_t id96 = idesc_bf16(128, 2 * N);
+        const uint32_t tA = tbase + 128;                           // variant 2: A slices at TMEM columns [128, 128 + 8 * 3 * CQ/2)
         for (int rep = 0; rep < a.reps; ++rep) {
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
                 for (int j = 0; j < CQ / 2; ++j) {                 // one K=16 instruction = 8 channels = 2 chunks
                     const uint64_t ad = make_desc_nosw(smem_u32(sA) + kx * 16 + 2 * j * LBO_A, lboA, sboA);
+                    const uint32_t first = (rep | kx | j) ? 1u : 0u;
+                    if (a.variant == 1) {                          // B rows [0,48) = w1 image, [48,96) = w2 image: same chunk, 96 rows
+                        const uint64_t bd = make_desc_nosw(smem_u32(sB) + (kx * CQ + 2 * j) * (2 * LBO_B), a.swap ? 128u : 2u * LBO_B,
+                                                           a.swap ? 2u * LBO_B : 128u);
+                        umma_bf16_ss(tbase, ad, bd, id96, first);
+                    } else {
+                        if (a.variant == 2) tmem_cp_128x256b(tA + 8 * (kx * (CQ / 2) + j), ad);
 #pragma unroll
-                    for (int img = 0; img < 2; ++img) {
-                        const uint64_t bd = make_desc_nosw(smem_u32(sB) + img * B_IMG + (kx * CQ + 2 * j) * LBO_B, lboB, sboB);
-                        umma_bf16_ss(tbase, ad, bd, id, (rep | kx | j | img) ? 1u : 0u);
+                        for (int img = 0; img < 2; ++img) {
+                            const uint64_t bd = make_desc_nosw(smem_u32(sB) + img * B_IMG + (kx * CQ + 2 * j) * LBO_B, lboB, sboB);
+                            if (a.variant == 2) umma_bf16_ts(tbase, tA + 8 * (kx * (CQ / 2) + j), bd, id, first | (uint32_t)img);
+                            else umma_bf16_ss(tbase, ad, bd, id, first | (uint32_t)img);
+                        }
                     }
                 }
         }
@@ -124,19 +151,21 @@ __global__ void __launch_bounds__(128) probe(const __grid_constant__ CUtensorMap
     mbar_wait(smem_u32(&bar_mma), 0);
     t3 = clock64();
     tc_fence_after();
-    if (tid == 0) { a.clk[0] = t3 - t2; a.clk[1] = (long long)a.reps * 3 * (CQ / 2) * 2; }
+    if (tid == 0) { a.clk[0] = t3 - t2; a.clk[1] = (long long)a.reps * 3 * (CQ / 2) * (a.variant == 1 ? 1 : 2); }
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
 #pragma unroll
     for (int c = 0; c < N; c += 16) {
-        uint32_t v[16];
+        uint32_t v[16], u[16];
         tmem_ld16(tbase + lane_off + c, v);
+        tmem_ld16(tbase + lane_off + N + c, u);                      // variant 1: the w2 half of the accumulator
         tc_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) a.out[(size_t)tid * N + c + i] = __uint_as_float(v[i]);
+        for (int i = 0; i < 16; ++i)
+            a.out[(size_t)tid * N + c + i] = __uint_as_float(v[i]) + (a.variant == 1 ? __uint_as_float(u[i]) : 0.f);
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tbase, 128);
+    if (warp == 0) tmem_dealloc(tbase, 256);
 }
 
 static uint16_t bf16_rn(float f) {
@@ -180,6 +209,15 @@ int main(int argc, char** argv) {
                             const size_t base = (size_t)img * (B_IMG / 2) + (((size_t)(kx * CQ + q) * N + ky * COUT + co) * 8) + 2 * e;
                             wimg[base] = wimg[base + 1] = img ? w2 : w1;
                         }
+    const int variant = argc > 2 ? atoi(argv[2]) : 0;
+    if (variant == 1) {                     // [kx][chunk][96 rows = w1 image | w2 image][16 B]
+        std::vector<uint16_t> w96(wimg.size());
+        for (int kq = 0; kq < 3 * CQ; ++kq)
+            for (int img = 0; img < 2; ++img)
+                for (int i = 0; i < N * 8; ++i)
+                    w96[((size_t)kq * 2 + img) * N * 8 + i] = wimg[(size_t)img * (B_IMG / 2) + (size_t)kq * N * 8 + i];
+        wimg = w96;
+    }
     uint32_t* d_act; uint8_t* d_w; float* d_out; long long* d_clk;
     cudaMalloc(&d_act, words.size() * 4); cudaMalloc(&d_w, 2 * B_IMG); cudaMalloc(&d_out, 128 * N * 4); cudaMallocManaged(&d_clk, 64);
     cudaMemcpy(d_act, words.data(), words.size() * 4, cudaMemcpyHostToDevice);
@@ -193,7 +231,7 @@ int main(int argc, char** argv) {
     cuuint32_t box[4] = {4, BOXW, 1, CQ}, es[4] = {1, 1, 1, 1};
     CUresult er = ((EncodeTiledFn)ptr)(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, d_act, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    printf("cuTensorMapEncodeTiled (uint32, 4-D box {4,%d,1,%d}) -> %d ; swap_lbo_sbo=%d\n", BOXW, CQ, (int)er, swap);
+    printf("cuTensorMapEncodeTiled (uint32, 4-D box {4,%d,1,%d}) -> %d ; swap_lbo_sbo=%d variant=%d\n", BOXW, CQ, (int)er, swap, variant);
 
     const int smem = 8192 + 2 * B_IMG + 1024;
     cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -201,7 +239,7 @@ int main(int argc, char** argv) {
     const int cases[][2] = {{3, 0}, {0, 0}, {H - 1, 64}, {4, 128}};            // (row y, tile origin x0): x0 = 0 reads pixel -1, 128 runs past W
     for (int mode = 0; mode <= 1; ++mode)
         for (auto& cs : cases) {
-            Args a{d_act, d_w, d_out, d_clk, mode, cs[0], cs[1], swap, 1};
+            Args a{d_act, d_w, d_out, d_clk, mode, cs[0], cs[1], swap, 1, variant};
             cudaMemset(d_out, 0, 128 * N * 4);
             probe<<<1, 128, smem>>>(tm, a);
             cudaError_t e = cudaDeviceSynchronize();
@@ -230,11 +268,12 @@ int main(int argc, char** argv) {
         }
     // cost of SS-form UMMAs with A from shared memory
     for (int reps : {1, 64, 512}) {
-        Args a{d_act, d_w, d_out, d_clk, 0, 3, 0, swap, reps};
+        Args a{d_act, d_w, d_out, d_clk, 0, 3, 0, swap, reps, variant};
         probe<<<1, 128, smem>>>(tm, a);
         if (cudaDeviceSynchronize() != cudaSuccess) { printf("timing run failed\n"); return 1; }
-        printf("SS-form kind::f16 M=128 N=%d K=16: %lld MMAs in %lld clk -> %.1f clk per MMA (N/2 = %d would be the tensor rate)\n", N,
-               d_clk[1], d_clk[0], (double)d_clk[0] / d_clk[1], N / 2);
+        const int n = variant == 1 ? 2 * N : N;
+        printf("variant %d kind::f16 M=128 N=%d K=16: %lld MMAs in %lld clk -> %.1f clk per MMA (N/2 = %d would be the tensor rate)\n", variant, n,
+               d_clk[1], d_clk[0], (double)d_clk[0] / d_clk[1], n / 2);
     }
     return 0;
 }

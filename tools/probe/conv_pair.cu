@@ -69,6 +69,17 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t adesc, ui
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(1), "r"(0), "r"(0), "r"(0), "r"(0)
         : "memory");
 }
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}\n"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(1), "r"(0), "r"(0), "r"(0), "r"(0)
+        : "memory");
+}
+// 128 lanes x 256 bits (one K = 16 slice of a 16-bit A operand = 8 TMEM columns): shared memory (matrix descriptor) -> TMEM
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t sdesc) {
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
 // x -> (b1, b2): b1 = bf16(x) round-to-nearest-even, b2 = bf16(x - b1); packed b1 | b2 << 16 (b1 = the even K element)
 __device__ __forceinline__ uint32_t bf16_rn_bits(float v) {
     const uint32_t u = __float_as_uint(v);
@@ -96,7 +107,12 @@ struct PairGeom {
     static_assert(CQ % 2 == 0 && SMEM_BYTES <= 227 * 1024, "geometry");
 };
 
-template <int CQA, int CQB, int COUT, int EPI>
+// A_CP = false: SS form, the UMMAs read A from shared memory (4 KB per instruction, twice per tap: once per weight image).
+// A_CP = true : each 128 x K16 slice of the staged row is copied ONCE into TMEM by tcgen05.cp (no registers involved) and the UMMAs
+//               use the TS form; two A buffers alternate between input rows.  Relies on the tensor pipe executing the cp / mma
+//               stream of the single issuing thread in order (cp -> mma is documented; the mma -> cp WAR two rows later is the
+//               thing to confirm on hardware: if not, wait on the s_empty commit of row i-2 before the copies).
+template <int CQA, int CQB, int COUT, int EPI, bool A_CP>
 __global__ void __launch_bounds__(PTHREADS, 1) conv3x3_pair_kernel(const __grid_constant__ PairParams p) {
     constexpr int CQ = CQA + CQB;
     using G = PairGeom<CQ, COUT>;
@@ -116,7 +132,8 @@ __global__ void __launch_bounds__(PTHREADS, 1) conv3x3_pair_kernel(const __grid_
 
     for (int i = tid; i < G::W_BYTES / 16; i += PTHREADS)
         reinterpret_cast<int4*>(sm)[i] = __ldg(reinterpret_cast<const int4*>(job.wimg) + i);
-    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 128);
+    constexpr uint32_t TCOLS = A_CP ? 512u : 128u;                    // accumulator ring [0,128) (+ two A buffers of 24 * KSTEPS columns from 128)
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), TCOLS);
     if (tid == 0) {
         for (int i = 0; i < NS; ++i) { mbar_init(s_full(i), 1); mbar_init(s_empty(i), 1); }
         for (int i = 0; i < PND; ++i) { mbar_init(d_full(i), 1); mbar_init(d_empty(i), 4); }
@@ -191,6 +208,14 @@ __global__ void __launch_bounds__(PTHREADS, 1) conv3x3_pair_kernel(const __grid_
                     }
                     tc_fence_after();
                     const uint32_t sA = stage_base + (uint32_t)s * G::STAGE;
+                    const uint32_t tA = tbase + 128u + (uint32_t)(i & 1) * (24u * G::KSTEPS);
+                    if (A_CP) {
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                            for (int j = 0; j < G::KSTEPS; ++j)
+                                tmem_cp_128x256b(tA + 8u * (uint32_t)(kx * G::KSTEPS + j), desc_nosw(sA + kx * 16 + 2 * j * PCHUNK, PCHUNK, 128));
+                    }
                     const int lo = r - 1 < 0 ? 0 : r - 1, hi = r + 1 > nrows - 1 ? nrows - 1 : r + 1;
                     int o = lo;
                     while (o <= hi) {                                 // runs of output rows whose ring slots are adjacent (the ring wraps)
@@ -208,7 +233,8 @@ __global__ void __launch_bounds__(PTHREADS, 1) conv3x3_pair_kernel(const __grid_
 #pragma unroll
                                 for (int img = 0; img < 2; ++img) {
                                     const uint64_t bd = desc_nosw(sW + img * G::IMG_HALF + ((kx * CQ + 2 * j) * PBROWS + brow) * 16, PBROWS * 16, 128);
-                                    umma_bf16_ss(d, ad, bd, id);
+                                    if (A_CP) umma_bf16_ts(d, tA + 8u * (uint32_t)(kx * G::KSTEPS + j), bd, id);
+                                    else umma_bf16_ss(d, ad, bd, id);
                                 }
                             }
                         o += n;
@@ -301,7 +327,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) conv3x3_pair_kernel(const __grid_
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tbase, 128);
+    if (warp == 1) tmem_dealloc(tbase, TCOLS);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -364,7 +390,8 @@ static bool make_tmap_pair(CUtensorMap* tm, const uint32_t* ptr, int cq, int H, 
 template <int CQA, int CQB, int COUT, int EPI>
 static int launch_pair(PairParams& p, int njobs, cudaStream_t st) {
     using G = PairGeom<CQA + CQB, COUT>;
-    auto k = conv3x3_pair_kernel<CQA, CQB, COUT, EPI>;
+    static const bool a_cp = [] { const char* e = getenv("POPCORN_PAIR_A_CP"); return e && atoi(e) != 0; }();
+    auto k = a_cp ? conv3x3_pair_kernel<CQA, CQB, COUT, EPI, true> : conv3x3_pair_kernel<CQA, CQB, COUT, EPI, false>;
     PC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);

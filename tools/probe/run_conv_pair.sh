@@ -1,0 +1,11 @@
+#!/bin/bash
+# Round-2 bring-up (after run_pair_probe.sh has confirmed the descriptor semantics):
+#   gpurun --timeout 600 -- 'bash tools/probe/run_conv_pair.sh > gpurun_out/conv_pair.txt 2>&1'
+cd "$(dirname "$0")/../.."
+bash tools/probe/build_conv_pair.sh 2>&1 | grep -i "error" && exit 1
+python tools/probe/emulate_conv_pair.py
+for cp in 0 1; do
+  echo "=== POPCORN_PAIR_A_CP=$cp ==="
+  POPCORN_PAIR_A_CP=$cp timeout 180 python tools/probe/test_conv_pair.py
+  echo "exit code $?"
+done

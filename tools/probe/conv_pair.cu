@@ -201,10 +201,14 @@ __global__ void __launch_bounds__(PTHREADS, 1) conv3x3_pair_kernel(const __grid_
 #pragma unroll 1
                 for (int r = -1; r <= nrows; ++r, ++i) {
                     const int s = i % NS;
-                    mbar_wait_sleep(s_full(s), (uint32_t)(i / NS) & 1u);
-                    if (r + 1 <= nrows - 1) {                         // this row opens the slot of output row r+1: it must have been drained
+                    {
+                        // the row has landed (s_full) + the slot of output row r+1, which this row opens, has been drained (d_empty):
+                        // ONE merged probe — a blocking mbarrier probe costs ~200 cycles even when the phase completed long ago
+                        const uint32_t m1 = s_full(s), p1 = (uint32_t)(i / NS) & 1u;
+                        uint32_t m2 = m1, p2 = p1;
                         const int g = g0 + r + 1;
-                        if (g >= PND) mbar_wait_sleep(d_empty(g % PND), (uint32_t)(g / PND - 1) & 1u);
+                        if (r + 1 <= nrows - 1 && g >= PND) { m2 = d_empty(g % PND); p2 = (uint32_t)(g / PND - 1) & 1u; }
+                        mbar_wait3_sleep(m1, p1, m2, p2, m2, p2);
                     }
                     tc_fence_after();
                     const uint32_t sA = stage_base + (uint32_t)s * G::STAGE;

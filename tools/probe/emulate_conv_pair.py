@@ -3,7 +3,7 @@
 Re-implements in numpy what the kernel's three roles do — the host weight packing ([w1 | w2][kx][chunk][48 rows][4 ch x (w, w)]),
 the staged 136-pixel rows in 16-byte chunks, the UMMA windows (A = 128 pixels x K16 at a +kx pixel shift, B = 16*n rows starting
 at the ky block of the first output row of the run), the 8-slot accumulator ring with its wrap, halo rows and zero padding — and
-checks the result against conv2d on the same bf16-pair operands.  What it cannot check is the hardware's reading of the
+checks the result against conv2d on the same fp16-pair operands.  What it cannot check is the hardware's reading of the
 descriptors (LBO / SBO / element order inside a chunk): that is tools/probe/pair_probe.cu's job on a B200."""
 import sys, numpy as np, torch, torch.nn.functional as F
 import os
@@ -11,8 +11,8 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from test_conv_pair import to_pair, from_pair, pair_value, bf16_pieces
 PBOX, PBROWS, PND = 136, 48, 8
 
-def bf(x):  # bf16 RN as float32
-    return torch.tensor(x).to(torch.bfloat16).float().numpy()
+def bf(x):  # fp16 RN as float32
+    return torch.tensor(x).to(torch.float16).float().numpy()
 
 def pack_layer(flat, cin, cout):
     cq = cin // 4; half = 3 * cq * PBROWS * 8

@@ -1,6 +1,6 @@
-// Standalone probe for the round-2 "bf16 pair" convolution design (profiles/r1c_precision_study.md):
+// Standalone probe for the round-2 "fp16 pair" convolution design (profiles/r1c_precision_study.md):
 //
-//   * activations live in memory as 16-byte pixel chunks  [C/4][H][W][4 channels x (b1, b2)]  with x = b1 + b2, two bf16 in one
+//   * activations live in memory as 16-byte pixel chunks  [C/4][H][W][4 channels x (b1, b2)]  with x = h1 + h2, two fp16 in one
 //     32-bit word (b1 in the low half = the even K element);
 //   * a row of 130 pixels (128 + the kx halo) x C/4 chunks is brought to shared memory by ONE 4-D TMA box {4 words, 130, 1, C/4}
 //     (out-of-bounds pixels zero-filled), which IS the canonical K-major no-swizzle ("interleave") UMMA operand layout:
@@ -23,6 +23,7 @@
 //                (A is fetched from shared memory once instead of twice)
 //     variant 2: tcgen05.cp.128x256b copies each 128 x K16 slice of A from shared memory into TMEM, then two TS-form N = 48 UMMAs
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -44,9 +45,9 @@ constexpr int LBO_B = N * 16;               // same for B (N rows of 16 bytes pe
 constexpr int A_BYTES = CQ * BOXW * 16;
 constexpr int B_IMG = 3 * CQ * N * 16;      // one weight image: [kx][chunk][n][16 B]
 
-// instruction descriptor kind::f16: D = f32 (bits 4-5 = 1), A = B = bf16 (bits 7-9, 10-12 = 1), K-major, N>>3 @17, M>>4 @24
-__host__ __device__ constexpr uint32_t idesc_bf16(uint32_t M, uint32_t n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((M >> 4) << 24);
+// instruction descriptor kind::f16: D = f32 (bits 4-5 = 1), A = B = fp16 (bits 7-9, 10-12 = 0; bf16 would be 1), K-major, N>>3 @17, M>>4 @24
+__host__ __device__ constexpr uint32_t idesc_bf16(uint32_t M, uint32_t n) {      // (name kept; the operands are fp16 pairs, see r1c_precision_study.md)
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((n >> 3) << 17) | ((M >> 4) << 24);
 }
 // K-major no-swizzle descriptor: start>>4 | LBO>>4 @16 | SBO>>4 @32 | version 1 @46 | layout 0 @61
 __device__ __forceinline__ uint64_t make_desc_nosw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
@@ -168,12 +169,9 @@ __global__ void __launch_bounds__(128) probe(const __grid_constant__ CUtensorMap
     if (warp == 0) tmem_dealloc(tbase, 256);
 }
 
-static uint16_t bf16_rn(float f) {
-    uint32_t u; memcpy(&u, &f, 4);
-    u += 0x7FFFu + ((u >> 16) & 1u);
-    return (uint16_t)(u >> 16);
-}
-static float bf16_f(uint16_t h) { uint32_t u = (uint32_t)h << 16; float f; memcpy(&f, &u, 4); return f; }
+// fp16 pieces (the names say bf16 for historical reasons: the first version of this probe used bf16 pairs, which fail the parity bar)
+static uint16_t bf16_rn(float f) { const __half h = __float2half_rn(f); uint16_t u; memcpy(&u, &h, 2); return u; }
+static float bf16_f(uint16_t u) { __half h; memcpy(&h, &u, 2); return __half2float(h); }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,

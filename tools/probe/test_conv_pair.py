@@ -1,13 +1,13 @@
-"""Round-2 bring-up check of tools/probe/conv_pair.cu (the bf16-pair, stager-free conv kernel) — needs a B200.
+"""Round-2 bring-up check of tools/probe/conv_pair.cu (the fp16-pair, stager-free conv kernel) — needs a B200.
 
     bash tools/probe/build_conv_pair.sh && timeout 120 python tools/probe/test_conv_pair.py
 
 Each case runs in the same process; a trap (barrier protocol mistake) poisons the context, so the first failure ends the run.
 Checks, per layer shape of the DDA UNet:
-  * planar fp32 output  == relu(conv2d(x_pair, w_pair) + b) computed in fp64 on the SAME bf16-pair operands   (tolerance 2e-5 rel:
+  * planar fp32 output  == relu(conv2d(x_pair, w_pair) + b) computed in fp64 on the SAME fp16-pair operands   (tolerance 2e-5 rel:
     fp32 accumulation order only);
-  * pair output         == the pair packing of that result (to 2^-15 relative);
-  * against the true fp32 conv the error is the 16-bit operand rounding (~1e-4 relative), what profiles/r1c_precision_study.md
+  * pair output         == the pair packing of that result (to 2^-21 relative);
+  * against the true fp32 conv the error is the 22-bit operand rounding (~1e-6 relative), what profiles/r1c_precision_study.md
     budgets for.
 """
 import ctypes as C
@@ -22,8 +22,9 @@ LIB = os.path.join(ROOT, "popcorn_b200", "libpopcorn_b200_probe.so")
 
 
 def bf16_pieces(x: torch.Tensor):
-    b1 = x.to(torch.bfloat16)
-    b2 = (x - b1.float()).to(torch.bfloat16)
+    """(h1, h2) fp16 pieces of x (the name predates the switch from bf16 to fp16 pairs: profiles/r1c_precision_study.md)."""
+    b1 = x.clamp(-65504.0, 65504.0).to(torch.float16)
+    b2 = (x.clamp(-65504.0, 65504.0) - b1.float()).to(torch.float16)
     return b1, b2
 
 
@@ -37,8 +38,8 @@ def to_pair(x: torch.Tensor) -> torch.Tensor:
 
 def from_pair(w: torch.Tensor) -> torch.Tensor:
     """[C/4,H,W,4] int32 -> [C,H,W] fp32 (b1 + b2)."""
-    b1 = (w << 16).view(torch.float32)
-    b2 = (w & ~0xFFFF).view(torch.float32)
+    b1 = (w & 0xFFFF).to(torch.int16).view(torch.float16).float()
+    b2 = (w >> 16).to(torch.int16).view(torch.float16).float()
     v = b1 + b2
     q, H, W, _ = w.shape
     return v.permute(0, 3, 1, 2).reshape(4 * q, H, W).contiguous()
@@ -83,12 +84,12 @@ def run_case(lib, cin_a, cin_b, cout, H, W, pool=False, b_shape=None, b_off=(0, 
     e_pair = float((from_pair(out_pair.cpu()).double() - ref).abs().max()) / scale
     e_fp32 = float((out_planar.cpu().double() - ref32).abs().max()) / scale
     msg = f"cin {cin_a}+{cin_b} cout {cout} {H}x{W} TR {tile_rows}: planar {e_planar:.2e}  pair {e_pair:.2e}  vs fp32 conv {e_fp32:.2e}"
-    ok = e_planar < 2e-5 and e_pair < 6e-5
+    ok = e_planar < 2e-5 and e_pair < 2e-5
     if pool:
         pref = F.max_pool2d(ref[None], 2)[0]
         e_pool = float((from_pair(pool_pair.cpu()).double() - pref).abs().max()) / scale
         msg += f"  pool {e_pool:.2e}"
-        ok = ok and e_pool < 6e-5
+        ok = ok and e_pool < 2e-5
     print(("OK   " if ok else "FAIL ") + msg, flush=True)
     return ok
 

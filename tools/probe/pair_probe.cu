@@ -22,6 +22,9 @@
 //     variant 1: SS form, ONE N = 96 UMMA per (tap, 8 channels) — [B(w1) | B(w2)] side by side, the read-out adds the halves
 //                (A is fetched from shared memory once instead of twice)
 //     variant 2: tcgen05.cp.128x256b copies each 128 x K16 slice of A from shared memory into TMEM, then two TS-form N = 48 UMMAs
+//     variant 3: the 3xTF32 sibling (tools/probe/conv_ss.cu): fp32 chunks [C/4][H][W][4 floats], kind::tf32 (K = 8 = 2 chunks) reads
+//                the RAW staged row as A_hi (the tensor core ignores the low 13 mantissa bits), a thread pass writes lo = x - hi
+//                into a second buffer; D = A*B_hi + A_lo*B_hi + A*B_lo with tf32 hi/lo weight images
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -86,7 +89,8 @@ __global__ void __launch_bounds__(128) probe(const __grid_constant__ CUtensorMap
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = sm;                                   // A_BYTES (4160), padded to 8 KB
-    uint8_t* sB = sm + 8192;                            // 2 * B_IMG
+    uint8_t* sAlo = sm + 8192;                          // variant 3: lo = x - trunc_tf32(x), same layout
+    uint8_t* sB = sm + 16384;                           // 2 * B_IMG
     __shared__ __align__(8) unsigned long long bar_tma, bar_mma;
     __shared__ uint32_t slot;
     const int tid = threadIdx.x, warp = uniform_warp_idx();
@@ -118,6 +122,14 @@ __global__ void __launch_bounds__(128) probe(const __grid_constant__ CUtensorMap
         mbar_wait(smem_u32(&bar_tma), 0);
         if (tid == 0) { t1 = clock64(); a.clk[2] = t1 - t0; }
     }
+    if (a.variant == 3) {
+        for (int i = tid; i < CQ * BOXW * 4; i += 128) {
+            const float v = reinterpret_cast<const float*>(sA)[i];
+            reinterpret_cast<float*>(sAlo)[i] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+    }
     if (warp == 0 && elect_one()) {
         const uint32_t lboA = a.swap ? 128u : (uint32_t)LBO_A, sboA = a.swap ? (uint32_t)LBO_A : 128u;
         const uint32_t lboB = a.swap ? 128u : (uint32_t)LBO_B, sboB = a.swap ? (uint32_t)LBO_B : 128u;
@@ -132,7 +144,18 @@ __global__ void __launch_bounds__(128) probe(const __grid_constant__ CUtensorMap
                 for (int j = 0; j < CQ / 2; ++j) {                 // one K=16 instruction = 8 channels = 2 chunks
                     const uint64_t ad = make_desc_nosw(smem_u32(sA) + kx * 16 + 2 * j * LBO_A, lboA, sboA);
                     const uint32_t first = (rep | kx | j) ? 1u : 0u;
-                    if (a.variant == 1) {                          // B rows [0,48) = w1 image, [48,96) = w2 image: same chunk, 96 rows
+                    if (a.variant == 3) {
+                        const uint32_t idt = umma_idesc_tf32(128, N);
+                        const uint64_t alo = make_desc_nosw(smem_u32(sAlo) + kx * 16 + 2 * j * LBO_A, lboA, sboA);
+                        const uint64_t bhi = make_desc_nosw(smem_u32(sB) + (kx * CQ + 2 * j) * LBO_B, lboB, sboB);
+                        const uint64_t blo = make_desc_nosw(smem_u32(sB) + B_IMG + (kx * CQ + 2 * j) * LBO_B, lboB, sboB);
+                        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}\n"
+                                     ::"r"(tbase), "l"(ad), "l"(bhi), "r"(idt), "r"(first), "r"(0), "r"(0), "r"(0), "r"(0) : "memory");
+                        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}\n"
+                                     ::"r"(tbase), "l"(alo), "l"(bhi), "r"(idt), "r"(1), "r"(0), "r"(0), "r"(0), "r"(0) : "memory");
+                        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}\n"
+                                     ::"r"(tbase), "l"(ad), "l"(blo), "r"(idt), "r"(1), "r"(0), "r"(0), "r"(0), "r"(0) : "memory");
+                    } else if (a.variant == 1) {                          // B rows [0,48) = w1 image, [48,96) = w2 image: same chunk, 96 rows
                         const uint64_t bd = make_desc_nosw(smem_u32(sB) + (kx * CQ + 2 * j) * (2 * LBO_B), a.swap ? 128u : 2u * LBO_B,
                                                            a.swap ? 2u * LBO_B : 128u);
                         umma_bf16_ss(tbase, ad, bd, id96, first);
@@ -152,7 +175,7 @@ __global__ void __launch_bounds__(128) probe(const __grid_constant__ CUtensorMap
     mbar_wait(smem_u32(&bar_mma), 0);
     t3 = clock64();
     tc_fence_after();
-    if (tid == 0) { a.clk[0] = t3 - t2; a.clk[1] = (long long)a.reps * 3 * (CQ / 2) * (a.variant == 1 ? 1 : 2); }
+    if (tid == 0) { a.clk[0] = t3 - t2; a.clk[1] = (long long)a.reps * 3 * (CQ / 2) * (a.variant == 1 ? 1 : a.variant == 3 ? 3 : 2); }
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
 #pragma unroll
     for (int c = 0; c < N; c += 16) {
@@ -216,6 +239,23 @@ int main(int argc, char** argv) {
                     w96[((size_t)kq * 2 + img) * N * 8 + i] = wimg[(size_t)img * (B_IMG / 2) + (size_t)kq * N * 8 + i];
         wimg = w96;
     }
+    auto tf32_hi = [](float f) { uint32_t u; memcpy(&u, &f, 4); u &= 0xFFFFE000u; float r; memcpy(&r, &u, 4); return r; };
+    if (variant == 3) {                     // fp32 chunks (same bytes as the pair words) + tf32 hi / lo weight images [kx][chunk][n][4 floats]
+        for (int c = 0; c < C; ++c)
+            for (int y = 0; y < H; ++y)
+                for (int x = 0; x < W; ++x) memcpy(&words[(((size_t)(c / 4) * H + y) * W + x) * 4 + c % 4], &act[(c * H + y) * W + x], 4);
+        std::vector<float> w32(2 * B_IMG / 4, 0.f);
+        for (int kx = 0; kx < 3; ++kx)
+            for (int q = 0; q < CQ; ++q)
+                for (int ky = 0; ky < 3; ++ky)
+                    for (int co = 0; co < COUT; ++co)
+                        for (int e = 0; e < 4; ++e) {
+                            const float w = wt[((co * C + q * 4 + e) * 3 + ky) * 3 + kx], hi = tf32_hi(w);
+                            const size_t at = ((size_t)(kx * CQ + q) * N + ky * COUT + co) * 4 + e;
+                            w32[at] = hi; w32[B_IMG / 4 + at] = w - hi;
+                        }
+        memcpy(wimg.data(), w32.data(), 2 * B_IMG);
+    }
     uint32_t* d_act; uint8_t* d_w; float* d_out; long long* d_clk;
     cudaMalloc(&d_act, words.size() * 4); cudaMalloc(&d_w, 2 * B_IMG); cudaMalloc(&d_out, 128 * N * 4); cudaMallocManaged(&d_clk, 64);
     cudaMemcpy(d_act, words.data(), words.size() * 4, cudaMemcpyHostToDevice);
@@ -231,7 +271,7 @@ int main(int argc, char** argv) {
                                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     printf("cuTensorMapEncodeTiled (uint32, 4-D box {4,%d,1,%d}) -> %d ; swap_lbo_sbo=%d variant=%d\n", BOXW, CQ, (int)er, swap, variant);
 
-    const int smem = 8192 + 2 * B_IMG + 1024;
+    const int smem = 16384 + 2 * B_IMG + 1024;
     cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     std::vector<float> out(128 * N);
     const int cases[][2] = {{3, 0}, {0, 0}, {H - 1, 64}, {4, 128}};            // (row y, tile origin x0): x0 = 0 reads pixel -1, 128 runs past W
@@ -254,13 +294,17 @@ int main(int argc, char** argv) {
                                 if (x < 0 || x >= W) continue;
                                 const float v = act[(ci * H + cs[0]) * W + x], w = wt[((co * C + ci) * 3 + ky) * 3 + kx];
                                 const uint16_t b1 = bf16_rn(v), b2 = bf16_rn(v - bf16_f(b1)), w1 = bf16_rn(w), w2 = bf16_rn(w - bf16_f(w1));
+                                if (variant == 3) {
+                                    const float vh = tf32_hi(v), vl = tf32_hi(v - vh), wh = tf32_hi(w), wl = tf32_hi(w - wh);
+                                    rp += (double)vh * wh + (double)vl * wh + (double)vh * wl;
+                                } else
                                 rp += ((double)bf16_f(b1) + bf16_f(b2)) * ((double)bf16_f(w1) + bf16_f(w2));
                                 rf += (double)v * w;
                             }
                         const double g = out[(size_t)t * N + ky * COUT + co];
                         err_pair = fmax(err_pair, fabs(g - rp)); err_fp32 = fmax(err_fp32, fabs(g - rf)); ref_max = fmax(ref_max, fabs(rf));
                     }
-            printf("mode %d (%s) y=%d x0=%3d : max|err| vs same bf16 operands %.3e, vs fp32 conv %.3e (max |ref| %.2f)%s\n", mode,
+            printf("mode %d (%s) y=%d x0=%3d : max|err| vs same split operands %.3e, vs fp32 conv %.3e (max |ref| %.2f)%s\n", mode,
                    mode ? "TMA 4-D box" : "thread copy", cs[0], cs[1], err_pair, err_fp32, ref_max, err_pair < 1e-4 ? "  OK" : "  MISMATCH");
             if (mode == 1) printf("         TMA row (%d B) issue -> landed: %lld clk\n", A_BYTES, d_clk[2]);
         }

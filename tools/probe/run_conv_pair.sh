@@ -4,6 +4,9 @@
 cd "$(dirname "$0")/../.."
 bash tools/probe/build_conv_pair.sh 2>&1 | grep -i "error" && exit 1
 python tools/probe/emulate_conv_pair.py
+echo "=== conv_ss (3xTF32, SS form) ==="
+timeout 180 python tools/probe/test_conv_pair.py ss
+echo "exit code $?"
 for cp in 0 1; do
   echo "=== POPCORN_PAIR_A_CP=$cp ==="
   POPCORN_PAIR_A_CP=$cp timeout 180 python tools/probe/test_conv_pair.py

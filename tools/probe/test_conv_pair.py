@@ -1,6 +1,7 @@
-"""Round-2 bring-up check of tools/probe/conv_pair.cu (the fp16-pair, stager-free conv kernel) — needs a B200.
+"""Round-2 bring-up check of tools/probe/conv_pair.cu (fp16-pair operands) and tools/probe/conv_ss.cu (3xTF32, raw fp32 A from
+shared memory) — the two stager-free conv candidates — needs a B200.
 
-    bash tools/probe/build_conv_pair.sh && timeout 120 python tools/probe/test_conv_pair.py
+    bash tools/probe/build_conv_pair.sh && timeout 120 python tools/probe/test_conv_pair.py [pair|ss]
 
 Each case runs in the same process; a trap (barrier protocol mistake) poisons the context, so the first failure ends the run.
 Checks, per layer shape of the DDA UNet:
@@ -48,6 +49,59 @@ def from_pair(w: torch.Tensor) -> torch.Tensor:
 def pair_value(x: torch.Tensor) -> torch.Tensor:
     b1, b2 = bf16_pieces(x)
     return b1.double() + b2.double()
+
+
+def to_c4(x: torch.Tensor) -> torch.Tensor:
+    """[C,H,W] fp32 -> [C/4,H,W,4] fp32 chunks (conv_ss.cu's layout)."""
+    Cc, H, W = x.shape
+    return x.view(Cc // 4, 4, H, W).permute(0, 2, 3, 1).contiguous()
+
+
+def from_c4(c: torch.Tensor) -> torch.Tensor:
+    q, H, W, _ = c.shape
+    return c.permute(0, 3, 1, 2).reshape(4 * q, H, W).contiguous()
+
+
+def run_case_ss(lib, cin_a, cin_b, cout, H, W, pool=False, b_shape=None, b_off=(0, 0), tile_rows=0, seed=0):
+    """conv_ss.cu: 3xTF32 — compared with the exact conv (fp64); expected error ~1e-6 relative, bar 1e-5."""
+    g = torch.Generator().manual_seed(seed)
+    cin = cin_a + cin_b
+    xa = torch.randn(cin_a, H, W, generator=g) * 2
+    bH, bW = b_shape or (H, W)
+    xb = torch.randn(cin_b, bH, bW, generator=g) * 2 if cin_b else None
+    w = torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (9 * cin)) ** 0.5
+    bias = torch.randn(cout, generator=g) * 0.1
+    flat = torch.cat([w.permute(1, 2, 3, 0).reshape(-1), bias]).contiguous()
+    x_all = xa
+    if cin_b:
+        full_b = torch.zeros(cin_b, H, W)
+        full_b[:, b_off[0]:b_off[0] + bH, b_off[1]:b_off[1] + bW] = xb
+        x_all = torch.cat([xa, full_b], 0)
+    ref = F.relu(F.conv2d(x_all[None].double(), w.double(), bias.double(), padding=1))[0]
+    dev = "cuda"
+    a_c = to_c4(xa).to(dev)
+    b_c = to_c4(xb).to(dev) if cin_b else None
+    out_c4 = torch.full((cout // 4, H, W, 4), float("nan"), device=dev)
+    out_planar = torch.full((cout, H, W), float("nan"), device=dev)
+    pool_c4 = torch.full((cout // 4, H // 2, W // 2, 4), float("nan"), device=dev) if pool else None
+    rc = lib.pc_probe_conv3x3_ss(a_c.data_ptr(), cin_a // 4, H, W, 0, 0, b_c.data_ptr() if cin_b else None, cin_b // 4, bH, bW,
+                                 b_off[0], b_off[1], flat.data_ptr(), cout, 1, H, W, out_c4.data_ptr(), out_planar.data_ptr(),
+                                 pool_c4.data_ptr() if pool else None, tile_rows, None)
+    assert rc == 0, f"pc_probe_conv3x3_ss returned {rc}"
+    torch.cuda.synchronize()
+    scale = float(ref.abs().max())
+    e_planar = float((out_planar.cpu().double() - ref).abs().max()) / scale
+    e_c4 = float((from_c4(out_c4.cpu()).double() - ref).abs().max()) / scale
+    same = torch.equal(from_c4(out_c4.cpu()), out_planar.cpu())
+    msg = f"ss cin {cin_a}+{cin_b} cout {cout} {H}x{W} TR {tile_rows}: planar {e_planar:.2e}  chunks {e_c4:.2e}  planar == chunks {same}"
+    ok = e_planar < 1e-5 and same
+    if pool:
+        pref = F.max_pool2d(ref[None], 2)[0]
+        e_pool = float((from_c4(pool_c4.cpu()).double() - pref).abs().max()) / scale
+        msg += f"  pool {e_pool:.2e}"
+        ok = ok and e_pool < 1e-5
+    print(("OK   " if ok else "FAIL ") + msg, flush=True)
+    return ok
 
 
 def run_case(lib, cin_a, cin_b, cout, H, W, pool=False, b_shape=None, b_off=(0, 0), tile_rows=0, seed=0):
@@ -100,6 +154,10 @@ if __name__ == "__main__":
     vp, i = C.c_void_p, C.c_int
     lib.pc_probe_conv3x3_pair.restype = i
     lib.pc_probe_conv3x3_pair.argtypes = [vp, i, i, i, i, i, vp, i, i, i, i, i, vp, i, i, i, i, vp, vp, vp, i, vp]
+    lib.pc_probe_conv3x3_ss.restype = i
+    lib.pc_probe_conv3x3_ss.argtypes = lib.pc_probe_conv3x3_pair.argtypes
+    if len(sys.argv) > 1 and sys.argv[1] == "ss":
+        run_case = run_case_ss                                                # same shapes, the 3xTF32 SS-form kernel
     ok = True
     ok &= run_case(lib, 8, 0, 8, 64, 128)                                   # one tile, no halo columns outside
     ok &= run_case(lib, 8, 0, 8, 70, 200, tile_rows=32)                      # several tiles, ragged right edge, ring wraps

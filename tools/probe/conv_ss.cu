@@ -14,7 +14,7 @@
 //     8-slot TMEM ring, B rows [W_ky2 | W_ky1 | W_ky0]; TMEM carries accumulators only (no A traffic on its single port);
 //   * the epilogue stores 16-byte pixel chunks (coalesced) instead of 8-16 scalar plane stores per thread.
 // Roles: warp 0 = TMA producer (one lane), warp 1 = UMMA issuer (one lane), warps 2-9 = two epilogue groups alternating output-row
-// pairs, warps 10-13 = the lo pass.
+// pairs, warps 10-17 = the lo pass (two groups alternating input rows).
 // Sibling of conv_pair.cu (fp16-pair operands: fewer tensor slots, but a 65504 range that the parity weights nearly exhaust —
 // profiles/r1c_precision_study.md); this variant changes nothing numerically.  Hardware questions: tools/probe/pair_probe.cu.
 #include <cuda.h>
@@ -32,7 +32,7 @@ constexpr int PBOX = 136;                      // staged pixels per row: x0-1 ..
 constexpr int PCHUNK = PBOX * 16;              // bytes of one 4-channel chunk of a staged row = LBO of the A descriptor
 constexpr int PND = 8;                         // accumulator ring: output rows in flight (16 TMEM columns each)
 constexpr int PBROWS = 48;                     // B rows: [W_ky2 | W_ky1 | W_ky0] x 16 output channels (Cout 8 zero-padded)
-constexpr int PTHREADS = 14 * 32;
+constexpr int PTHREADS = 18 * 32;
 enum { PEPI_STORE = 0, PEPI_POOL = 1 };
 
 struct SsJob {
@@ -210,7 +210,8 @@ __global__ void __launch_bounds__(PTHREADS, 1) conv3x3_ss_kernel(const __grid_co
         }
     } else if (warp >= 10) {
         // =========================== lo pass: lo = x - trunc_tf32(x) for every staged value, same layout, second buffer ===========================
-        const int t = (warp - 10) * 32 + lane;                                     // 128 threads: 16-byte slots t, t + 128, ... of the row
+        const int lgroup = (warp - 10) >> 2;                                       // two groups of four warps alternate input rows: a blocking
+        const int t = ((warp - 10) & 3) * 32 + lane;                               // barrier probe (~200 clk) per row must not serialise them
         uint8_t* stage0 = sm + G::OFF_STAGE;
         int i = 0;
 #pragma unroll 1
@@ -218,6 +219,7 @@ __global__ void __launch_bounds__(PTHREADS, 1) conv3x3_ss_kernel(const __grid_co
             const int nrows = tile_rows(tile);
 #pragma unroll 1
             for (int r = -1; r <= nrows; ++r, ++i) {
+                if ((i & 1) != lgroup) continue;
                 const int s = i % NS;
                 mbar_wait_sleep(s_full(s), (uint32_t)(i / NS) & 1u);
                 const float4* raw = reinterpret_cast<const float4*>(stage0 + (size_t)s * G::STAGE);

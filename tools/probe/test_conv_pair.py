@@ -104,6 +104,39 @@ def run_case_ss(lib, cin_a, cin_b, cout, H, W, pool=False, b_shape=None, b_off=(
     return ok
 
 
+def run_c4_helpers(lib):
+    """tools/probe/c4_kernels.cu: layout converters (exact) and ConvTranspose2d k2 s2 on chunks (vs F.conv_transpose2d)."""
+    vp, i, ll = C.c_void_p, C.c_int, C.c_longlong
+    lib.pc_probe_planar_to_c4.restype = i
+    lib.pc_probe_planar_to_c4.argtypes = [vp, ll, i, i, i, i, vp, vp]
+    lib.pc_probe_c4_to_planar.restype = i
+    lib.pc_probe_c4_to_planar.argtypes = [vp, i, i, i, vp, ll, i, vp]
+    lib.pc_probe_convt2x2_c4.restype = i
+    lib.pc_probe_convt2x2_c4.argtypes = [vp, vp, i, i, i, vp, vp]
+    ok = True
+    for Cc, H, W in ((8, 37, 301), (16, 64, 128)):
+        x = torch.randn(Cc, H, W).cuda()
+        c4 = torch.empty(Cc // 4, H, W, 4, device="cuda")
+        back = torch.empty_like(x)
+        assert lib.pc_probe_planar_to_c4(x.data_ptr(), H * W, W, Cc, H, W, c4.data_ptr(), None) == 0
+        assert lib.pc_probe_c4_to_planar(c4.data_ptr(), Cc, H, W, back.data_ptr(), H * W, W, None) == 0
+        torch.cuda.synchronize()
+        good = torch.equal(c4.cpu(), to_c4(x.cpu())) and torch.equal(back, x)
+        print(("OK   " if good else "FAIL ") + f"planar <-> c4 {Cc}x{H}x{W}", flush=True)
+        ok &= good
+        wt = torch.randn(Cc, Cc, 2, 2) * 0.3
+        bt = torch.randn(Cc) * 0.1
+        pack = torch.cat([wt.permute(0, 2, 3, 1).reshape(-1), bt]).contiguous().cuda()       # [ci][dy][dx][co] + bias
+        out = torch.empty(Cc // 4, 2 * H, 2 * W, 4, device="cuda")
+        assert lib.pc_probe_convt2x2_c4(c4.data_ptr(), pack.data_ptr(), Cc, H, W, out.data_ptr(), None) == 0
+        torch.cuda.synchronize()
+        ref = F.conv_transpose2d(x.cpu().double()[None], wt.double(), bt.double(), stride=2)[0]
+        e = float((from_c4(out.cpu()).double() - ref).abs().max() / ref.abs().max())
+        print(("OK   " if e < 1e-6 else "FAIL ") + f"convt2x2_c4<{Cc}> {H}x{W}: {e:.2e}", flush=True)
+        ok &= e < 1e-6
+    return ok
+
+
 def run_case(lib, cin_a, cin_b, cout, H, W, pool=False, b_shape=None, b_off=(0, 0), tile_rows=0, seed=0):
     g = torch.Generator().manual_seed(seed)
     cin = cin_a + cin_b
@@ -156,9 +189,10 @@ if __name__ == "__main__":
     lib.pc_probe_conv3x3_pair.argtypes = [vp, i, i, i, i, i, vp, i, i, i, i, i, vp, i, i, i, i, vp, vp, vp, i, vp]
     lib.pc_probe_conv3x3_ss.restype = i
     lib.pc_probe_conv3x3_ss.argtypes = lib.pc_probe_conv3x3_pair.argtypes
+    ok = True
     if len(sys.argv) > 1 and sys.argv[1] == "ss":
         run_case = run_case_ss                                                # same shapes, the 3xTF32 SS-form kernel
-    ok = True
+        ok &= run_c4_helpers(lib)
     ok &= run_case(lib, 8, 0, 8, 64, 128)                                   # one tile, no halo columns outside
     ok &= run_case(lib, 8, 0, 8, 70, 200, tile_rows=32)                      # several tiles, ragged right edge, ring wraps
     ok &= run_case(lib, 8, 0, 8, 37, 130, tile_rows=32)                      # odd height

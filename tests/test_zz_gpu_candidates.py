@@ -8,7 +8,10 @@ from popcorn_b200 import timeseries as ts
 from oracle import popcorn_oracle as po
 from util import build_model, golden_state_dict, max_rel
 
-pytestmark = pytest.mark.gpu
+# Not yet run on hardware: a failure here must be visible (XFAIL in the report) without turning the validated suite red, a pass
+# shows up as XPASS.  Remove the xfail mark once a B200 run has confirmed them.
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="written after round 1's GPU budget was spent; first hardware run pending")]
 
 
 @pytest.fixture(scope="module")

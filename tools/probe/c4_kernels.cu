@@ -65,6 +65,15 @@ __global__ void __launch_bounds__(128) convt2x2_c4_kernel(const float4* __restri
     }
 }
 
+// host launcher used by dda_c4.cu
+int convt2x2_c4_launch(int C, const float* in, const float* w, int Hl, int Wl, float* out, cudaStream_t st) {
+    const dim3 grid(cdiv(Wl, 32), cdiv(Hl, 4)), block(32, 4);
+    if (C == 8) convt2x2_c4_kernel<8><<<grid, block, 0, st>>>(reinterpret_cast<const float4*>(in), w, Hl, Wl, reinterpret_cast<float4*>(out));
+    else if (C == 16) convt2x2_c4_kernel<16><<<grid, block, 0, st>>>(reinterpret_cast<const float4*>(in), w, Hl, Wl, reinterpret_cast<float4*>(out));
+    else return PC_ERR_INVALID;
+    return (int)cudaGetLastError();
+}
+
 }  // namespace pc
 
 using namespace pc;
@@ -82,8 +91,5 @@ extern "C" int pc_probe_c4_to_planar(const float* in, int C, int H, int W, float
 // in: [C/4][Hl][Wl][4], w: device [C][4][C] + bias[C], out: [C/4][2Hl][2Wl][4]
 extern "C" int pc_probe_convt2x2_c4(const float* in, const float* w, int C, int Hl, int Wl, float* out, void* stream) {
     if (!in || !w || !out || (C != 8 && C != 16) || Hl < 1 || Wl < 1) return PC_ERR_INVALID;
-    const dim3 grid(cdiv(Wl, 32), cdiv(Hl, 4)), block(32, 4);
-    if (C == 8) convt2x2_c4_kernel<8><<<grid, block, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(in), w, Hl, Wl, reinterpret_cast<float4*>(out));
-    else convt2x2_c4_kernel<16><<<grid, block, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(in), w, Hl, Wl, reinterpret_cast<float4*>(out));
-    return (int)cudaGetLastError();
+    return convt2x2_c4_launch(C, in, w, Hl, Wl, out, (cudaStream_t)stream);
 }

@@ -24,30 +24,9 @@
 #include <vector>
 
 #include "tc_common.cuh"
+#include "conv_ss.cuh"
 
 namespace pc {
-
-constexpr int PJOBS = 8;
-constexpr int PBOX = 136;                      // staged pixels per row: x0-1 .. x0+134 (136 * 16 B = 17 * 128 B keeps every chunk 128-B aligned)
-constexpr int PCHUNK = PBOX * 16;              // bytes of one 4-channel chunk of a staged row = LBO of the A descriptor
-constexpr int PND = 8;                         // accumulator ring: output rows in flight (16 TMEM columns each)
-constexpr int PBROWS = 48;                     // B rows: [W_ky2 | W_ky1 | W_ky0] x 16 output channels (Cout 8 zero-padded)
-constexpr int PTHREADS = 18 * 32;
-enum { PEPI_STORE = 0, PEPI_POOL = 1 };
-
-struct SsJob {
-    const uint8_t* wimg;                       // packed weights (conv_ss_pack_layer), device
-    float* out_c4;                             // [COUT/4][H][W][4] fp32 chunks, or null
-    float* out_planar; long long out_cs; int out_rs;   // planar fp32 output (the layer that feeds the head), or null
-    float* pool_c4;                            // [COUT/4][H/2][W/2][4] fp32 chunks (PEPI_POOL)
-    int a_oy, a_ox, b_oy, b_ox;                // source offsets (the Up block's zero-padded upsampled branch)
-    int linear;                                // 1: no ReLU
-};
-struct alignas(64) SsParams {
-    CUtensorMap tmA[PJOBS], tmB[PJOBS];
-    int H, W, TR, tiles_x, tiles_y;
-    SsJob jobs[PJOBS];
-};
 
 // K-major no-swizzle matrix descriptor: start>>4 | LBO>>4 @16 (between 16-byte K chunks) | SBO>>4 @32 (between 8-row groups) | version 1 @46
 __device__ __forceinline__ uint64_t desc_nosw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
@@ -389,6 +368,24 @@ static int launch_ss(SsParams& p, int njobs, cudaStream_t st) {
     return 0;
 }
 
+// ---- API for the layer schedule (dda_c4.cu) ----
+int conv_ss_image_bytes(int cin, int cout) { return conv_ss_img_bytes(cin, cout); }
+void conv_ss_pack(const float* flat, int cin, int cout, uint8_t* img) { conv_ss_pack_layer(flat, cin, cout, img); }
+bool conv_ss_tmap(CUtensorMap* tm, const float* ptr, int cq, int H, int W) { return make_tmap_c4(tm, ptr, cq, H, W); }
+int conv_ss_launch(int cqa, int cqb, int cout, int epi, SsParams& p, int njobs, cudaStream_t st) {
+    const int key = ((cqa * 10 + cqb) * 100 + cout) * 10 + epi;
+    switch (key) {
+        case 20080 + PEPI_STORE: return launch_ss<2, 0, 8, PEPI_STORE>(p, njobs, st);
+        case 20080 + PEPI_POOL: return launch_ss<2, 0, 8, PEPI_POOL>(p, njobs, st);
+        case 20160 + PEPI_STORE: return launch_ss<2, 0, 16, PEPI_STORE>(p, njobs, st);
+        case 40160 + PEPI_STORE: return launch_ss<4, 0, 16, PEPI_STORE>(p, njobs, st);
+        case 40160 + PEPI_POOL: return launch_ss<4, 0, 16, PEPI_POOL>(p, njobs, st);
+        case 44080 + PEPI_STORE: return launch_ss<4, 4, 8, PEPI_STORE>(p, njobs, st);
+        case 22080 + PEPI_STORE: return launch_ss<2, 2, 8, PEPI_STORE>(p, njobs, st);
+    }
+    return PC_ERR_INVALID;
+}
+
 // pc::set_error for the probe library is defined in conv_pair.cu
 
 }  // namespace pc
@@ -417,20 +414,7 @@ extern "C" int pc_probe_conv3x3_ss(const float* a, int cqa, int a_H, int a_W, in
     if (!make_tmap_c4(&p.tmA[0], a, cqa, a_H, a_W)) return PC_ERR_INVALID;
     if (cqb > 0 && !make_tmap_c4(&p.tmB[0], b, cqb, b_H, b_W)) return PC_ERR_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
-    const int key = (cqa * 10 + cqb) * 100 + cout;
-    int rc = PC_ERR_INVALID;
-    if (pool_c4) {
-        if (key == 2008) rc = launch_ss<2, 0, 8, PEPI_POOL>(p, 1, st);
-        else if (key == 4016) rc = launch_ss<4, 0, 16, PEPI_POOL>(p, 1, st);
-    } else {
-        switch (key) {
-            case 2008: rc = launch_ss<2, 0, 8, PEPI_STORE>(p, 1, st); break;
-            case 2016: rc = launch_ss<2, 0, 16, PEPI_STORE>(p, 1, st); break;
-            case 4016: rc = launch_ss<4, 0, 16, PEPI_STORE>(p, 1, st); break;
-            case 4408: rc = launch_ss<4, 4, 8, PEPI_STORE>(p, 1, st); break;
-            case 2208: rc = launch_ss<2, 2, 8, PEPI_STORE>(p, 1, st); break;
-        }
-    }
+    const int rc = conv_ss_launch(cqa, cqb, cout, pool_c4 ? PEPI_POOL : PEPI_STORE, p, 1, st);
     cudaError_t e = cudaStreamSynchronize(st);
     cudaFree(d_img);
     if (rc) return rc;

@@ -12,3 +12,6 @@ for cp in 0 1; do
   POPCORN_PAIR_A_CP=$cp timeout 180 python tools/probe/test_conv_pair.py
   echo "exit code $?"
 done
+echo "=== DDA feature pass, chunk layout vs shipped (A/B) ==="
+timeout 300 python tools/probe/test_dda_c4.py 2048 2048
+echo "exit code $?"

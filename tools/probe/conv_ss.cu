@@ -55,6 +55,10 @@ struct SsGeom {
     static constexpr int SMEM_NEED = OFF_TMEM + 16 + 1024;
     static constexpr int SMEM_BYTES = SMEM_NEED > 116 * 1024 ? SMEM_NEED : 116 * 1024;   // one CTA per SM
     static_assert(CQ % 2 == 0 && SMEM_BYTES <= 227 * 1024, "geometry");
+    // the two lo-pass groups alternate input rows (i & 1): with an even ring depth a stage is always served by the same group, so a
+    // group has seen phase n-1 of a stage's barrier complete before it waits for phase n (parity waits alias two phases apart —
+    // tools/probe/simulate_protocol.py finds the false wake-up with an odd NS)
+    static_assert(NS % 2 == 0, "ring depth must be even");
 };
 
 template <int CQA, int CQB, int COUT, int EPI>

@@ -226,6 +226,14 @@ __global__ void __launch_bounds__(PTHREADS, 1) conv3x3_ss_kernel(const __grid_co
         // =========================== epilogue: two groups alternate output-row pairs ===========================
         const int group = (warp - 2) >> 2;
         const int px = (warp & 3) * 32 + lane;                                     // TMEM lane == pixel; (warp & 3) is also the lane quarter
+        const int cH = p.crop_H > 0 ? p.crop_H : H, cW = p.crop_H > 0 ? p.crop_W : W;
+        float dotw[EPI == PEPI_DOT ? 8 : 1];
+        float dotb = 0.f;
+        if (EPI == PEPI_DOT) {
+#pragma unroll
+            for (int o = 0; o < 8; ++o) dotw[o] = __ldg(job.dotw + o);
+            dotb = __ldg(job.dotw + 8);
+        }
         int g0 = 0;
 #pragma unroll 1
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -273,9 +281,22 @@ __global__ void __launch_bounds__(PTHREADS, 1) conv3x3_ss_kernel(const __grid_co
                             reinterpret_cast<float4*>(job.out_c4)[((size_t)q * H + oy) * W + vx] =
                                 make_float4(acc[h][4 * q], acc[h][4 * q + 1], acc[h][4 * q + 2], acc[h][4 * q + 3]);
                     }
-                    if (job.out_planar) {
+                    const int yy = oy - p.crop_y, xx = vx - p.crop_x;
+                    const bool inside = yy >= 0 && yy < cH && xx >= 0 && xx < cW;
+                    if (job.out_planar && inside) {
 #pragma unroll
-                        for (int o = 0; o < COUT; ++o) job.out_planar[(long long)o * job.out_cs + (long long)oy * job.out_rs + vx] = acc[h][o];
+                        for (int o = 0; o < COUT; ++o) job.out_planar[(long long)o * job.out_cs + (long long)yy * job.out_rs + xx] = acc[h][o];
+                    }
+                    if (EPI == PEPI_DOT && inside) {
+                        float sacc = 0.f;
+#pragma unroll
+                        for (int o = 0; o < 8; ++o) sacc = fmaf(acc[h][o], dotw[o], sacc);
+                        if (job.dot_in) sacc += job.dot_in[(long long)yy * job.dot_in_rs + xx];
+                        if (job.dot_final) {
+                            sacc += dotb;
+                            sacc = 1.f / (1.f + expf(-sacc));
+                        }
+                        job.dot_out[(long long)yy * job.dot_out_rs + xx] = sacc;
                     }
                 }
                 if (EPI == PEPI_POOL) {                               // 2x2 max over (rows 2m, 2m+1) x (lanes 2k, 2k+1)
@@ -381,6 +402,7 @@ int conv_ss_launch(int cqa, int cqb, int cout, int epi, SsParams& p, int njobs, 
     switch (key) {
         case 20080 + PEPI_STORE: return launch_ss<2, 0, 8, PEPI_STORE>(p, njobs, st);
         case 20080 + PEPI_POOL: return launch_ss<2, 0, 8, PEPI_POOL>(p, njobs, st);
+        case 20080 + PEPI_DOT: return launch_ss<2, 0, 8, PEPI_DOT>(p, njobs, st);
         case 20160 + PEPI_STORE: return launch_ss<2, 0, 16, PEPI_STORE>(p, njobs, st);
         case 40160 + PEPI_STORE: return launch_ss<4, 0, 16, PEPI_STORE>(p, njobs, st);
         case 40160 + PEPI_POOL: return launch_ss<4, 0, 16, PEPI_POOL>(p, njobs, st);

@@ -12,7 +12,7 @@ constexpr int PCHUNK = PBOX * 16;              // bytes of one 4-channel chunk o
 constexpr int PND = 8;                         // accumulator ring: output rows in flight (16 TMEM columns each)
 constexpr int PBROWS = 48;                     // B rows: [W_ky2 | W_ky1 | W_ky0] x 16 output channels (Cout 8 zero-padded)
 constexpr int PTHREADS = 18 * 32;
-enum { PEPI_STORE = 0, PEPI_POOL = 1 };
+enum { PEPI_STORE = 0, PEPI_POOL = 1, PEPI_DOT = 2 };
 
 struct SsJob {
     const uint8_t* wimg;                       // packed weights (conv_ss_pack_layer), device
@@ -21,10 +21,16 @@ struct SsJob {
     float* pool_c4;                            // [COUT/4][H/2][W/2][4] fp32 chunks (PEPI_POOL)
     int a_oy, a_ox, b_oy, b_ox;                // source offsets (the Up block's zero-padded upsampled branch)
     int linear;                                // 1: no ReLU
+    // PEPI_DOT (builtup copy, last layer): 1x1 out-conv slice over the 8 outputs (+ the other stream's partial logits, + bias and
+    // sigmoid when dot_final), planar fp32 [crop_H][crop_W]   (model/popcorn.py:301, 317-320; networks.py:323-330)
+    const float* dotw;                         // [8] weights + [1] bias
+    const float* dot_in; int dot_in_rs;
+    float* dot_out; int dot_out_rs; int dot_final;
 };
 struct alignas(64) SsParams {
     CUtensorMap tmA[PJOBS], tmB[PJOBS];
     int H, W, TR, tiles_x, tiles_y;
+    int crop_y, crop_x, crop_H, crop_W;        // planar / dot outputs go to (y - crop_y, x - crop_x) if inside [0,crop_H) x [0,crop_W); crop_H = 0: no crop
     SsJob jobs[PJOBS];
 };
 

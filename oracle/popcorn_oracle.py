@@ -231,6 +231,52 @@ def train_loss(output: dict, y: Tensor, scale_regularization: float = 0.01, lam_
     return loss * lam_weak
 
 
+def train_loss_terms(output: dict, y: Tensor, scale_regularization: float = 0.01, lam_weak: float = 100.0):
+    """The additive terms of ``train_loss``: one log-L1 term per region of the batch (F.l1_loss averages over the
+    batch, utils/losses.py:24) and the scale regulariser; ``sum(terms) == train_loss`` (tests/test_oracle_golden.py).
+    Test infrastructure: gradients of the separate terms give the natural SCALE of the total gradient.  The per-region
+    terms can cancel (one region over-, one under-predicted: d log(pop)/dW is ~equal for both, the signs differ), so an
+    error relative to the cancelled total measures the conditioning of the batch, not the implementation."""
+    B = y.numel()
+    terms = [(torch.log(output["popcount"][b] + 1) - torch.log(y[b] + 1)).abs() / B * lam_weak for b in range(B)]
+    if output.get("scale") is not None and scale_regularization > 0:
+        terms.append(scale_regularization * output["scale"].float().abs().mean() * lam_weak)
+    return terms
+
+
+def head_grad_terms(sd: Dict[str, Tensor], inputs: dict, y: Tensor, grid=None, **fw):
+    """Oracle gradients of the census train step w.r.t. head.*: (total {name: grad}, [per-term {name: grad}], output).
+    One forward; the terms of train_loss_terms are back-propagated one by one (test infrastructure)."""
+    names = [k for k in sd if k.startswith("head.")]
+    sdg = {k: (v.clone().requires_grad_(True) if k.startswith("head.") else v) for k, v in sd.items()}
+    out = forward(sdg, inputs, sparse=True, grid=grid, **fw)
+    terms = train_loss_terms(out, y)
+    per = []
+    for t in terms:
+        g = torch.autograd.grad(t, [sdg[k] for k in names], retain_graph=True, allow_unused=True)
+        per.append({k: (torch.zeros_like(sdg[k]) if gi is None else gi) for k, gi in zip(names, g)})
+    total = {k: sum(p[k] for p in per) for k in names}
+    return total, per, out
+
+
+def grad_parity_errors(got: Dict[str, Tensor], total: Dict[str, Tensor], per) -> Tuple[float, float]:
+    """(norm-wise, element-wise) error of a gradient set against the oracle's, each normalised by the gradient scale of
+    the loss TERMS: max_k ||got_k - total_k||_F / sum_t ||per_t,k||_F  and  max_k max|got_k - total_k| / max_t max|per_t,k|.
+    Why not the cancelled total: see train_loss_terms.  Why not an element-wise relative error with a small floor: one
+    hidden unit of one pixel whose pre-activation sits within fp32 rounding of the ReLU knee flips its contribution
+    (~1/n of the term scale) between any two fp32 implementations (tools/diag_smoke.py, profiles/r2_smoke_bisect.md)."""
+    e_norm = e_elem = 0.0
+    for k, g in got.items():
+        d = g.detach().double().cpu() - total[k].detach().double()
+        sn = sum(float(p[k].double().norm()) for p in per)
+        se = max(float(p[k].double().abs().max()) for p in per)
+        if sn > 0:
+            e_norm = max(e_norm, float(d.norm()) / sn)
+        if se > 0:
+            e_elem = max(e_elem, float(d.abs().max()) / se)
+    return e_norm, e_elem
+
+
 # --------------------------------------------------------------------------------------
 # Tiling / accumulation / census aggregation
 # (data/PopulationDataset.py:294-334, 656-672, 675-729, 823-852; run_eval.py:83-154)

@@ -1,5 +1,5 @@
-"""GPU: checks of paths that were written after this round's GPU budget was spent (opt-in features, empty ranks).  The file
-sorts last on purpose: with `pytest -x` a surprise here cannot hide the validated parity suites that run before it."""
+"""GPU: balanced row shards, ranks without rows and the upload-once input path of CountryEngine (written at the end of round 1,
+confirmed on a B200 by the round-1 driver run and again in round 2: all five pass)."""
 import pytest
 import torch
 
@@ -8,10 +8,7 @@ from popcorn_b200 import timeseries as ts
 from oracle import popcorn_oracle as po
 from util import build_model, golden_state_dict, max_rel
 
-# Not yet run on hardware: a failure here must be visible (XFAIL in the report) without turning the validated suite red, a pass
-# shows up as XPASS.  Remove the xfail mark once a B200 run has confirmed them.
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="written after round 1's GPU budget was spent; first hardware run pending")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")

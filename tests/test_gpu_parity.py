@@ -9,7 +9,7 @@ import torch
 
 from popcorn_b200 import ops, weights
 from oracle import popcorn_oracle as po
-from util import TOL_PIXEL, TOL_REGION, build_model, golden, golden_state_dict, max_rel
+from util import TOL_GRAD, TOL_PIXEL, TOL_REGION, build_model, golden, golden_state_dict, max_rel
 
 pytestmark = pytest.mark.gpu
 
@@ -73,6 +73,11 @@ def test_single_modality_variants(sd, C):
     assert max_rel(out["popdensemap"], ref["popdensemap"]) < TOL_PIXEL
 
 
+def _kernel_vs_autograd(m, inp, y):
+    import __graft_entry__ as ge
+    return ge._head_backward_vs_autograd(m, inp, y)
+
+
 def test_sparse_train_step_vs_reference_golden(sd):
     g = golden("sparse_train")
     m = build_model(sd).train()
@@ -90,12 +95,101 @@ def test_sparse_train_step_vs_reference_golden(sd):
     assert max_rel(out["popdensemap"], g["popdensemap"]) < TOL_PIXEL
     assert max_rel(out["popcount"], g["popcount"], floor_frac=1.0) < TOL_REGION
     loss = po.train_loss(out, g["y"].cuda())
-    assert abs(float(loss) - float(g["loss"])) < 1e-3 * abs(float(g["loss"]))
+    assert abs(float(loss.detach()) - float(g["loss"])) < 1e-3 * abs(float(g["loss"]))
     loss.backward()
     grads = {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
     assert sorted(grads) == sorted(k[5:] for k in g if k.startswith("grad."))   # only head.* receive gradients
+    # gradient scale = the loss terms' own gradients (po.train_loss_terms: the per-region terms may cancel)
+    total, per, _ = po.head_grad_terms(sd, {"input": g["input"], "admin_mask": g["admin_mask"], "census_idx": g["census_idx"]},
+                                       g["y"], grid=(g["grid_x"], g["grid_y"]), padding=False)
+    for k in grads:                                                              # the oracle reproduces the reference's gradients
+        assert max_rel(total[k], g["grad." + k], floor_frac=1e-2) < 1e-4, k
+    e_norm, e_elem = po.grad_parity_errors(grads, {k: g["grad." + k] for k in grads}, per)
+    assert e_norm < TOL_GRAD and e_elem < 2 * TOL_GRAD, (e_norm, e_elem)
+    assert _kernel_vs_autograd(m, inp, g["y"].cuda()) < 1e-4
+
+
+# (name, boxes of the two regions in a 96x128 batch, census targets): n % 128 = 96 is __graft_entry__.smoke()'s batch
+# (region 0 over-, region 1 under-predicted on the random weights: the two log-L1 gradients nearly cancel), 0 = no tail
+# tile, 36 = the golden's tail length
+_TRAIN_CASES = [("tail96_mixed_sign", [(10, 70, 20, 100), (30, 90, 8, 64)], [2500.0, 9000.0], 96),
+                ("tail0", [(0, 64, 0, 64), (0, 32, 0, 128)], [2500.0, 9000.0], 0),
+                ("tail36", [(10, 71, 20, 104), (30, 90, 8, 64)], [3500.0, 12000.0], 36)]
+
+
+@pytest.mark.parametrize("weights", ["golden", "random1600"])
+@pytest.mark.parametrize("case", _TRAIN_CASES, ids=[c[0] for c in _TRAIN_CASES])
+def test_train_step_scale_and_gradients_vs_oracle(sd, weights, case):
+    """Census train step (run_train.py:201-230, unet_no_grad) on the parity weights AND the benchmark weights: index set
+    bit-exact, scale values, popcount, loss, and all 8 head gradients against the oracle; the backward kernel alone
+    against torch.float64 autograd over the same features."""
+    _, boxes, ys, tail = case
+    w = sd if weights == "golden" else po.random_state_dict(seed=1600)
+    B, H, W = 2, 96, 128
+    x = po.synthetic_input(H, W, seed=3, B=B)
+    admin = torch.zeros(B, H, W)
+    for b, (r0, r1, c0, c1) in enumerate(boxes):
+        admin[b, r0:r1, c0:c1] = float(4 + 5 * b)
+    cidx, y = torch.tensor([4, 9]), torch.tensor(ys)
+    m = build_model(w).train()
+    torch.manual_seed(7)
+    grid = po.sparsity_grid(H, W)
+    torch.manual_seed(7)
+    inp = {"input": x.cuda(), "admin_mask": admin.cuda(), "census_idx": cidx.cuda()}
+    out = m(inp, train=True, padding=False, encoder_no_grad=True, unet_no_grad=True, sparse=True)
+    loss = po.train_loss(out, y.cuda())
+    loss.backward()
+    total, per, ref = po.head_grad_terms(w, {"input": x, "admin_mask": admin, "census_idx": cidx}, y, grid=grid, padding=False)
+    idx, n = m._last_compaction
+    n = int(n.item())
+    assert n % 128 == tail and n == int(ref["mask"].sum())
+    mask = torch.zeros(B * H * W, dtype=torch.bool)
+    mask[idx[:n].long().cpu()] = True
+    assert torch.equal(mask.view(B, H, W), ref["mask"])
+    assert out["scale"].shape == ref["scale"].shape
+    assert max_rel(out["scale"], ref["scale"]) < 1e-4                 # values, in compaction (row-major) order
+    assert max_rel(out["popdensemap"], ref["popdensemap"]) < 1e-4
+    assert max_rel(out["popcount"], ref["popcount"], floor_frac=1.0) < 1e-5
+    assert abs(float(loss.detach()) - float(po.train_loss(ref, y).detach())) < 1e-5 * abs(float(loss.detach()))
+    grads = {k: p.grad for k, p in m.named_parameters() if k.startswith("head.")}
+    e_norm, e_elem = po.grad_parity_errors(grads, total, per)
+    assert e_norm < TOL_GRAD and e_elem < 2 * TOL_GRAD, (e_norm, e_elem)
+    assert _kernel_vs_autograd(m, inp, y.cuda()) < 1e-4
+
+
+def test_train_step_config3_size_gradients(sd):
+    """BASELINE config 3's batch shape (B=2 x 896x960, ~1e6 selected pixels): with this many pixels single ReLU-knee flips
+    are negligible and the plain element-wise relative error (floor 1e-2 of the largest element) meets 1e-3 as well."""
+    B, H, W = 2, 896, 960
+    x = po.synthetic_input(H, W, seed=11, B=B)
+    yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    admin = torch.zeros(B, H, W)
+    admin[0][((yy - 448) / 400.0) ** 2 + ((xx - 480) / 420.0) ** 2 < 1] = 17.0
+    admin[1][((yy - 430) / 380.0) ** 2 + ((xx - 500) / 400.0) ** 2 < 1] = 5.0
+    cidx = torch.tensor([17, 5])
+    m = build_model(sd).train()
+    torch.manual_seed(7)
+    grid = po.sparsity_grid(H, W)
+    with torch.no_grad():
+        ref0 = po.forward(sd, {"input": x, "admin_mask": admin, "census_idx": cidx}, padding=False, sparse=True, grid=grid)
+    y = (ref0["popcount"] * torch.tensor([1.6, 2.3])).float()        # both regions under-predicted: no cancellation
+    torch.manual_seed(7)
+    inp = {"input": x.cuda(), "admin_mask": admin.cuda(), "census_idx": cidx.cuda()}
+    out = m(inp, train=True, padding=False, encoder_no_grad=True, unet_no_grad=True, sparse=True)
+    po.train_loss(out, y.cuda()).backward()
+    total, per, ref = po.head_grad_terms(sd, {"input": x, "admin_mask": admin, "census_idx": cidx}, y, grid=grid, padding=False)
+    assert max_rel(out["popcount"], ref["popcount"], floor_frac=1.0) < 1e-5
+    grads = {k: p.grad for k, p in m.named_parameters() if k.startswith("head.")}
+    e_norm, e_elem = po.grad_parity_errors(grads, total, per)
+    assert e_norm < TOL_GRAD and e_elem < TOL_GRAD, (e_norm, e_elem)
     for k, v in grads.items():
-        assert max_rel(v, g["grad." + k], floor_frac=1e-2) < 1e-2, k
+        assert max_rel(v, total[k], floor_frac=1e-2) < TOL_GRAD, k
+
+
+def test_smoke_entry_point():
+    """__graft_entry__.smoke() is what the driver runs on a fresh B200 at round end: keep it green in every GPU test run."""
+    import __graft_entry__ as ge
+    ge.smoke()
 
 
 def test_backward_is_deterministic(sd):

@@ -42,6 +42,21 @@ def test_sparse_train_step_matches_reference_golden(sd):
         assert max_rel(sdg[k[5:]].grad, g[k], floor_frac=1e-2) < 1e-3, k
 
 
+def test_loss_terms_sum_to_the_loss_and_their_gradients_to_the_reference_gradient(sd):
+    """po.train_loss_terms / head_grad_terms (the gradient-scale helpers of the GPU parity tests): the terms add up to
+    train_loss and their gradients to the gradients the imported reference produced (tests/golden/sparse_train.npz)."""
+    g = golden("sparse_train")
+    inp = {"input": g["input"].clone(), "admin_mask": g["admin_mask"].clone(), "census_idx": g["census_idx"].clone()}
+    total, per, out = po.head_grad_terms(sd, inp, g["y"], grid=(g["grid_x"], g["grid_y"]), padding=False)
+    assert len(per) == g["y"].numel() + 1
+    terms = po.train_loss_terms(out, g["y"])
+    assert abs(float(sum(terms)) - float(po.train_loss(out, g["y"]))) < 1e-5 * abs(float(g["loss"]))
+    for k in [k for k in g if k.startswith("grad.")]:
+        assert max_rel(total[k[5:]], g[k], floor_frac=1e-2) < 1e-3, k
+    e_norm, e_elem = po.grad_parity_errors({k[5:]: g[k] for k in g if k.startswith("grad.")}, total, per)
+    assert e_norm < 1e-5 and e_elem < 1e-5
+
+
 def test_tiled_eval_matches_reference_golden(sd):
     g = golden("tiled_eval")
     ps, ov = int(g["patchsize"]), int(g["overlap"])

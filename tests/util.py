@@ -9,6 +9,7 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 # tolerances of BASELINE.json's north_star
 TOL_PIXEL = 1e-2     # per-pixel density, relative
 TOL_REGION = 1e-3    # region counts, relative
+TOL_GRAD = 1e-3      # head / UNet gradients, relative to the gradient scale of the loss terms (oracle.grad_parity_errors)
 
 
 def golden(name):

@@ -7,7 +7,7 @@ nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I popcorn_b200/csrc
 for variant in 0 1 2 3; do
   for swap in 0 1; do
     echo "=== variant $variant swap_lbo_sbo $swap ==="
-    timeout 60 tools/probe/pair_probe $swap $variant
+    timeout 20 tools/probe/pair_probe $swap $variant
     echo "exit code $?"
   done
 done

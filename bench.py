@@ -89,18 +89,30 @@ def _conv_work(name):
     ca, cb, co, epi = name[name.index("<") + 1:-1].split(",")
     cin, co = int(ca) + int(cb), int(co)
     flop = 2 * 9 * cin * co
-    out_b = {"store": co * 4, "pool": co * 4 + co, "dot": 4 + 4}[epi]
+    # convt: the Up block's ConvTranspose2d 2x2 rides in the epilogue: 4 output pixels x co channels written per input pixel
+    out_b = {"store": co * 4, "pool": co * 4 + co, "dot": 4 + 4, "convt": 4 * co * 4}[epi]
+    if epi == "convt":
+        flop += 2 * 4 * co * co
     return flop, cin * 4 + out_b
 
 
-# dram bytes per processed pixel measured by `ncu --set full` (profiles/r1_hot_kernels.md); None = not captured
-NCU_TRAFFIC_PER_PX = {"head_tc<dense>": (285.33 + 28.78) / 4.194, "conv3x3_tc<8,8,8,store>": (540.59 + 240.97) / 8.389,
-                      "conv3x3_tc<8,0,8,store>": (268.74 + 224.13) / 8.389, "conv3x3_tc<8,0,8,pool>": (278.07 + 297.78) / 8.389,
-                      "conv3x3_tc<16,16,8,store>": (278.14 + 52.58) / 2.097, "conv3x3_tc<16,0,16,pool>": (137.48 + 116.45) / 2.097,
-                      "conv3x3_tc<8,0,16,store>": (67.52 + 80.30) / 2.097}
+FLOP_PER_SEL_PX_HEAD_BWD = 2 * (9280 + 8256 + 9280)   # recomputed forward + dgrad (64x64 x2 + 64) + wgrad, per selected pixel
 
 
-def kernel_table(prof, ms_total, hbm_peak, tensor_peak):
+def ncu_traffic_per_px():
+    """dram__bytes_read.sum + dram__bytes_write.sum per processed pixel and kernel, from the committed `ncu --set full` capture of
+    THIS command's launches (profiles/r2_ncu_bench_traffic.json, written by tools/ncu_traffic.py from the ncu CSV); {} if absent."""
+    p = os.path.join(ROOT, "profiles", "r2_ncu_bench_traffic.json")
+    try:
+        return {k: v["dram_bytes_per_px"] for k, v in json.load(open(p))["kernels"].items()}
+    except Exception:
+        return {}
+
+
+def kernel_table(prof, ms_total, hbm_peak, tensor_peak, fp32_peak=None, frac_multi=0.0, maps=4):
+    """prof = {name: (ms, launches, units)} from ops.profile_results().  `bound`: "hbm" | "tensor" as in the contract, plus "fp32" for the
+    kernels whose ceiling is the FP32 FFMA2 pipe (measured by pc_test_fma_peak), which is neither."""
+    traffic_px = ncu_traffic_per_px()
     rows = []
     for name, (ms, n, units) in prof.items():
         if ms <= 0:
@@ -112,8 +124,7 @@ def kernel_table(prof, ms_total, hbm_peak, tensor_peak):
                     f"{tensor_peak / 6:.0f} TFLOP/s): the layer moves (Cin+Cout)*4 B per pixel and is HBM-bound")
         elif name.startswith("conv3x3<"):
             flop, byts = _conv_work(name)
-            bound, note = "hbm" if flop / byts < 11 else "tensor", "fp32 FFMA2 stencil (first layer: reflect padding + channel remap, Cin 2|4); " \
-                "compare `tflops` with fp32_simt.peak_tflops_measured_ffma2"
+            bound, note = "hbm", "fp32 FFMA2 stencil (first layer: reflect padding + channel remap, Cin 2|4): 12-48 B and 144-288 MAC per pixel"
         elif name.startswith("convt2x2<"):
             c = int(name[len("convt2x2<"):-1])
             flop, byts, bound, note = 8 * c * c, 5 * c * 4, "hbm", "units = low-res pixels"
@@ -121,15 +132,21 @@ def kernel_table(prof, ms_total, hbm_peak, tensor_peak):
             flop, byts, bound = FLOP_PER_PX_HEAD, BYTES_PER_PX_HEAD, "tensor"
             note = "tcgen05 kind::tf32 with 3xTF32 splitting: 3 MMAs per algorithmic MAC at half the bf16 rate -> ceiling = peak/6"
         elif name.startswith("head_forward_simt"):
-            flop, byts, bound, note = FLOP_PER_PX_HEAD, BYTES_PER_PX_HEAD, "tensor", "fp32 SIMT head"
+            flop, byts, bound, note = FLOP_PER_PX_HEAD, BYTES_PER_PX_HEAD, "fp32", "fp32 SIMT head"
+        elif name == "head_backward":
+            flop, byts, bound = FLOP_PER_SEL_PX_HEAD_BWD, 64 + 4 + 4 + 4, "fp32"
+            note = "units = selected pixels; forward recomputed in shared memory + dgrad + wgrad on the FP32 pipe (csrc/head_bwd.cu)"
+        elif name.startswith("compact_") or name == "sparse_mask_compact":
+            flop, byts, bound, note = 2, 9, "hbm", "mask = (builtup>0)&(admin==idx)|grid, row-major compaction: 9 B/px + 4 B per selected"
         elif name == "ingest_normalize":
             flop, byts, bound, note = 12, 16 + 24, "hbm", "uint16 S2 x4 + float32 S1 x2 read, 6 fp32 planes written"
         elif name == "region_sum":
             flop, byts, bound, note = 1, 8, "hbm", "dens + id read once"
         elif name == "accumulate":
-            flop, byts, bound, note = 4, 8 + 4 * 8 + 4, "hbm", "tile dens+scale read, 4 maps + count read-modify-write"
+            flop, byts, bound, note = 4, 8 + maps * 8 + 4, "hbm", f"tile dens+scale read, {maps} maps + count read-modify-write"
         elif name == "finalize":
-            flop, byts, bound, note = 10, 4 * 8 + 2, "hbm", "4 maps read+write, count read"
+            flop, byts, bound = 10, 2 + maps * 8 * frac_multi, "hbm"
+            note = f"int16 count read for every pixel; {maps} maps read+written only where count > 1 ({100 * frac_multi:.1f} % of the pixels here)"
         else:
             flop, byts, bound, note = 0, 0, "hbm", ""
         sec = ms * 1e-3
@@ -137,18 +154,52 @@ def kernel_table(prof, ms_total, hbm_peak, tensor_peak):
         gbs = byts * units / sec / 1e9
         if bound == "hbm":
             ach, peak, unit = gbs, hbm_peak, "GB/s"
+        elif bound == "fp32":
+            ach, peak, unit = tfl, fp32_peak, "TFLOP/s"
         else:
             ach, peak, unit = tfl, tensor_peak, "TFLOP/s"
-        tpp = NCU_TRAFFIC_PER_PX.get(name)
+        tpp = traffic_px.get(name)
         rows.append({"kernel": name, "ms": ms, "launches": n, "pixels": units, "share_of_step": ms / ms_total if ms_total else None,
                      "tflops": tfl, "gbs": gbs, "bound": bound, "achieved": ach, "peak": peak, "unit": unit,
-                     "frac": ach / peak if peak else None,
+                     "frac": ach / peak if peak else None, "algorithmic_bytes": byts * units / n,
                      "traffic": None if tpp is None else tpp * units / n, "note": note})
         if name.startswith("head_tc"):   # fp32-accurate tensor-core arithmetic costs 3 tf32 MMAs (= 6 bf16-rate slots) per MAC
             rows[-1]["ceiling_3xtf32"] = tensor_peak / 6
             rows[-1]["frac_of_3xtf32_ceiling"] = tfl / (tensor_peak / 6) if tensor_peak else None
     rows.sort(key=lambda r: -r["ms"])
     return rows
+
+
+def roofline_of(kernels, peak_src):
+    dom = max(kernels, key=lambda k: k["ms"]) if kernels else None
+    if dom is None:
+        return None
+    r = {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"], "unit": dom["unit"],
+         "frac": dom["frac"], "traffic": dom.get("traffic"), "algorithmic_bytes": dom.get("algorithmic_bytes"),
+         "traffic_source": "ncu --set full capture of this command's launches (profiles/r2_ncu_bench_traffic.json)" if dom.get("traffic") else None,
+         "launches": dom["launches"], "avg_launch_ms": dom["ms"] / dom["launches"], "share_of_step": dom["share_of_step"],
+         "note": dom["note"], "peak_source": peak_src}
+    for k in ("ceiling_3xtf32", "frac_of_3xtf32_ceiling"):
+        if k in dom:
+            r[k] = dom[k]
+    return r
+
+
+def measure_fp32_peak(dev):
+    """Register-resident FFMA2 loop (pc_test_fma_peak): the practical ceiling of the FP32 pipe, TFLOP/s."""
+    from popcorn_b200 import _lib
+    o = torch.zeros(4, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    iters = 4096
+    for _ in range(2):
+        nthr = _lib.lib().pc_test_fma_peak(1, iters, 8, o.data_ptr(), st)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    nthr = _lib.lib().pc_test_fma_peak(1, iters, 8, o.data_ptr(), st)
+    b.record()
+    torch.cuda.synchronize()
+    return 2 * 32 * iters * nthr / (a.elapsed_time(b) * 1e-3) / 1e12
+
 
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
@@ -208,21 +259,70 @@ def measured_peaks():
 # ---------------------------------------------------------------------------------------------------
 # CPU baseline = the oracle port of the reference algorithm on the host cores (bounded sample)
 # ---------------------------------------------------------------------------------------------------
-def cpu_reference_tiles(n_tiles: int, sd=None):
-    """Runs n_tiles reference-sized (2048^2) tiles through the oracle + census sums; returns (seconds, unique px)."""
+def bench_weights():
+    """BASELINE config 1's weight recipe: `unetmodel` re-initialised by the reference's own init code at seed 1600 (kaiming fan_out, BN
+    gamma 1 / beta 0, running stats of the checkpoint), default-init head with bias 0.9407, `building_extractor` = the pretrained DDA
+    checkpoint.  That state_dict was produced by the UNMODIFIED reference (oracle/make_golden.py) and is committed as a fixture
+    (tests/golden/state_dict.npz, 324 keys); without it (stripped checkout) the synthetic generator of popcorn_b200.synthetic is used."""
+    p = os.path.join(ROOT, "tests", "golden", "state_dict.npz")
+    if os.path.isfile(p) and os.environ.get("POPCORN_BENCH_WEIGHTS", "reference") != "synthetic":
+        import numpy as np
+        return {k: torch.from_numpy(np.asarray(v)) for k, v in np.load(p).items()}, \
+            "config-1 recipe from the unmodified reference (tests/golden/state_dict.npz: pretrained DDA checkpoint in building_extractor, " \
+            "reference re-init of unetmodel + head at seed 1600)"
+    from popcorn_b200 import synthetic as sy
+    return sy.random_state_dict(seed=1600), "random-init DDA x2 + head (popcorn_b200.synthetic.random_state_dict seed 1600)"
+
+
+def cpu_reference_tiles(n_tiles: int, sd=None, keep=None):
+    """Runs n_tiles reference-sized (2048^2) tiles through the oracle + census sums; returns (seconds, unique px).
+    keep: optional dict that receives tile 0's input, centre density and region sums (for the GPU-vs-oracle check of the bench)."""
     from oracle import popcorn_oracle as po
     torch.set_num_threads(os.cpu_count() or 1)
-    sd = sd or po.random_state_dict(seed=1600)
+    sd = sd or bench_weights()[0]
     ids = po.synthetic_regions(2048, 2048, 40)
     xs = [po.synthetic_input(2048, 2048, seed=1610 + i) for i in range(n_tiles)]   # untimed: data generation
     t0 = time.perf_counter()
-    for x in xs:
+    for i, x in enumerate(xs):
         with torch.no_grad():
             out = po.forward(sd, {"input": x}, padding=False)
         centre = out["popdensemap"][0][128:-128, 128:-128]
-        po.region_sums(centre, ids[128:-128, 128:-128], 41)
+        sums = po.region_sums(centre, ids[128:-128, 128:-128], 41)
+        if keep is not None and i == 0:
+            keep.update(x=x, centre=centre.clone(), sums=sums.clone(), ids=ids)
     dt = time.perf_counter() - t0
     return dt, n_tiles * 1792 * 1792
+
+
+def gpu_reference_tiles(n_tiles: int, sd, dev, tf32: bool):
+    """The SAME oracle restatement (the ATen/cuDNN ops the reference model executes) on this GPU through stock PyTorch: the honest
+    "before" of SURVEY.md §8(d).  fp32 with TF32 off is the reference's own setting (utils/utils.py:57-58 never enables TF32)."""
+    from oracle import popcorn_oracle as po
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.allow_tf32 = tf32
+    torch.backends.cuda.matmul.allow_tf32 = tf32
+    torch.backends.cudnn.benchmark = True
+    try:
+        sdd = {k: v.to(dev) for k, v in sd.items()}
+        ids = po.synthetic_regions(2048, 2048, 40).to(dev)
+        x = po.synthetic_input(2048, 2048, seed=1610).to(dev)
+
+        def one():
+            with torch.no_grad():
+                out = po.forward(sdd, {"input": x}, padding=False)
+                centre = out["popdensemap"][0][128:-128, 128:-128]
+                return torch.zeros(41, dtype=torch.float64, device=dev).index_add_(
+                    0, ids[128:-128, 128:-128].reshape(-1).long(), centre.reshape(-1).double())
+        for _ in range(2):
+            one()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n_tiles):
+            one()
+        torch.cuda.synchronize()
+        return n_tiles * 1792 * 1792 / (time.perf_counter() - t0)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
 
 
 def run_reference_arm(args):
@@ -230,8 +330,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     H, W, name = workload(args.gpus)
-    from oracle import popcorn_oracle as po
-    sd = po.random_state_dict(seed=1600)
+    sd, wname = bench_weights()
     torch.set_num_threads(os.cpu_count() or 1)
     # warm-up is bounded to one tile: every further warm-up tile costs seconds of host time and changes nothing
     for _ in range(min(args.warmup, 1)):
@@ -249,16 +348,14 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / max(args.steps, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": name, "sampled": sample},
+            "config": {"workload": name, "sampled": sample, "weights": wname},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------
-def train_step_ms(model, device, iters: int = 5):
-    """BASELINE config 3: census-supervised step B=2, 896x960, sparse head, log-L1 loss, clip 0.01, Adam (run_train.py)."""
-    from popcorn_b200 import synthetic as sy
+def _train_batch(device):
     B, H, W = 2, 896, 960
     x = synth_raster_slab(B * H, W, 12345, device).view(6, B, H, W).permute(1, 0, 2, 3).contiguous()
     yy, xx = torch.meshgrid(torch.arange(H, device=device), torch.arange(W, device=device), indexing="ij")
@@ -267,14 +364,63 @@ def train_step_ms(model, device, iters: int = 5):
     admin[1][((yy - 430) / 380.0) ** 2 + ((xx - 500) / 400.0) ** 2 < 1] = 5.0
     cidx = torch.tensor([17, 5], device=device)
     y = torch.tensor([3500.0, 12000.0], device=device)
+    return x, admin, cidx, y
+
+
+def oracle_train_step_ms(sd, batch, device, iters: int, tf32: bool = False):
+    """The reference algorithm's census train step (run_train.py:201-238 with unet_no_grad: two frozen DDA passes, sparse head, log-L1
+    + scale regulariser, backward, clip 0.01, Adam) as stock PyTorch autograd through the oracle restatement, on `device` (cpu | cuda)."""
+    from oracle import popcorn_oracle as po
+    x, admin, cidx, y = (t.to(device) for t in batch)
+    sdd = {k: v.to(device) for k, v in sd.items()}
+    params = [sdd[k].requires_grad_(True) for k in sdd if k.startswith("head.")]
+    opt = torch.optim.Adam(params, lr=1e-4)
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = tf32
+    torch.backends.cuda.matmul.allow_tf32 = tf32
+    times = []
+    try:
+        for it in range(iters + 1):
+            if x.is_cuda:
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            out = po.forward(sdd, {"input": x, "admin_mask": admin, "census_idx": cidx}, padding=False, sparse=True, unet_no_grad=True)
+            po.train_loss(out, y).backward()
+            torch.nn.utils.clip_grad_norm_(params, 0.01)
+            opt.step()
+            opt.zero_grad()
+            if x.is_cuda:
+                torch.cuda.synchronize()
+            if it >= 1:
+                times.append(1e3 * (time.perf_counter() - t0))
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    return sorted(times)[len(times) // 2]
+
+
+def train_step_section(model, sd, device, peaks, fp32_peak, cpu_baseline: bool, iters: int = 5):
+    """BASELINE config 3 / metric (ii): census-supervised step B=2, 896x960, sparse head, log-L1 loss, clip 0.01, Adam (run_train.py),
+    with its own per-kernel table, roofline (dominant kernel of the step), CPU baseline and stock-PyTorch GPU baseline."""
+    from popcorn_b200 import ops
+    from popcorn_b200 import synthetic as sy
+    hbm_peak, bf16_peak, bf16_sust, peak_src = peaks
+    batch = _train_batch(device)
+    x, admin, cidx, y = batch
+    B, _, H, W = x.shape
     model.train()
     params = [p for n, p in model.named_parameters() if n.startswith("head.")]
     opt = torch.optim.Adam(params, lr=1e-4)
     times = []
     n_sel = 0
-    for it in range(iters + 2):
+    prof, ev_ms = {}, 0.0
+    for it in range(iters + 3):
+        profiled = it == iters + 2          # the last iteration runs with the per-launch CUDA events on (not part of the median)
+        if profiled:
+            ops.profile_enable(True)
         torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
+        e0.record()
         inp = {"input": x, "admin_mask": admin, "census_idx": cidx}
         out = model(inp, train=True, padding=False, encoder_no_grad=True, unet_no_grad=True, sparse=True)
         loss = sy.census_loss(out, y)
@@ -282,12 +428,37 @@ def train_step_ms(model, device, iters: int = 5):
         torch.nn.utils.clip_grad_norm_(params, 0.01)
         opt.step()
         opt.zero_grad()
+        e1.record()
         torch.cuda.synchronize()
-        if it >= 2:
+        if profiled:
+            ops.profile_enable(False)
+            prof, ev_ms = ops.profile_results(), e0.elapsed_time(e1)
+        elif it >= 2:
             times.append(1e3 * (time.perf_counter() - t0))
         n_sel = int(out["scale"].numel())
-    res = {"ms": sorted(times)[len(times) // 2], "config": f"B=2 x 896x960, sparse head on {n_sel} px, unet_no_grad, log-L1 + scale reg, clip 0.01, Adam",
-           "includes": "2 frozen DDA passes + mask compaction + sparse head fwd + loss + head bwd + clip + Adam"}
+    ms = sorted(times)[len(times) // 2]
+    kernels = kernel_table(prof, ev_ms, hbm_peak, bf16_sust, fp32_peak)
+    res = {"metric": "census_train_step_ms", "value": ms, "ms": ms, "unit": "ms", "higher_is_better": False,
+           "config": f"B=2 x {H}x{W}, sparse head on {n_sel} px, unet_no_grad, log-L1 + scale reg, clip 0.01, Adam",
+           "includes": "2 frozen DDA passes + mask compaction + sparse head fwd + loss + head bwd + clip + Adam (host-timed, one sync per step "
+                       "as in the reference's n = mask.sum())",
+           "px_per_step": B * H * W, "selected_px": n_sel, "kernels": kernels, "roofline": roofline_of(kernels, peak_src),
+           "kernel_ms_sum": sum(k["ms"] for k in kernels), "profiled_step_ms": ev_ms}
+    try:   # stock PyTorch / cuDNN on this GPU (fp32, TF32 off = the reference's setting; TF32 on for information)
+        g32 = oracle_train_step_ms(sd, batch, device, 3, tf32=False)
+        gtf = oracle_train_step_ms(sd, batch, device, 3, tf32=True)
+        res["gpu_baseline"] = {"ms": g32, "ms_tf32": gtf, "kind": "port", "speedup_over_fp32": g32 / ms,
+                               "what": "oracle restatement of the reference step as stock PyTorch autograd / cuDNN on the same B200"}
+    except Exception as ex:
+        res["gpu_baseline"] = {"error": repr(ex)[:200]}
+    if cpu_baseline:
+        try:
+            torch.set_num_threads(os.cpu_count() or 1)
+            c = oracle_train_step_ms(sd, batch, "cpu", 2)
+            res["cpu_baseline"] = {"value": c, "unit": "ms", "cores": torch.get_num_threads(), "kind": "port",
+                                   "sample": "the full step (B=2 x 896x960), median of 2 after 1 warm-up, oracle port on all host threads"}
+        except Exception as ex:
+            res["cpu_baseline"] = {"error": repr(ex)[:200]}
     # the reference's default for batches < 9 M px: unetmodel is fine-tuned as well (run_train.py:191-202)
     try:
         params_ft = [p for n, p in model.named_parameters() if n.startswith("head.") or n.startswith("unetmodel.")]
@@ -307,9 +478,9 @@ def train_step_ms(model, device, iters: int = 5):
                 ft.append(1e3 * (time.perf_counter() - t0))
         res["finetune_ms"] = sorted(ft)[len(ft) // 2]
         res["finetune_includes"] = "builtup pass + layer-by-layer unetmodel forward (activations kept) + sparse head fwd/bwd + full UNet backward + clip + Adam"
-        model.load_state_dict(sy.random_state_dict(seed=1600))      # undo the updates: the timed inference uses the benchmark weights
     except Exception as ex:
         res["finetune_error"] = repr(ex)[:200]
+    model.load_state_dict(sd)      # undo the updates: everything after this uses the benchmark weights again
     model.eval()
     return res
 
@@ -326,11 +497,14 @@ def main():
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-train", action="store_true")
     ap.add_argument("--skip-timeseries", action="store_true")
-    ap.add_argument("--timeseries-multi", action="store_true", help="also run the time-series section when world > 1")
-    ap.add_argument("--balance", action="store_true",
-                    help="N>1: shard the main grid at 256-row granularity (country.plan_balanced_shards) instead of whole strips")
-    ap.add_argument("--upload-once", action="store_true",
-                    help="e2e: copy every raw input row to the device once (CountryEngine(upload_once=True)) instead of per window")
+    ap.add_argument("--no-balance", action="store_true",
+                    help="N>1: shard whole row strips instead of 256-row units (country.plan_balanced_shards is the default)")
+    ap.add_argument("--per-window-upload", action="store_true",
+                    help="e2e: upload every window separately (halo rows cross PCIe twice) instead of each raw row once")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not bind the rank to its GPU's NUMA node")
+    ap.add_argument("--skip-ensemble", action="store_true")
+    ap.add_argument("--skip-gpu-baseline", action="store_true")
+    ap.add_argument("--skip-alone", action="store_true", help="N>1: skip the one-rank-alone run of rank 0's slab")
     ap.add_argument("--height", type=int, default=0, help="override raster rows (debug)")
     ap.add_argument("--width", type=int, default=0, help="override raster cols (debug)")
     args = ap.parse_args()
@@ -354,21 +528,25 @@ def main():
 
     import popcorn_b200 as pb
     from popcorn_b200 import country as ct
-    from popcorn_b200 import ops
-    from popcorn_b200 import synthetic as sy   # benchmark weights; the oracle is imported by the cpu_baseline leg only
+    from popcorn_b200 import numa, ops
+
+    # host threads (and the pinned staging buffers they first-touch) on the NUMA node of this rank's GPU
+    numa_info = numa.bind_to_gpu_node(local) if not args.no_numa_bind else {"bound": False}
 
     H, W, name = workload(world)
     if args.height and args.width:
         H, W, name = args.height, args.width, f"debug_{args.height}x{args.width}"
-    sd = sy.random_state_dict(seed=1600)
+    sd, weights_name = bench_weights()
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         model = pb.POPCORN(6, occupancymodel=True, pretrained=False, biasinit=0.9407, sentinelbuildings=True, device=dev)
     model.load_state_dict(sd)
     model.eval()
 
+    balance = not args.no_balance
+    upload_once = not args.per_window_upload
     eng = ct.CountryEngine([model], H, W, merge=not args.no_merge, rows_per_strip=args.rows_per_strip, rank=rank, world=world,
-                           first_strip_rows=1, balance=args.balance, upload_once=args.upload_once)     # short first strip: a streamed run starts computing after a small upload
+                           first_strip_rows=1, balance=balance, upload_once=upload_once)     # short first strip: a streamed run starts computing after a small upload
     i0, i1 = eng.in_rows
     lo, hi = eng.out_rows
     raster = synth_raster_slab(i1 - i0, W, i0, dev)
@@ -411,21 +589,31 @@ def main():
     if world > 1:
         dist.all_reduce(mt)
     map_total = float(mt.item())
+    frac_multi = float((out["count"] > 1).float().mean().item()) if out["count"].numel() else 0.0
 
-    hbm_peak, bf16_peak, bf16_sust, peak_src = measured_peaks()
-    kernels = kernel_table(prof, ms_total, hbm_peak, bf16_sust)
-    dom = max(kernels, key=lambda k: k["ms"]) if kernels else None
-    roofline = None
-    if dom is not None:
-        roofline = {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"],
-                    "unit": dom["unit"], "frac": dom["frac"], "traffic": dom.get("traffic"),
-                    "launches": dom["launches"], "avg_launch_ms": dom["ms"] / dom["launches"],
-                    "share_of_step": dom["share_of_step"], "note": dom["note"], "peak_source": peak_src}
-        for k in ("ceiling_3xtf32", "frac_of_3xtf32_ceiling"):
-            if k in dom:
-                roofline[k] = dom[k]
-    head = next((k for k in kernels if k["kernel"].startswith("head_")), None)
-    head_tflops = head["tflops"] if head else 0.0
+    peaks = measured_peaks()
+    hbm_peak, bf16_peak, bf16_sust, peak_src = peaks
+    fp32_peak = measure_fp32_peak(dev)
+    kernels = kernel_table(prof, ms_total, hbm_peak, bf16_sust, fp32_peak, frac_multi)
+    roofline = roofline_of(kernels, peak_src)
+
+    # ---- N > 1: the same per-GPU slab on ONE rank alone (the other ranks idle at the barrier): the apples-to-apples N = 1 point of
+    #      the weak-scaling series (the N = 1 line of the contract is the Rwanda-shaped raster, another shape)
+    alone = None
+    if world > 1 and not args.skip_alone:
+        barrier()
+        if rank == 0:
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(2):
+                with torch.no_grad():
+                    eng.run(raster, ids, R, row_offset=i0, reduce=False)
+            a1.record()
+            torch.cuda.synchronize()
+            px_rank = (hi - lo) * W
+            alone = {"ms": a0.elapsed_time(a1) / 2, "px": px_rank, "value": px_rank / (a0.elapsed_time(a1) / 2 * 1e-3),
+                     "note": "rank 0's slab with the other ranks idle, no collective: per-GPU rate without neighbours"}
+        barrier()
 
     # ---- end-to-end: pinned host raster in, pinned host map + sums out, copies inside the timed region ----
     e2e = None
@@ -473,64 +661,134 @@ def main():
         e2e = {"value": H * W / (float(tt.item()) / k_e2e), "unit": UNIT, "h2d_bytes_per_step": int(h2d.item()),
                "d2h_bytes_per_step": int(d2h.item()), "steps": k_e2e,
                "api": "popcorn_b200.country.CountryEngine.run(RawRaster(pinned uint16 S2 + float32 S1), map_out=pinned host map) + sums.cpu()",
-               "upload": "once_per_row" if args.upload_once else "per_window",
+               "upload": "once_per_row" if upload_once else "per_window", "numa": numa_info,
                "host_input": "raw on-disk dtypes: S2 uint16 x4 (file band order) + S1 float32 x2 = 16 B/px; converted + normalised on the device"}
+        del host_raster, host_s2, host_s1, host_map
+    else:
+        del raster
+    torch.cuda.empty_cache()
 
     train = None
     cpu_base = None
+    gpu_base = None
     fp32 = None
+    check = {"sum_of_region_sums": sums_check, "map_total": map_total}
+    ens = None
     if rank == 0:
         if not args.skip_train:
             try:
-                train = train_step_ms(model, dev)
+                train = train_step_section(model, sd, dev, peaks, fp32_peak, cpu_baseline=(world == 1 and not args.skip_cpu_baseline))
             except Exception as ex:   # the headline metric must still be printed
-                train = {"error": repr(ex)[:200]}
-        # measured FP32 SIMT ceiling (packed FFMA2), the practical bound of the stencil + SIMT head kernels
-        from popcorn_b200 import _lib
-        o = torch.zeros(4, device=dev)
-        st = torch.cuda.current_stream().cuda_stream
-        iters = 4096
-        for _ in range(2):
-            nthr = _lib.lib().pc_test_fma_peak(1, iters, 8, o.data_ptr(), st)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        nthr = _lib.lib().pc_test_fma_peak(1, iters, 8, o.data_ptr(), st)
-        b.record()
-        torch.cuda.synchronize()
-        fp32_peak = 2 * 32 * iters * nthr / (a.elapsed_time(b) * 1e-3) / 1e12
+                train = {"error": repr(ex)[:300]}
         conv_ms = sum(k["ms"] for k in kernels if k["kernel"].startswith("conv3x3<"))
         conv_fl = sum(k["tflops"] * k["ms"] for k in kernels if k["kernel"].startswith("conv3x3<"))
         tc_ms = sum(k["ms"] for k in kernels if k["kernel"].startswith("conv3x3_tc<"))
         tc_fl = sum(k["tflops"] * k["ms"] for k in kernels if k["kernel"].startswith("conv3x3_tc<"))
         tc_gb = sum(k["gbs"] * k["ms"] for k in kernels if k["kernel"].startswith("conv3x3_tc<"))
+        alg_b = sum(k["algorithmic_bytes"] * k["launches"] for k in kernels)
+        trf = [k for k in kernels if k.get("traffic")]
         fp32 = {"peak_tflops_measured_ffma2": fp32_peak,
                 "conv3x3_all_tflops": conv_fl / conv_ms if conv_ms else None,
                 "conv3x3_all_frac_of_fp32_peak": conv_fl / conv_ms / fp32_peak if conv_ms and fp32_peak else None,
                 "note": "register-resident FFMA2 loop (pc_test_fma_peak): the practical ceiling of the fp32 stencil kernels",
                 "conv3x3_tc_all_tflops_algorithmic": tc_fl / tc_ms if tc_ms else None,
                 "conv3x3_tc_all_gbs_algorithmic": tc_gb / tc_ms if tc_ms else None,
-                "conv3x3_tc_all_frac_of_hbm_peak": tc_gb / tc_ms / hbm_peak if tc_ms else None}
+                "conv3x3_tc_all_frac_of_hbm_peak": tc_gb / tc_ms / hbm_peak if tc_ms else None,
+                "path_bytes_per_unique_px_kernel_sum": alg_b / args.steps / (H * W / world) if kernels else None,
+                "path_dram_bytes_per_unique_px_ncu": (sum(k["traffic"] * k["launches"] for k in trf) / args.steps / (H * W / world)) if trf else None}
+        if world == 1 and not args.skip_gpu_baseline:
+            # stock PyTorch / cuDNN on this very GPU: the honest "before" (SURVEY.md §8d), fp32 with TF32 off (the reference's setting) and on
+            try:
+                g32 = gpu_reference_tiles(3, sd, dev, tf32=False)
+                gtf = gpu_reference_tiles(3, sd, dev, tf32=True)
+                gpu_base = {"value": g32, "value_tf32": gtf, "unit": UNIT, "kind": "port", "speedup_over_fp32": value / g32,
+                            "speedup_over_tf32": value / gtf,
+                            "sample": "3 reference tiles of 2048x2048 (oracle restatement = the reference's ATen/cuDNN ops, stock PyTorch "
+                                      f"{torch.__version__}) + census sums on the same B200; unique px = centre 1792^2 per tile"}
+            except Exception as ex:
+                gpu_base = {"error": repr(ex)[:200]}
+            torch.cuda.empty_cache()
         if world == 1 and not args.skip_cpu_baseline:
-            dt, px = cpu_reference_tiles(4)
+            keep = {}
+            dt, px = cpu_reference_tiles(4, sd, keep)
             cpu_base = {"value": px / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                         "sample": "4 reference tiles of 2048x2048 (oracle port of POPCORN.forward, fp32, all host threads) "
                                   "+ census sums; unique px = centre 1792^2 per tile"}
+            # parity at bench size: the same 2048^2 tile through the product path (model API -> C-ABI), centre against the oracle's
+            try:
+                with torch.no_grad():
+                    o = model({"input": keep["x"].to(dev)}, padding=False)
+                    cg = o["popdensemap"][0][128:-128, 128:-128].contiguous()
+                    sg = ops.region_sum(cg, keep["ids"][128:-128, 128:-128].contiguous().to(dev), 41).cpu()
+                ref = keep["centre"].double()
+                err = ((cg.cpu().double() - ref).abs() / torch.clamp(ref.abs(), min=1e-3 * float(ref.abs().max()))).max()
+                nz = keep["sums"].abs() > 0
+                serr = ((sg - keep["sums"]).abs()[nz] / keep["sums"].abs()[nz]).max()
+                check.update(tile2048_density_max_rel=float(err), tile2048_region_sum_max_rel=float(serr),
+                             tile2048_ok=bool(err < 1e-2 and serr < 1e-3),
+                             tile2048_note="one 2048^2 tile of the cpu_baseline leg re-run through popcorn_b200 on the GPU; bars 1e-2 / 1e-3")
+            except Exception as ex:
+                check["tile2048_error"] = repr(ex)[:200]
+            del keep
 
-    # ---- BASELINE configs[4]: multi-temporal inference, 4 seasonal frames of a Switzerland-shaped raster (rows sharded) ----
+    # ---- 5-member ensemble (run_eval.py:108-115; README: seeds 1600-1604): members share the builtup pass ----
+    if world == 1 and not args.skip_ensemble:
+        try:
+            members = [model]
+            for k in range(1, 5):
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    mk = pb.POPCORN(6, occupancymodel=True, pretrained=False, biasinit=0.9407, sentinelbuildings=True, device=dev)
+                sdk = dict(sd)
+                g = torch.Generator().manual_seed(1600 + k)       # fine-tuned parts differ per member; building_extractor is shared
+                for key, v in sd.items():
+                    if (key.startswith("unetmodel.") or key.startswith("head.")) and v.is_floating_point() and "running" not in key:
+                        sdk[key] = v * (1.0 + 0.05 * torch.randn(v.shape, generator=g))
+                mk.load_state_dict(sdk)
+                members.append(mk.eval())
+            He, We = 2048 + 2 * 1792, W                     # three tile-rows of the Rwanda-shaped raster
+            res_e = {}
+            xe = synth_raster_slab(He, We, 777, dev)
+            for tag, mods, share in (("one_member", members[:1], True), ("five_members", members, True), ("five_members_unshared", members, False)):
+                e5 = ct.CountryEngine(mods, He, We, merge=not args.no_merge, rows_per_strip=args.rows_per_strip)
+                if not share:
+                    e5._bext_shared = False
+                with torch.no_grad():
+                    e5.run(xe, None, 1)
+                    torch.cuda.synchronize()
+                    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a0.record()
+                    for _ in range(2):
+                        e5.run(xe, None, 1)
+                    a1.record()
+                    torch.cuda.synchronize()
+                res_e[tag] = a0.elapsed_time(a1) / 2
+                res_e[tag + "_shared_builtup"] = bool(e5._bext_shared)
+                del e5
+            ens = {"raster": f"{He}x{We}", "ms_one_member": res_e["one_member"], "ms_five_members": res_e["five_members"],
+                   "ms_five_members_unshared_builtup": res_e["five_members_unshared"],
+                   "builtup_shared": res_e["five_members_shared_builtup"],
+                   "value": He * We / (res_e["five_members"] * 1e-3), "unit": "pixels/s (5-member ensemble mean + std maps)",
+                   "saving_from_sharing": 1.0 - res_e["five_members"] / res_e["five_members_unshared"],
+                   "note": "N2: building_extractor never trains, so the ensemble's members carry identical copies -> one builtup pass per window"}
+            del xe, members
+            torch.cuda.empty_cache()
+        except Exception as ex:
+            ens = {"error": repr(ex)[:300]}
+
+    # ---- BASELINE configs[4]: multi-temporal inference, 4 seasonal frames of a Switzerland-shaped raster, frames x row shards ----
     tseries = None
-    # Single-GPU by default: with more ranks than row strips some ranks own no rows, and this section is an extra to the
-    # headline metric — it must never be able to stall the ranks of a scaling run (--timeseries-multi opts in).
-    if not args.skip_timeseries and (world == 1 or args.timeseries_multi):
+    if not args.skip_timeseries:
         try:
             from popcorn_b200 import timeseries as tsm
             Hs, Ws, T = 13408, 30592, 4
             torch.cuda.empty_cache()
-            tse = tsm.TimeSeriesEngine([model], Hs, Ws, rank=rank, world=world, merge=True, rows_per_strip=args.rows_per_strip)
+            tse = tsm.TimeSeriesEngine([model], Hs, Ws, rank=rank, world=world, merge=True, rows_per_strip=args.rows_per_strip, frames=T)
             j0, j1 = tse.in_rows
             frame = synth_raster_slab(j1 - j0, Ws, j0, dev, seed=99) if j1 > j0 else torch.empty(6, 0, Ws, device=dev)
-            frames = [frame] * T                      # same cost as independent draws; keeps 30 GB of host-free generation out
+            frames = {t_: frame for t_ in tse.my_frames}    # same cost as independent draws; keeps 30 GB of generation out
             with torch.no_grad():
-                tse.run(frames[:1], None, 0, row_offset=j0)
+                tse.run(frames, None, 0, row_offset=j0)
                 barrier()
                 a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a0.record()
@@ -540,8 +798,8 @@ def main():
             tms = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-            tseries = {"workload": f"switzerland_shaped_{Hs}x{Ws}_x{T}_seasonal_frames_rows_sharded_over_{world}_gpus",
-                       "ms": float(tms.item()), "value": T * Hs * Ws / (float(tms.item()) * 1e-3), "unit": UNIT,
+            tseries = {"workload": f"switzerland_shaped_{Hs}x{Ws}_x{T}_seasonal_frames_over_{world}_gpus",
+                       "partition": tse.describe(), "ms": float(tms.item()), "value": T * Hs * Ws / (float(tms.item()) * 1e-3), "unit": UNIT,
                        "season_total": float(o["season_total"].item()), "frames": T,
                        "note": "per-frame tiled inference + season mean/std/totals on the device (popcorn_b200.timeseries); inputs resident in HBM"}
             del frame, frames, o, tse
@@ -555,13 +813,13 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": name, "H": H, "W": W, "regions": R_REGIONS, "patch": 2048, "overlap": 128,
                            "windows": "merged_row_strips" if not args.no_merge else "reference_tiles",
-                           "rows_per_strip": args.rows_per_strip, "sharding": "balanced_256_row_units" if (args.balance and world > 1) else "strips", "ensemble": 1, "head": "dense",
+                           "rows_per_strip": args.rows_per_strip, "sharding": "balanced_256_row_units" if (balance and world > 1) else "strips", "ensemble": 1, "head": "dense",
                            "l2": "inputs (>=6 GB per GPU) far larger than the 126 MB L2; no flush needed",
-                           "weights": "random-init DDA x2 + head (popcorn_b200.synthetic.random_state_dict seed 1600)"},
+                           "weights": weights_name},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kernels,
                 "fp32_simt": fp32,
-                "cpu_baseline": cpu_base, "train_step": train, "time_series": tseries,
-                "check": {"sum_of_region_sums": sums_check, "map_total": map_total}}
+                "cpu_baseline": cpu_base, "gpu_baseline": gpu_base, "train_step": train, "ensemble5": ens, "time_series": tseries,
+                "same_slab_one_rank": alone, "check": check}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

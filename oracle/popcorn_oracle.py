@@ -199,7 +199,7 @@ def forward(sd: Dict[str, Tensor], inputs: dict, padding: bool = True, sparse: b
         m = sparsity_mask(builtup, inputs["admin_mask"], inputs["census_idx"], occupancymodel, grid)
         flat = feats.permute(1, 0, 2, 3).reshape(C, -1)
         mf = m.reshape(-1)
-        o = torch.zeros(2, B * H * W, dtype=feats.dtype)
+        o = torch.zeros(2, B * H * W, dtype=feats.dtype, device=feats.device)
         o[:, mf] = head_mlp(sd, flat[:, mf].t()).t()          # sparse_module_forward, popcorn.py:195-228
         out = o.view(2, B, H, W).permute(1, 0, 2, 3)[:, 0]
         aux["mask"] = m

@@ -287,7 +287,7 @@ class CountryEngine:
         ops.copy_d2h(map_out[r0:r1], self._maps[0][r0:r1], self._d2h_stream.cuda_stream)
 
     def run(self, raster: torch.Tensor, ids: Optional[torch.Tensor], R: int, row_offset: int = 0,
-            group=None, finalize: bool = True, map_out: Optional[torch.Tensor] = None):
+            group=None, finalize: bool = True, map_out: Optional[torch.Tensor] = None, reduce: bool = True):
         """raster: [6, rows, W] fp32 normalised, holding raster rows [row_offset, row_offset+rows) — a CUDA tensor, or a
         pinned host tensor (then windows are streamed H2D on a copy stream, overlapped with compute) — or a RawRaster
         (uint16 S2 + float32 S1 in on-disk form, device or pinned host: converted and normalised on the device).
@@ -295,6 +295,7 @@ class CountryEngine:
         map_out: optional pinned host tensor [owned rows, W]: finished strips are finalised and copied out while later
         strips still compute (replaces the per-tile .cpu() of run_eval.py:127-135); the copies are asynchronous — call
         engine.wait_download() (or torch.cuda.synchronize()) before reading map_out.
+        reduce=False skips the all-reduce (the returned sums are this rank's partial sums).
         Returns dict(map, std, scale_map, scale_std, count, sums[R] float64 all-reduced)."""
         if map_out is not None:
             if not finalize:
@@ -337,7 +338,8 @@ class CountryEngine:
         sums = torch.zeros(max(R, 1), dtype=torch.float64, device=dev)
         if ids is not None and maps[0].numel():
             ops.region_sum(maps[0], ids, R, sums)
-        allreduce_sums(sums, group)
+        if reduce:
+            allreduce_sums(sums, group)
         return {"map": maps[0], "std": maps[1], "scale_map": maps[2], "scale_std": maps[3], "count": maps[4],
                 "sums": sums, "rows": self.out_rows}
 

@@ -382,6 +382,7 @@ __global__ void __launch_bounds__(128) convt2x2_kernel(const __grid_constant__ C
 // ---------------------------------------------------------------------------------------------------
 // Host side: packed-weight layout and the layer schedule
 // ---------------------------------------------------------------------------------------------------
+constexpr int PC_NO_TC = -7001;   // launch_conv<..., EPI_CONVT>: no tensor-core launch was possible (internal, never returned to callers)
 struct LayerSpec { int cin, cout, is_t; };
 static const LayerSpec kLayers[12] = {
     {-1, 8, 0}, {8, 8, 0}, {8, 16, 0}, {16, 16, 0}, {16, 16, 0}, {16, 16, 0},
@@ -505,7 +506,7 @@ static int launch_conv(ConvParams& p, int njobs, cudaStream_t st) {
     }();
     static const int cat = [] {
         char nm[64];
-        snprintf(nm, sizeof(nm), "conv3x3<%d,%d,%d,%s>", CIN_A, CIN_B, COUT, EPI == EPI_STORE ? "store" : EPI == EPI_POOL ? "pool" : "dot");
+        snprintf(nm, sizeof(nm), "conv3x3<%d,%d,%d,%s>", CIN_A, CIN_B, COUT, EPI == EPI_STORE ? "store" : EPI == EPI_POOL ? "pool" : EPI == EPI_DOT ? "dot" : "convt");
         return prof_register(nm);
     }();
     // tensor-core path (conv_tc.cu): every job carries a pre-swizzled weight image and its sources can be read by TMA
@@ -524,6 +525,9 @@ static int launch_conv(ConvParams& p, int njobs, cudaStream_t st) {
         }
         if (tc) return launch_conv_tc(CIN_A, CIN_B, COUT, EPI, tp, njobs, st);
     }
+    if constexpr (EPI == EPI_CONVT) {
+        return PC_NO_TC;       // the fused transposed-conv epilogue exists on the tensor-core path only: the caller runs conv + convT kernels
+    } else {
     constexpr int CC = conv_cc<CIN_A + CIN_B>();
     // TMA staging needs plain (non-reflected, identity-channel) 16-byte-aligned sources: every layer but the first
     bool tma = allow_tma && CIN_A >= 8;
@@ -541,6 +545,7 @@ static int launch_conv(ConvParams& p, int njobs, cudaStream_t st) {
     if (rc) return rc;
     PC_LAUNCH_CHECK();
     return 0;
+    }
 }
 
 static void set_a(ConvJob& j, const Plane& t) {
@@ -670,21 +675,36 @@ extern "C" int pc_dda_forward(const float* wpack, long long wpack_floats, const 
         reset(H4, W4);
         for (int j = 0; j < nj; ++j) { ConvJob& J = p.jobs[j]; set_a(J, bufs[j].QA); J.w = W_(js(j), 4); J.wtc = WT_(js(j), 4); set_out(J, bufs[j].QB); }
         if ((rc = launch_conv<16, 0, 16, EPI_STORE>(p, nj, st))) return rc;
-        reset(H4, W4);
-        for (int j = 0; j < nj; ++j) { ConvJob& J = p.jobs[j]; set_a(J, bufs[j].QB); J.w = W_(js(j), 5); J.wtc = WT_(js(j), 5); set_out(J, bufs[j].QA); }
-        if ((rc = launch_conv<16, 0, 16, EPI_STORE>(p, nj, st))) return rc;
-        // ---- L6 up2.up : QA -> HD [16, 2*H4, 2*W4]
-        memset(&pt, 0, sizeof(pt)); pt.Hl = H4; pt.Wl = W4;
-        for (int j = 0; j < nj; ++j) {
-            ConvTJob& J = pt.jobs[j]; J.in = bufs[j].QA.p; J.in_cs = bufs[j].QA.cs; J.in_rs = bufs[j].QA.rs;
-            J.w = W_(js(j), 6); J.out = bufs[j].HD.p; J.out_cs = bufs[j].HD.cs; J.out_rs = bufs[j].HD.rs;
+        // L5 + L6: down2.conv.3 with the Up block's transposed conv in its epilogue (QB -> HD [16, 2*H4, 2*W4]; the quarter-resolution
+        // activation never reaches HBM); without the tensor-core path: conv -> QA, then the convT kernel
+        static const bool fuse_ct = [] { const char* e = getenv("POPCORN_FUSE_CONVT"); return e ? atoi(e) != 0 : true; }();
+        rc = PC_NO_TC;
+        if (fuse_ct && have_tc) {
+            reset(H4, W4);
+            for (int j = 0; j < nj; ++j) {
+                ConvJob& J = p.jobs[j]; set_a(J, bufs[j].QB); J.w = W_(js(j), 5); J.wtc = WT_(js(j), 5);
+                J.ctw = W_(js(j), 6); J.ct_out = bufs[j].HD.p; J.ct_cs = bufs[j].HD.cs; J.ct_rs = bufs[j].HD.rs;
+            }
+            rc = launch_conv<16, 0, 16, EPI_CONVT>(p, nj, st);
+            if (rc && rc != PC_NO_TC) return rc;
         }
-        {
-            static const int cat = prof_register("convt2x2<16>");
-            ProfScope prof(cat, st, (double)H4 * W4 * nj);
-            convt2x2_kernel<16><<<dim3(cdiv(W4, 32), cdiv(H4, 4), nj), dim3(32, 4), 0, st>>>(pt);
+        if (rc == PC_NO_TC) {
+            reset(H4, W4);
+            for (int j = 0; j < nj; ++j) { ConvJob& J = p.jobs[j]; set_a(J, bufs[j].QB); J.w = W_(js(j), 5); J.wtc = WT_(js(j), 5); set_out(J, bufs[j].QA); }
+            if ((rc = launch_conv<16, 0, 16, EPI_STORE>(p, nj, st))) return rc;
+            // ---- L6 up2.up : QA -> HD [16, 2*H4, 2*W4]
+            memset(&pt, 0, sizeof(pt)); pt.Hl = H4; pt.Wl = W4;
+            for (int j = 0; j < nj; ++j) {
+                ConvTJob& J = pt.jobs[j]; J.in = bufs[j].QA.p; J.in_cs = bufs[j].QA.cs; J.in_rs = bufs[j].QA.rs;
+                J.w = W_(js(j), 6); J.out = bufs[j].HD.p; J.out_cs = bufs[j].HD.cs; J.out_rs = bufs[j].HD.rs;
+            }
+            {
+                static const int cat = prof_register("convt2x2<16>");
+                ProfScope prof(cat, st, (double)H4 * W4 * nj);
+                convt2x2_kernel<16><<<dim3(cdiv(W4, 32), cdiv(H4, 4), nj), dim3(32, 4), 0, st>>>(pt);
+            }
+            PC_LAUNCH_CHECK();
         }
-        PC_LAUNCH_CHECK();
         // ---- L7 up2.conv.0 : cat[HC(16), pad(HD)(16)] -> HA(8) ; L8 up2.conv.3 : HA -> HB(8)
         reset(H2, W2);
         for (int j = 0; j < nj; ++j) {
@@ -694,21 +714,34 @@ extern "C" int pc_dda_forward(const float* wpack, long long wpack_floats, const 
             J.w = W_(js(j), 7); J.wtc = WT_(js(j), 7); set_out(J, bufs[j].HA);
         }
         if ((rc = launch_conv<16, 16, 8, EPI_STORE>(p, nj, st))) return rc;
-        reset(H2, W2);
-        for (int j = 0; j < nj; ++j) { ConvJob& J = p.jobs[j]; set_a(J, bufs[j].HA); J.w = W_(js(j), 8); J.wtc = WT_(js(j), 8); set_out(J, bufs[j].HB); }
-        if ((rc = launch_conv<8, 0, 8, EPI_STORE>(p, nj, st))) return rc;
-        // ---- L9 up1.up : HB(8) -> F2 [8, 2*H2, 2*W2]
-        memset(&pt, 0, sizeof(pt)); pt.Hl = H2; pt.Wl = W2;
-        for (int j = 0; j < nj; ++j) {
-            ConvTJob& J = pt.jobs[j]; J.in = bufs[j].HB.p; J.in_cs = bufs[j].HB.cs; J.in_rs = bufs[j].HB.rs;
-            J.w = W_(js(j), 9); J.out = bufs[j].F2.p; J.out_cs = bufs[j].F2.cs; J.out_rs = bufs[j].F2.rs;
+        // L8 + L9: up2.conv.3 with up1's transposed conv in its epilogue (HA -> F2 [8, 2*H2, 2*W2])
+        rc = PC_NO_TC;
+        if (fuse_ct && have_tc) {
+            reset(H2, W2);
+            for (int j = 0; j < nj; ++j) {
+                ConvJob& J = p.jobs[j]; set_a(J, bufs[j].HA); J.w = W_(js(j), 8); J.wtc = WT_(js(j), 8);
+                J.ctw = W_(js(j), 9); J.ct_out = bufs[j].F2.p; J.ct_cs = bufs[j].F2.cs; J.ct_rs = bufs[j].F2.rs;
+            }
+            rc = launch_conv<8, 0, 8, EPI_CONVT>(p, nj, st);
+            if (rc && rc != PC_NO_TC) return rc;
         }
-        {
-            static const int cat = prof_register("convt2x2<8>");
-            ProfScope prof(cat, st, (double)H2 * W2 * nj);
-            convt2x2_kernel<8><<<dim3(cdiv(W2, 32), cdiv(H2, 4), nj), dim3(32, 4), 0, st>>>(pt);
+        if (rc == PC_NO_TC) {
+            reset(H2, W2);
+            for (int j = 0; j < nj; ++j) { ConvJob& J = p.jobs[j]; set_a(J, bufs[j].HA); J.w = W_(js(j), 8); J.wtc = WT_(js(j), 8); set_out(J, bufs[j].HB); }
+            if ((rc = launch_conv<8, 0, 8, EPI_STORE>(p, nj, st))) return rc;
+            // ---- L9 up1.up : HB(8) -> F2 [8, 2*H2, 2*W2]
+            memset(&pt, 0, sizeof(pt)); pt.Hl = H2; pt.Wl = W2;
+            for (int j = 0; j < nj; ++j) {
+                ConvTJob& J = pt.jobs[j]; J.in = bufs[j].HB.p; J.in_cs = bufs[j].HB.cs; J.in_rs = bufs[j].HB.rs;
+                J.w = W_(js(j), 9); J.out = bufs[j].F2.p; J.out_cs = bufs[j].F2.cs; J.out_rs = bufs[j].F2.rs;
+            }
+            {
+                static const int cat = prof_register("convt2x2<8>");
+                ProfScope prof(cat, st, (double)H2 * W2 * nj);
+                convt2x2_kernel<8><<<dim3(cdiv(W2, 32), cdiv(H2, 4), nj), dim3(32, 4), 0, st>>>(pt);
+            }
+            PC_LAUNCH_CHECK();
         }
-        PC_LAUNCH_CHECK();
         // ---- L10 up1.conv.0 : cat[F1(8), pad(F2)(8)] -> F0(8)
         reset(Hv, Wv);
         for (int j = 0; j < nj; ++j) {

@@ -9,7 +9,7 @@ namespace pc {
 constexpr int MAX_JOBS = 8;
 constexpr int TC_BOXW = 136;         // floats per staged row: box starts at x0-4 (TMA needs a 16-byte aligned inner coordinate), 128 px + halo
 
-enum { EPI_STORE = 0, EPI_POOL = 1, EPI_DOT = 2 };
+enum { EPI_STORE = 0, EPI_POOL = 1, EPI_DOT = 2, EPI_CONVT = 3 };
 
 // One (image, stream) instance of a conv layer.  The input is the channel concatenation of source A (first CIN_A
 // channels; optional reflect folding and plane remap for the first layer) and source B (next CIN_B channels, placed
@@ -25,6 +25,10 @@ struct ConvJob {
     const float* dotw;                   // [8] weights + [1] bias of the 1x1 out conv slice (EPI_DOT)
     const float* dot_in; int dot_in_rs;  // partial logits of the other stream (or null)
     float* dot_out; int dot_out_rs; int dot_final;
+    // EPI_CONVT (tensor-core kernel only): the Up block's ConvTranspose2d(k=2, s=2) applied to this layer's activated output
+    // in the epilogue; ctw = [COUT][4 taps dy*2+dx][COUT] then bias[COUT] (the SIMT pack of the transposed conv),
+    // ct_out = [COUT][2H][2W] planes.  The layer's own output is not stored unless `out` is set.
+    const float* ctw; float* ct_out; long long ct_cs; int ct_rs;
 };
 
 // geometry of one launch of the tensor-core conv (all jobs share it)

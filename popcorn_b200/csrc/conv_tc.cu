@@ -47,9 +47,9 @@ __device__ long long g_tc_dbg[32];
 __device__ long long g_tc_trace[4096];   // [role 0..7][batch 0..63][event 0..7] clock64 stamps of CTA (0,0)
 #define TCP_TRACE(role, batch, ev) do { if (blockIdx.x == 0 && blockIdx.y == 0 && (batch) >= 64 && (batch) < 128) g_tc_trace[((role) * 64 + (batch) - 64) * 8 + (ev)] = clock64(); } while (0)
 #define TCP_T(var) const long long var = clock64()
-#define TCP_DECL long long tcp_acc[5] = {0, 0, 0, 0, 0}
+#define TCP_DECL long long tcp_acc[6] = {0, 0, 0, 0, 0, 0}
 #define TCP_ADD(slot, a, b) tcp_acc[(slot) & 7] += (b) - (a)
-#define TCP_FLUSH(base) do { if (blockIdx.x == 0 && blockIdx.y == 0) for (int q = 0; q < 5; ++q) g_tc_dbg[(base) + q] = tcp_acc[q]; } while (0)
+#define TCP_FLUSH(base) do { if (blockIdx.x == 0 && blockIdx.y == 0) for (int q = 0; q < 6; ++q) g_tc_dbg[(base) + q] = tcp_acc[q]; } while (0)
 #else
 #define TCP_TRACE(role, batch, ev)
 #define TCP_T(var)
@@ -60,7 +60,9 @@ __device__ long long g_tc_trace[4096];   // [role 0..7][batch 0..63][event 0..7]
 
 constexpr int TCM = 128;           // pixels per UMMA
 constexpr int TCN = 16;            // UMMA N (output channels, zero-padded)
-constexpr int ND = 8;              // accumulator ring (output rows in flight)
+#ifndef PC_TC_ND8
+#define PC_TC_ND8 8                // accumulator ring depth (output rows in flight) of the Cout = 8 kernels
+#endif
 constexpr int NGROUP = 2;          // stager groups / epilogue groups (4 warps each: one per TMEM lane quarter)
 constexpr int WS_THREADS = (4 * NGROUP * 2 + 3) * 32;    // stagers + epilogue + 2 MMA warps + TMA warp
 constexpr int W_EPI0 = 4 * NGROUP, W_MMA = 8 * NGROUP, W_TMA = 8 * NGROUP + 2;
@@ -69,6 +71,7 @@ constexpr int TMEM_ALL = 512;
 template <int CIN, int COUT>
 struct TcGeom {
     static constexpr int SLOTW = COUT == 8 ? 8 : 16;            // accumulator columns per output row
+    static constexpr int ND = COUT == 8 ? PC_TC_ND8 : 8;        // accumulator ring: output rows in flight
     static constexpr int BROWS = COUT == 8 ? 64 : 48;           // rows of a B matrix (see conv_tc_pack_layer)
     static constexpr int KROW = (3 * CIN + 7) / 8 * 8;          // A columns per half (hi | lo) of one input row
     static constexpr int KSTEPS = KROW / 8;
@@ -79,7 +82,8 @@ struct TcGeom {
     static constexpr int IMG_BYTES = OFF_BIAS + 64;             // + bias[16]
     static constexpr int A_COLS = 2 * KROW;                     // one A buffer: hi at [0, KROW), lo at [KROW, 2*KROW)
     static constexpr int NA_FIT = (TMEM_ALL - ND * SLOTW) / A_COLS;
-    static constexpr int NA = NA_FIT >= 4 ? 4 : 2;              // A buffers (power of two)
+    static constexpr int NA = NA_FIT >= 8 ? 8 : NA_FIT >= 4 ? 4 : 2;   // A buffers (power of two): Cin 8 -> 8 (four row pairs in flight:
+                                                                // the stagers run ahead of the UMMAs of the two batches before), Cin 16 -> 4, Cin 32 -> 2
     static constexpr int D_COL0 = NA * A_COLS;                  // accumulator slots of 16 columns
     static constexpr int STAGE_BYTES = CIN * TC_BOXW * 4;       // one input row, all channels
     static constexpr int NS = CIN <= 8 ? 16 : CIN <= 16 ? 8 : 4;   // shared-memory ring depth (~70 KB in flight per SM)
@@ -87,7 +91,9 @@ struct TcGeom {
     static constexpr int OFF_BARS = OFF_STAGE + NS * STAGE_BYTES;   // s_full[NS] s_empty[NS] full_a[NA/2] empty_a[NA/2] d_full[ND/2] d_empty[ND/2]
     static constexpr int NBARS = 2 * NS + 2 * NA + 2 * ND;
     static constexpr int OFF_TMEM = OFF_BARS + 8 * NBARS;
-    static constexpr int SMEM_NEED = OFF_TMEM + 16 + 1024;
+    static constexpr int OFF_CTW = (OFF_TMEM + 16 + 15) / 16 * 16;  // EPI_CONVT: [COUT][4][COUT] + bias[COUT] floats of the transposed conv
+    static constexpr int CTW_FLOATS = COUT * 4 * COUT + COUT;
+    static constexpr int SMEM_NEED = OFF_CTW + CTW_FLOATS * 4 + 1024;
     // > half of the SM's shared memory: exactly one CTA per SM (it owns all 512 TMEM columns)
     static constexpr int SMEM_BYTES = SMEM_NEED > 116 * 1024 ? SMEM_NEED : 116 * 1024;
     static_assert(NA_FIT >= 2, "TMEM budget");
@@ -108,7 +114,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1)
 conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
     constexpr int CIN = CIN_A + CIN_B;
     using G = TcGeom<CIN, COUT>;
-    constexpr int NA = G::NA, NS = G::NS, NP = NA / 2, NDP = ND / 2;
+    constexpr int NA = G::NA, NS = G::NS, NP = NA / 2, ND = G::ND, NDP = ND / 2;
     constexpr unsigned FULL = 0xffffffffu;
 
     extern __shared__ uint8_t smem_raw[];
@@ -129,6 +135,9 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
 
     for (int i = tid; i < G::IMG_BYTES / 16; i += WS_THREADS)
         reinterpret_cast<int4*>(sm)[i] = __ldg(reinterpret_cast<const int4*>(job.wtc) + i);
+    if (EPI == EPI_CONVT)
+        for (int i = tid; i < G::CTW_FLOATS / 4; i += WS_THREADS)
+            reinterpret_cast<float4*>(sm + G::OFF_CTW)[i] = __ldg(reinterpret_cast<const float4*>(job.ctw) + i);
     if (warp == W_MMA) tmem_alloc(smem_u32(tmem_slot), TMEM_ALL);
     if (tid == 0) {
         for (int i = 0; i < NS; ++i) { mbar_init(s_full(i), 1); mbar_init(s_empty(i), 4); }     // 4 = the stager warps of a group
@@ -188,7 +197,19 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
                     if (n >= 1) { m2 = empty_a(pb); p2 = (uint32_t)(n - 1) & 1u; }
                     const int P = P0 + b;
                     if (b < nb - 1 && P >= NDP) { m3 = d_empty(P & (NDP - 1)); p3 = (uint32_t)(P / NDP - 1) & 1u; }
+#if PC_TC_PROBE
+                    {   // probe build: the three waits one after the other, timed separately (slot 5 = empty_a, slot 1 = d_empty)
+                        mbar_wait_sleep(m1, p1);
+                        const long long ta = clock64();
+                        mbar_wait_sleep(m2, p2);
+                        const long long tb = clock64();
+                        mbar_wait_sleep(m3, p3);
+                        const long long tc_ = clock64();
+                        tcp_acc[5] += tb - ta; tcp_acc[1] += tc_ - tb; tcp_acc[0] -= tc_ - ta;
+                    }
+#else
                     mbar_wait3_sleep(m1, p1, m2, p2, m3, p3);
+#endif
                 }
                 TCP_T(t1);
                 tc_fence_after();
@@ -217,7 +238,7 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
                 if (lane == 0) mbar_arrive(full_a(pb));
                 TCP_T(t4);
                 if ((warp & 3) == 0 && lane == 0) TCP_TRACE(group, B, 4);
-                TCP_ADD(0, t0, t1); TCP_ADD(1, t1, t2); TCP_ADD(2, t2, t3); TCP_ADD(3, t3, t4); TCP_ADD(4, t4 - 1, t4);
+                TCP_ADD(0, t0, t1); TCP_ADD(2, t2, t3); TCP_ADD(3, t3, t4); TCP_ADD(4, t4 - 1, t4);
             }
             P0 += nb - 1;
         }
@@ -299,6 +320,50 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
                         float* dst = job.out + (long long)yy * job.out_rs + xx;
 #pragma unroll
                         for (int o = 0; o < COUT; ++o) dst[(long long)o * job.out_cs] = acc[h][o];
+                    }
+                }
+                if (EPI == EPI_CONVT) {
+                    // ConvTranspose2d(k=2, s=2) of the Up block on the two activated rows this thread holds (networks.py:302):
+                    // up[co][2y+dy][2x+dx] = b[co] + sum_ci act[ci][y][x] * w[ci][dy*2+dx][co] — purely per pixel, so it rides in
+                    // the epilogue (FP32 pipe, otherwise idle here) and the low-resolution activation never travels to HBM.
+                    const float* ctw = reinterpret_cast<const float*>(sm + G::OFF_CTW);
+                    const float* ctb = ctw + COUT * 4 * COUT;
+                    const bool row_ok[2] = {in_x && (y0 + 2 * m) < H, in_x && (y0 + 2 * m + 1) < H};
+#pragma unroll 1
+                    for (int cg = 0; cg < COUT; cg += 8) {
+#pragma unroll 1
+                        for (int dy = 0; dy < 2; ++dy) {
+                            float u[2][2][8];                        // [row h][dx][co]
+#pragma unroll
+                            for (int o = 0; o < 8; ++o) {
+                                const float bo = ctb[cg + o];
+                                u[0][0][o] = bo; u[0][1][o] = bo; u[1][0][o] = bo; u[1][1][o] = bo;
+                            }
+#pragma unroll
+                            for (int ci = 0; ci < COUT; ++ci) {
+#pragma unroll
+                                for (int dx = 0; dx < 2; ++dx) {
+                                    const float* wr = ctw + (ci * 4 + dy * 2 + dx) * COUT + cg;
+                                    const float4 wa = *reinterpret_cast<const float4*>(wr);
+                                    const float4 wb = *reinterpret_cast<const float4*>(wr + 4);
+                                    const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+                                    for (int o = 0; o < 8; ++o) {
+                                        u[0][dx][o] = fmaf(acc[0][ci], wv[o], u[0][dx][o]);
+                                        u[1][dx][o] = fmaf(acc[1][ci], wv[o], u[1][dx][o]);
+                                    }
+                                }
+                            }
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                if (!row_ok[h]) continue;
+                                const int oy = y0 + 2 * m + h;
+                                float* dst = job.ct_out + (long long)cg * job.ct_cs + (long long)(2 * oy + dy) * job.ct_rs + 2 * vx;
+#pragma unroll
+                                for (int o = 0; o < 8; ++o)
+                                    *reinterpret_cast<float2*>(dst + (long long)o * job.ct_cs) = make_float2(u[h][0][o], u[h][1][o]);
+                            }
+                        }
                     }
                 }
                 if (EPI == EPI_POOL) {                               // 2x2 max over (rows 2m, 2m+1) x (lanes 2k, 2k+1)
@@ -512,7 +577,7 @@ static int launch_tc_impl(TcConvParams& p, int njobs, cudaStream_t st) {
     using G = TcGeom<CIN_A + CIN_B, COUT>;
     static const int cat = [] {
         char nm[64];
-        snprintf(nm, sizeof(nm), "conv3x3_tc<%d,%d,%d,%s>", CIN_A, CIN_B, COUT, EPI == EPI_STORE ? "store" : EPI == EPI_POOL ? "pool" : "dot");
+        snprintf(nm, sizeof(nm), "conv3x3_tc<%d,%d,%d,%s>", CIN_A, CIN_B, COUT, EPI == EPI_STORE ? "store" : EPI == EPI_POOL ? "pool" : EPI == EPI_DOT ? "dot" : "convt");
         return prof_register(nm);
     }();
     auto k = conv3x3_tc_kernel<CIN_A, CIN_B, COUT, EPI>;
@@ -545,6 +610,8 @@ int launch_conv_tc(int cin_a, int cin_b, int cout, int epi, TcConvParams& p, int
         case ((16 * 100 + 0) * 100 + 16) * 10 + EPI_POOL: return launch_tc_impl<16, 0, 16, EPI_POOL>(p, njobs, st);
         case ((16 * 100 + 16) * 100 + 8) * 10 + EPI_STORE: return launch_tc_impl<16, 16, 8, EPI_STORE>(p, njobs, st);
         case ((8 * 100 + 8) * 100 + 8) * 10 + EPI_STORE: return launch_tc_impl<8, 8, 8, EPI_STORE>(p, njobs, st);
+        case ((8 * 100 + 0) * 100 + 8) * 10 + EPI_CONVT: return launch_tc_impl<8, 0, 8, EPI_CONVT>(p, njobs, st);
+        case ((16 * 100 + 0) * 100 + 16) * 10 + EPI_CONVT: return launch_tc_impl<16, 0, 16, EPI_CONVT>(p, njobs, st);
     }
     set_error("launch_conv_tc: no instantiation for (%d,%d,%d,%d)", cin_a, cin_b, cout, epi);
     return PC_ERR_INVALID;

@@ -376,6 +376,8 @@ extern "C" int pc_sparse_mask_compact(const float* builtup, const float* admin, 
     int32_t* w = reinterpret_cast<int32_t*>(round_up((long long)(uintptr_t)workspace, 256));
     a.counts = w; a.offsets = w + 2 * nb; a.flags = w + 3 * nb;
     cudaStream_t st = (cudaStream_t)stream;
+    static const int cat = prof_register("sparse_mask_compact");
+    ProfScope prof(cat, st, (double)npix);
     compact_count_kernel<<<nb, 256, 0, st>>>(a, nb);
     PC_LAUNCH_CHECK();
     compact_scan_kernel<<<1, 1024, 0, st>>>(a, nb);

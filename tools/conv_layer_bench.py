@@ -52,7 +52,7 @@ for cin, cout in cases:
             def per(a, n):
                 return [round(x / max(n, 1)) for x in a]
             print("   mma issuer0 batches", c[4], " wait_full_a, issue, commit =", per(c[0:3], c[4]))
-            print("   stager w0   rows", c[12], " wait_s_full, wait_empty_a, stage, wait_st+arrive =", per(c[8:12], c[12]))
+            print("   stager w0   rows", c[12], " wait_s_full, wait_d_empty, stage, wait_st+arrive, wait_empty_a =", per(c[8:12] + c[13:14], c[12]))
             print("   epilogue w8 rows", c[18], " wait_d_full, ld+zero+arrive =", per(c[16:18], c[18]))
         px = H * W
         print(f"cin {cin:2d} cout {cout:2d} {name:4s}: {ms:7.3f} ms  {px / ms / 1e6:7.1f} Gpx/s  {(cin + cout) * 4 * px / ms / 1e6:7.0f} GB/s  "

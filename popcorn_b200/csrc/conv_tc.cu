@@ -60,6 +60,14 @@ __device__ long long g_tc_trace[4096];   // [role 0..7][batch 0..63][event 0..7]
 
 constexpr int TCM = 128;           // pixels per UMMA
 constexpr int TCN = 16;            // UMMA N (output channels, zero-padded)
+// timing experiments of the probe build (results are then WRONG on purpose): 1 = no UMMAs, 2 = no tcgen05.st in the stagers,
+// 4 = stagers read no shared memory, 8 = epilogue skips tcgen05.ld / re-zeroing
+#ifndef PC_TC_EXP
+#define PC_TC_EXP 0
+#endif
+#ifndef PC_TC_ST16
+#define PC_TC_ST16 1               // stagers write the A operand with 16-column tcgen05.st
+#endif
 #ifndef PC_TC_ND8
 #define PC_TC_ND8 8                // accumulator ring depth (output rows in flight) of the Cout = 8 kernels
 #endif
@@ -72,7 +80,11 @@ template <int CIN, int COUT>
 struct TcGeom {
     static constexpr int SLOTW = COUT == 8 ? 8 : 16;            // accumulator columns per output row
     static constexpr int ND = COUT == 8 ? PC_TC_ND8 : 8;        // accumulator ring: output rows in flight
-    static constexpr int BROWS = COUT == 8 ? 64 : 48;           // rows of a B matrix (see conv_tc_pack_layer)
+    // MMA issue: two issuers that own alternate output row pairs (more UMMAs in flight per SM: one thread sustains one UMMA per
+    // ~24 clk in this pipeline, the tensor pipe takes one per 9-13), or ONE issuer with 3-row windows (fewer, wider UMMAs).
+    // Measured per layer shape (profiles/r2_conv_pipeline.md): windows win for Cin 8 and Cin 32, pairs for Cin 16 and for Cout 16.
+    static constexpr bool TWO_ISSUERS = COUT == 16 || CIN == 16;
+    static constexpr int BROWS = COUT == 8 ? 24 : 48;           // rows of a B matrix: [W_ky2 | W_ky1 | W_ky0] x Cout (see conv_tc_pack_layer)
     static constexpr int KROW = (3 * CIN + 7) / 8 * 8;          // A columns per half (hi | lo) of one input row
     static constexpr int KSTEPS = KROW / 8;
     static constexpr int KATOMS = (KROW + 31) / 32;             // 32-float swizzle atoms along K
@@ -141,7 +153,7 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
     if (warp == W_MMA) tmem_alloc(smem_u32(tmem_slot), TMEM_ALL);
     if (tid == 0) {
         for (int i = 0; i < NS; ++i) { mbar_init(s_full(i), 1); mbar_init(s_empty(i), 4); }     // 4 = the stager warps of a group
-        for (int i = 0; i < NP; ++i) { mbar_init(full_a(i), 8); mbar_init(empty_a(i), 2); }     // 8 = both stager groups, 2 = both MMA issuers
+        for (int i = 0; i < NP; ++i) { mbar_init(full_a(i), 8); mbar_init(empty_a(i), G::TWO_ISSUERS ? 2 : 1); }   // 8 = both stager groups; 2 = both MMA issuers commit (or the only one)
         for (int i = 0; i < NDP; ++i) { mbar_init(d_full(i), 1); mbar_init(d_empty(i), 4); }    // 4 = the epilogue warps of a group
         mbar_init_fence();
     }
@@ -217,18 +229,45 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
                 if ((warp & 3) == 0 && lane == 0) TCP_TRACE(group, B, 3);
                 const float* st = stage0 + s * (G::STAGE_BYTES / 4);
                 const uint32_t tA = tbase + (uint32_t)(2 * pb + group) * G::A_COLS + lane_off;
+                auto load_split = [&](int col, uint32_t& hi, uint32_t& lo) {                 // A column = kx * CIN + ci
+                    const float val = (col < 3 * CIN) ? ((PC_TC_EXP & 4) ? (float)(col + px) : st[(col % CIN) * TC_BOXW + col / CIN]) : 0.f;
+                    split_tf32(val, hi, lo);
+                };
+#if PC_TC_ST16
+                // 16-column tcgen05.st (64 B per lane and instruction): the .x8 form sustains only ~126 B/clk per SM here
+                if (G::KROW % 16 == 0) {
+#pragma unroll
+                    for (int j = 0; j < G::KROW / 16; ++j) {
+                        uint32_t hi[16], lo[16];
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) load_split(16 * j + q, hi[q], lo[q]);
+                        if (PC_TC_EXP & 2) { asm volatile("" ::"r"(hi[0] ^ hi[5] ^ hi[15] ^ lo[0] ^ lo[7] ^ lo[15])); continue; }
+                        tmem_st16(tA + 16 * j, hi);
+                        tmem_st16(tA + G::KROW + 16 * j, lo);
+                    }
+                } else {                                            // KROW = 24: [hi 0..23 | lo 0..23] = 48 contiguous columns, three stores
+                    uint32_t w[48];
+#pragma unroll
+                    for (int q = 0; q < 24; ++q) load_split(q, w[q], w[24 + q]);
+                    if (!(PC_TC_EXP & 2)) {
+                        tmem_st16(tA, reinterpret_cast<uint32_t(&)[16]>(w[0]));
+                        tmem_st16(tA + 16, reinterpret_cast<uint32_t(&)[16]>(w[16]));
+                        tmem_st16(tA + 32, reinterpret_cast<uint32_t(&)[16]>(w[32]));
+                    } else {
+                        asm volatile("" ::"r"(w[0] ^ w[13] ^ w[24] ^ w[47]));
+                    }
+                }
+#else
 #pragma unroll
                 for (int j = 0; j < G::KSTEPS; ++j) {
                     uint32_t hi[8], lo[8];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const int col = 8 * j + q;                                      // A column = kx * CIN + ci
-                        const float val = (col < 3 * CIN) ? st[(col % CIN) * TC_BOXW + col / CIN] : 0.f;
-                        split_tf32(val, hi[q], lo[q]);
-                    }
+                    for (int q = 0; q < 8; ++q) load_split(8 * j + q, hi[q], lo[q]);
+                    if (PC_TC_EXP & 2) { asm volatile("" ::"r"(hi[0] ^ hi[1] ^ hi[2] ^ hi[3] ^ hi[4] ^ hi[5] ^ hi[6] ^ hi[7] ^ lo[0] ^ lo[1] ^ lo[2] ^ lo[3] ^ lo[4] ^ lo[5] ^ lo[6] ^ lo[7])); continue; }
                     tmem_st8(tA + 8 * j, hi);
                     tmem_st8(tA + G::KROW + 8 * j, lo);
                 }
+#endif
                 __syncwarp();
                 if (lane == 0) mbar_arrive(s_empty(s));                               // the ring slot may be refilled
                 TCP_T(t3);
@@ -398,15 +437,17 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
 #pragma unroll
                 for (int j = 0; j < G::KSTEPS; ++j) {
                     const uint64_t koff = boff + (uint64_t)(((j >> 2) * G::BATOM + (j & 3) * 32) >> 4);   // address field: 16-byte units
+                    if (PC_TC_EXP & 1) continue;
                     umma_tf32_ts(d, tAhi + 8 * j, bd_hi + koff, idesc, 1u);
                     umma_tf32_ts(d, tAlo + 8 * j, bd_hi + koff, idesc, 1u);
                     umma_tf32_ts(d, tAhi + 8 * j, bd_lo + koff, idesc, 1u);
                 }
             };
             int B = 0, P0 = 0;
+            const bool active = G::TWO_ISSUERS || q == 0;                   // windows: issuer 1 has no work (see below)
             TCP_DECL;
 #pragma unroll 1
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (int tile = blockIdx.x; active && tile < ntiles; tile += gridDim.x) {
                 const int npairs = tile_rows(tile) / 2, nb = npairs + 1;
 #pragma unroll 1
                 for (int b = 0; b < nb; ++b, ++B) {
@@ -432,25 +473,45 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
                             issue(d, tA0, 2 * BLK, ID16);                      // row 2b (ky0)
                             issue(d, tA1, BLK, ID32);                          // rows 2b (ky1), 2b+1 (ky0)
                         }
-                    } else {
-                        // Cout 8: 8-column slots, a pair = 16 columns = one N=16 UMMA; B blocks of 16 rows:
-                        // X0 = [W_ky2 | W_ky1], X1 = [0 | W_ky2], X2 = [W_ky0 | 0], X3 = [W_ky1 | W_ky0]
+                    } else if (G::TWO_ISSUERS) {
+                        // Cout 8, pair ownership: 8-column slots, a pair = 16 columns; B rows [W_ky2 | W_ky1 | W_ky0] (8 each)
+                        constexpr uint32_t ID8 = umma_idesc_tf32(TCM, 8);
+                        constexpr uint64_t BLK8 = (uint64_t)((8 * 128) >> 4);   // one 8-row block of B, in descriptor address units
                         if ((Pl & 1) == q) {
                             if (b >= 1) {
                                 const uint32_t d = tD + 16 * (uint32_t)(Pl & (NDP - 1));
-                                issue(d, tA0, 0, ID16);                        // X0: rows 2b-2 (ky2), 2b-1 (ky1)
-                                issue(d, tA1, BLK, ID16);                      // X1: row 2b-1 (ky2)
+                                issue(d, tA0, 0, ID16);                        // rows 2b-2 (ky2), 2b-1 (ky1)
+                                issue(d + 8, tA1, 0, ID8);                     // row 2b-1 (ky2)
                             }
                         } else if (b < npairs) {
                             const uint32_t d = tD + 16 * (uint32_t)(Pu & (NDP - 1));
-                            issue(d, tA0, 2 * BLK, ID16);                      // X2: row 2b (ky0)
-                            issue(d, tA1, 3 * BLK, ID16);                      // X3: rows 2b (ky1), 2b+1 (ky0)
+                            issue(d, tA0, 2 * BLK8, ID8);                      // row 2b (ky0)
+                            issue(d, tA1, BLK8, ID16);                         // rows 2b (ky1), 2b+1 (ky0)
                         }
+                    } else if (q == 0) {
+                        // Cout 8, windows: 8-column slots; ONE issuer (the accumulation order of an output row is then program order, i.e.
+                        // reproducible).  Input row i feeds output rows i-1 (ky 2), i (ky 1), i+1 (ky 0): three ADJACENT ring slots, so
+                        // one N = 24 UMMA per k-step and split term against B = [W_ky2 | W_ky1 | W_ky0] (12.5 clk on the tensor pipe,
+                        // where two N = 16 UMMAs cost 19: tools/probe/umma_n_probe.cu — M = 128 accepts N = 8 / 24 on sm_100a).  The
+                        // window is clipped at the tile's first / last row and split in two where the 8-row ring wraps.
+                        constexpr uint32_t ID8 = umma_idesc_tf32(TCM, 8), ID24 = umma_idesc_tf32(TCM, 24);
+                        constexpr uint64_t BLK8 = (uint64_t)((8 * 128) >> 4);   // one 8-row block of B, in descriptor address units
+                        const int nrows = 2 * npairs;
+                        auto window = [&](int i, uint32_t tA) {
+                            const int lo = i - 1 < 0 ? 0 : i - 1, hi = i + 1 > nrows - 1 ? nrows - 1 : i + 1;
+                            const int n = hi - lo + 1, blk0 = lo - (i - 1);
+                            const int slot = (2 * P0 + lo) & (ND - 1);
+                            const int run1 = n < ND - slot ? n : ND - slot;
+                            issue(tD + 8 * (uint32_t)slot, tA, (uint64_t)blk0 * BLK8, run1 == 1 ? ID8 : run1 == 2 ? ID16 : ID24);
+                            if (run1 < n) issue(tD, tA, (uint64_t)(blk0 + run1) * BLK8, (n - run1) == 1 ? ID8 : ID16);
+                        };
+                        window(2 * b - 1, tA0);
+                        window(2 * b, tA1);
                     }
                     TCP_T(t2);
                     TCP_TRACE(2 + q, B, 2);
-                    umma_commit(empty_a(pb));                                  // the A buffer pair may be refilled (both issuers commit)
-                    if (b >= 1 && (Pl & 1) == q) umma_commit(d_full(Pl & (NDP - 1)));   // output rows 2b-2, 2b-1 are final
+                    if (G::TWO_ISSUERS || q == 0) umma_commit(empty_a(pb));    // the A buffer pair may be refilled (both issuers commit)
+                    if (b >= 1 && (G::TWO_ISSUERS ? (Pl & 1) == q : q == 0)) umma_commit(d_full(Pl & (NDP - 1)));   // output rows 2b-2, 2b-1 are final
                     TCP_T(t3);
                     TCP_TRACE(2 + q, B, 3);
                     TCP_ADD(0, t0, t1); TCP_ADD(1, t1, t2); TCP_ADD(2, t2, t3); TCP_ADD(3, t3 - 1, t3); TCP_ADD(4, t3 - 1, t3);
@@ -489,7 +550,7 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
-static int tc_brows(int cout) { return cout == 8 ? 64 : 48; }
+static int tc_brows(int cout) { return cout == 8 ? 24 : 48; }
 
 static int tc_geom_img_floats(int cin, int cout) {
     const int krow = (3 * cin + 7) / 8 * 8, katoms = (krow + 31) / 32;
@@ -499,9 +560,8 @@ static int tc_geom_img_floats(int cin, int cout) {
 int conv_tc_layer_floats(int cin, int cout) { return (int)round_up(tc_geom_img_floats(cin, cout), 64); }   // 256-B multiple
 
 // flat = [cin][ky][kx][cout] + bias[cout] (the SIMT pack)  ->  [hi|lo][katom][rows][32 floats] swizzled + bias[16], k = kx*cin + ci.
-//   cout 16: 48 rows [W_ky2 | W_ky1 | W_ky0]                         (row 16*(2-ky) + co)
-//   cout  8: 64 rows X0 = [W_ky2 | W_ky1], X1 = [0 | W_ky2], X2 = [W_ky0 | 0], X3 = [W_ky1 | W_ky0]   (8 + 8 rows each)
-// — the 16-row windows the issuers address for one or two adjacent output rows of a pair (conv3x3_tc_kernel).
+//   rows [W_ky2 | W_ky1 | W_ky0] (row cout*(2-ky) + co): 48 rows for cout 16, 24 for cout 8 — the issuers address 8- or 16-row
+//   aligned windows of it for one, two or three adjacent output rows (conv3x3_tc_kernel).
 void conv_tc_pack_layer(const float* flat, int cin, int cout, float* img) {
     const int krow = (3 * cin + 7) / 8 * 8, katoms = (krow + 31) / 32;
     const int rows = tc_brows(cout);
@@ -509,14 +569,8 @@ void conv_tc_pack_layer(const float* flat, int cin, int cout, float* img) {
     const int total = conv_tc_layer_floats(cin, cout);
     memset(img, 0, sizeof(float) * total);
     // (row offset, ky) placements of the 8/16-row weight blocks
-    int place[6][2], nplace = 0;
-    if (cout == 16) {
-        for (int ky = 0; ky < 3; ++ky) { place[nplace][0] = (2 - ky) * 16; place[nplace][1] = ky; ++nplace; }
-    } else {
-        const int p[6][2] = {{0, 2}, {8, 1}, {24, 2}, {32, 0}, {48, 1}, {56, 0}};
-        for (int i = 0; i < 6; ++i) { place[i][0] = p[i][0]; place[i][1] = p[i][1]; }
-        nplace = 6;
-    }
+    int place[3][2], nplace = 0;
+    for (int ky = 0; ky < 3; ++ky) { place[nplace][0] = (2 - ky) * cout; place[nplace][1] = ky; ++nplace; }
     for (int pi = 0; pi < nplace; ++pi) {
         const int r0 = place[pi][0], ky = place[pi][1];
         for (int co = 0; co < cout; ++co)

@@ -10,7 +10,7 @@
 
 using namespace pc;
 
-__global__ void __launch_bounds__(128) probe(int N, int nmma, float* dout, long long* clk) {
+__global__ void __launch_bounds__(128) probe(int N, int nmma, float* dout, long long* clk, int varyA, int varyB, int varyD) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     __shared__ __align__(8) unsigned long long bar;
@@ -58,6 +58,23 @@ __global__ void __launch_bounds__(128) probe(int N, int nmma, float* dout, long 
         mbar_wait(mbar, 1);
         t1 = clock64();
         clk[0] = t1 - t0;
+        // second timing: operands vary from one MMA to the next (values are garbage; only the clock matters)
+        //   varyA: A columns cycle through 3 positions; varyB: B start address cycles through 3 row blocks / k offsets; varyD: D columns cycle
+        t0 = clock64();
+#pragma unroll 1
+        for (int i = 0; i < nmma; i += 3) {
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+                const uint32_t a = tbase + 64 + (varyA ? 8u * u : 0u);
+                const uint64_t b = bdesc + (uint64_t)(varyB ? ((varyB == 1 ? 2 * u : 64 * u)) : 0);   // 1: +32 B along K, 2: +1024 B (8 rows)
+                const uint32_t d = tbase + (varyD ? 8u * u : 0u);
+                umma_tf32_ts(d, a, b, idesc, 1u);
+            }
+        }
+        umma_commit(mbar);
+        mbar_wait(mbar, 0);
+        t1 = clock64();
+        clk[1] = t1 - t0;
     }
     __syncthreads();
     tc_fence_after();
@@ -73,15 +90,16 @@ __global__ void __launch_bounds__(128) probe(int N, int nmma, float* dout, long 
 }
 
 int main(int argc, char** argv) {
-    const int N = argc > 1 ? atoi(argv[1]) : 24, nmma = 512;
+    const int N = argc > 1 ? atoi(argv[1]) : 24, nmma = 510;
+    const int vA = argc > 2 ? atoi(argv[2]) : 0, vB = argc > 3 ? atoi(argv[3]) : 0, vD = argc > 4 ? atoi(argv[4]) : 0;
     float* dout; long long* clk;
-    cudaMalloc(&dout, 128 * 64 * 4); cudaMalloc(&clk, 8);
+    cudaMalloc(&dout, 128 * 64 * 4); cudaMalloc(&clk, 16);
     cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 1024);
-    probe<<<1, 128, 16 * 1024>>>(N, nmma, dout, clk);
+    probe<<<1, 128, 16 * 1024>>>(N, nmma, dout, clk, vA, vB, vD);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("N=%d: %s\n", N, cudaGetErrorString(e)); return 1; }
-    static float h[128 * 64]; long long c;
-    cudaMemcpy(h, dout, sizeof(h), cudaMemcpyDeviceToHost); cudaMemcpy(&c, clk, 8, cudaMemcpyDeviceToHost);
+    static float h[128 * 64]; long long c, c2;
+    cudaMemcpy(h, dout, sizeof(h), cudaMemcpyDeviceToHost); cudaMemcpy(&c, clk, 8, cudaMemcpyDeviceToHost); cudaMemcpy(&c2, clk + 1, 8, cudaMemcpyDeviceToHost);
     int bad = 0, touched_beyond = 0;
     for (int m = 0; m < 128; ++m)
         for (int n = 0; n < 64; ++n) {
@@ -93,7 +111,7 @@ int main(int argc, char** argv) {
                 if (got != ref) { if (bad < 4) printf("  mismatch m=%d n=%d got %g ref %g\n", m, n, got, ref); ++bad; }
             } else if (got != -777.f) ++touched_beyond;
         }
-    printf("N=%3d: %d mismatches, %d columns beyond N touched, %lld clk for %d MMAs -> %.2f clk per MMA\n", N, bad, touched_beyond, c, nmma,
-           (double)c / nmma);
+    printf("N=%3d: %d mismatches, %d columns beyond N touched, %lld clk for %d MMAs -> %.2f clk per MMA | vary A=%d B=%d D=%d: %.2f clk per MMA\n",
+           N, bad, touched_beyond, c, nmma, (double)c / nmma, vA, vB, vD, (double)c2 / nmma);
     return 0;
 }

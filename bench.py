@@ -658,7 +658,44 @@ def main():
         d2h = torch.tensor([float(host_map.numel() * 4 + R * 8)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(h2d); dist.all_reduce(d2h)
-        e2e = {"value": H * W / (float(tt.item()) / k_e2e), "unit": UNIT, "h2d_bytes_per_step": int(h2d.item()),
+        # what the host <-> device links of this box deliver when every rank copies at once (1 GiB up and 256 MiB down per rank,
+        # concurrently, pinned memory): the ceiling of any end-to-end number that moves 16 B/px up and 4 B/px down
+        pcie = None
+        try:
+            nb_up, nb_dn = 1 << 30, 1 << 28
+            hb_up = torch.empty(nb_up, dtype=torch.uint8, pin_memory=True)
+            hb_dn = torch.empty(nb_dn, dtype=torch.uint8, pin_memory=True)
+            db_up = torch.empty(nb_up, dtype=torch.uint8, device=dev)
+            db_dn = torch.empty(nb_dn, dtype=torch.uint8, device=dev)
+            s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+            res_bw = {}
+            for mode in ("h2d", "d2h", "both"):
+                barrier()
+                t1 = time.perf_counter()
+                for _ in range(2):
+                    if mode in ("h2d", "both"):
+                        with torch.cuda.stream(s_up):
+                            db_up.copy_(hb_up, non_blocking=True)
+                    if mode in ("d2h", "both"):
+                        with torch.cuda.stream(s_dn):
+                            hb_dn.copy_(db_dn, non_blocking=True)
+                torch.cuda.synchronize()
+                barrier()
+                dtm = torch.tensor([time.perf_counter() - t1], dtype=torch.float64, device=dev)
+                if world > 1:
+                    dist.all_reduce(dtm, op=dist.ReduceOp.MAX)
+                sec = float(dtm.item())
+                res_bw[mode] = {"h2d_gbs_all_ranks": (2 * nb_up * world / sec / 1e9) if mode != "d2h" else 0.0,
+                                "d2h_gbs_all_ranks": (2 * nb_dn * world / sec / 1e9) if mode != "h2d" else 0.0}
+            up, dn = res_bw["h2d"]["h2d_gbs_all_ranks"], res_bw["d2h"]["d2h_gbs_all_ranks"]
+            t_px = max(16.0 / (up * 1e9), 4.0 / (dn * 1e9))          # full duplex: the slower direction bounds a pixel
+            pcie = {"h2d_gbs_all_ranks_alone": up, "d2h_gbs_all_ranks_alone": dn, "concurrent": res_bw["both"],
+                    "bound_px_per_s": 1.0 / t_px,
+                    "note": "every rank copying at once; bound = 16 B/px up, 4 B/px down over these links (full duplex)"}
+            del hb_up, hb_dn, db_up, db_dn
+        except Exception as ex:
+            pcie = {"error": repr(ex)[:200]}
+        e2e = {"value": H * W / (float(tt.item()) / k_e2e), "unit": UNIT, "host_links": pcie, "h2d_bytes_per_step": int(h2d.item()),
                "d2h_bytes_per_step": int(d2h.item()), "steps": k_e2e,
                "api": "popcorn_b200.country.CountryEngine.run(RawRaster(pinned uint16 S2 + float32 S1), map_out=pinned host map) + sums.cpu()",
                "upload": "once_per_row" if upload_once else "per_window", "numa": numa_info,

@@ -17,6 +17,8 @@ namespace pc {
 
 constexpr int WT = 32;             // wgrad tile edge
 constexpr int WIP = WT + 3;        // staged input pitch: 34 columns used, odd pitch -> distinct banks per channel
+constexpr int WGP = WT * (WT + 1) + 1;   // gradient plane pitch: odd, so the `cout` planes a warp reads at one (r, c) sit in distinct banks
+                                   // (32 * 33 is a multiple of 32: every channel hit the same bank, an 8- to 16-way conflict on a quarter of the loads)
 
 struct WgradArgs {
     const float* a; long long a_cs; int a_rs; int a_H, a_W, a_oy, a_ox, a_reflect; unsigned a_chmap; int cin_a;
@@ -34,7 +36,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const __grid_constant__
     const int G = 256 / NP;                         // row groups (1, 2 or 4)
     float* xs = sm;                                 // [cin][34][WIP]
     float* gs = xs + cin * (WT + 2) * WIP;          // [cout][32][33]
-    float* red = gs + cout * WT * (WT + 1);         // [G][NP][10]
+    float* red = gs + cout * WGP;                   // [G][NP][10]
     const int tid = threadIdx.x;
     const int ty = blockIdx.x / a.tiles_x, tx = blockIdx.x - ty * a.tiles_x;
     const int x0 = tx * WT, y0 = ty * WT;
@@ -64,7 +66,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const __grid_constant__
     for (int i = tid; i < cout * WT * WT; i += 256) {
         const int c = i / (WT * WT), r = (i / WT) % WT, col = i % WT;
         const int vy = y0 + r, vx = x0 + col;
-        gs[(c * WT + r) * (WT + 1) + col] = (vy < a.H && vx < a.W) ? __ldg(a.g + c * a.g_cs + (long long)vy * a.g_rs + vx) : 0.f;
+        gs[c * WGP + r * (WT + 1) + col] = (vy < a.H && vx < a.W) ? __ldg(a.g + c * a.g_cs + (long long)vy * a.g_rs + vx) : 0.f;
     }
     __syncthreads();
     float acc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -74,7 +76,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const __grid_constant__
     if (grp < G) {
         const int rows = WT / G;
         const float* xc = xs + ci * (WT + 2) * WIP;
-        const float* gc = gs + co * WT * (WT + 1);
+        const float* gc = gs + co * WGP;
         for (int r = grp * rows; r < (grp + 1) * rows; ++r) {
             const float* x0r = xc + r * WIP;          // input rows r, r+1, r+2 hold image rows y-1, y, y+1
             const float* x1r = x0r + WIP;
@@ -259,7 +261,7 @@ extern "C" int pc_conv3x3_wgrad(const float* a, int cin_a, long long a_cs, int a
     A.partial = reinterpret_cast<float*>(round_up((long long)(uintptr_t)workspace, 256));
     const int tiles = A.tiles_x * cdiv(H, WT);
     const int G = 256 / (cin * cout);
-    const int smem = (cin * (WT + 2) * WIP + cout * WT * (WT + 1) + G * cin * cout * 10) * 4;
+    const int smem = (cin * (WT + 2) * WIP + cout * WGP + G * cin * cout * 10) * 4;
     cudaStream_t st = (cudaStream_t)stream;
     PC_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     {

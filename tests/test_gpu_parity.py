@@ -252,3 +252,35 @@ def test_full_tile_properties_2048(model):
     with torch.no_grad():
         ref = po.forward(sd, {"input": crop}, padding=False)["popdensemap"][0]
     assert max_rel(dens[512 + 40:768 - 40, 1024 + 40:1280 - 40].cpu(), ref[40:-40, 40:-40]) < TOL_PIXEL
+
+
+def test_bench_sized_window_3840x16384_crops_vs_oracle(model, sd):
+    """One merged window of the size bench.py runs (3840 x 16384: TMA maps and index arithmetic beyond 2^24 pixels, 30 column tiles
+    of 128 x 60 row tiles per job): interior crops — first / last column tiles, rows beyond the first tile, the far corner — against
+    the oracle run on the crop plus a 64-px frame (origins multiples of 4 keep the pool phase)."""
+    H, W = 3840, 16384
+    g = torch.Generator(device="cuda").manual_seed(1610)
+    x = torch.empty(1, 6, H, W, device="cuda")
+    for c in range(6):
+        low = torch.nn.functional.interpolate(torch.randn(1, 1, H // 64 + 2, W // 64 + 2, generator=g, device="cuda"), size=(H, W),
+                                              mode="bilinear", align_corners=True)[0, 0]
+        x[0, c] = 0.6 * low + 0.8 * torch.randn(H, W, generator=g, device="cuda")
+        del low
+    with torch.no_grad():
+        bu = ops.dda_forward(model._dda_pack("building_extractor"), x, model.p2d, ops.PC_DDA_BUILTUP)
+        feats = ops.dda_forward(model._dda_pack("unetmodel"), x, (0, 0, 0, 0), ops.PC_DDA_FEATURES)
+        dens, scale = ops.head_dense_forward(model._head_pack(tc=True), feats, bu, None, None, None, want_scale=True, tc=True)
+        del feats
+        F_, C = 64, 192
+        worst = 0.0
+        for y0, x0 in [(128, 128), (2048, 8192 - 64), (H - C - 2 * F_ - 4, W - C - 2 * F_ - 4), (1792, 16384 - 512), (3000, 4)]:
+            y0, x0 = y0 // 4 * 4, x0 // 4 * 4
+            crop = x[:, :, y0:y0 + C + 2 * F_, x0:x0 + C + 2 * F_].cpu()
+            ref = po.forward(sd, {"input": crop}, padding=False)
+            a = dens[0, y0 + F_:y0 + F_ + C, x0 + F_:x0 + F_ + C].cpu()
+            b = ref["popdensemap"][0][F_:-F_, F_:-F_]
+            worst = max(worst, max_rel(a, b))
+            assert max_rel(bu[0, 0, y0 + F_:y0 + F_ + C, x0 + F_:x0 + F_ + C].cpu(), ref["popdensemap"][0][F_:-F_, F_:-F_] * 0 +
+                           po.building_score(sd, crop)[0, 0][F_:-F_, F_:-F_]) < 1e-3
+        assert worst < TOL_PIXEL, worst
+        assert torch.equal(dens, scale * bu[:, 0])

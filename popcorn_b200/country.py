@@ -189,7 +189,13 @@ class RawRaster:
     [2, rows, W] float32, both on the device or both in pinned host memory.  ``s2_plane_map`` gives the plane of each
     output channel R,G,B,NIR (GeoTIFF band order B02,B03,B04,B08 -> ops.S2_FILE_TO_RGBN).  CountryEngine.run uploads
     16 B/pixel instead of 24 and converts + normalises on the device (csrc/ingest.cu), bit-identical to the reference's
-    .astype(float32) + apply_normalize (data/PopulationDataset.py:594-604, utils/utils.py:105-127)."""
+    .astype(float32) + apply_normalize (data/PopulationDataset.py:594-604, utils/utils.py:105-127).
+
+    PRECONDITION — no NaNs.  The reference fills NaNs per tile before the model sees them (interpolate_nan, fall back to the other
+    orbit, raise above 5 %: data/PopulationDataset.py:477-499, 526-551); that loader logic is out of this path's scope.
+    A NaN in S1 (swath edges) would spread through the 23-px receptive field of every window that contains it and turn the fp64
+    census sums of whole regions — and the all-reduced totals — into NaN.  Fill before constructing a RawRaster; ``assert_finite()``
+    checks it (one pass over S1, not on the hot path)."""
 
     def __init__(self, s2: torch.Tensor, s1: torch.Tensor, s2_plane_map: int = ops.S2_FILE_TO_RGBN, stats: Optional[dict] = None):
         if s2.dim() != 3 or s1.dim() != 3 or s2.shape[0] != 4 or s1.shape[0] != 2 or s2.shape[1:] != s1.shape[1:]:
@@ -204,6 +210,13 @@ class RawRaster:
 
     def is_pinned(self) -> bool:
         return self.s2.is_pinned() and self.s1.is_pinned()
+
+    def assert_finite(self) -> "RawRaster":
+        """Raise ValueError if S1 (or a float32 S2) holds NaN / Inf (see the class docstring); returns self."""
+        for name, t in (("S1", self.s1), ("S2", self.s2)):
+            if t.is_floating_point() and not bool(torch.isfinite(t).all()):
+                raise ValueError(f"RawRaster: {name} contains NaN / Inf — fill them first (reference: PopulationDataset.interpolate_nan)")
+        return self
 
 
 class CountryEngine:

@@ -20,6 +20,7 @@ from .dda import STAGE1_FEATS, load_checkpoint
 
 # forward head on tcgen05 (3xTF32, csrc/head_tc.cu) unless POPCORN_HEAD_TC=0 selects the fp32 SIMT kernel (csrc/head.cu)
 USE_TENSOR_CORE_HEAD = os.environ.get("POPCORN_HEAD_TC", "1") != "0"
+_CHECK_IDS = os.environ.get("POPCORN_CHECK_IDS", "0") == "1"
 
 
 class _SparseHeadFn(torch.autograd.Function):
@@ -27,12 +28,11 @@ class _SparseHeadFn(torch.autograd.Function):
     hand-written backward for the head parameters (model/popcorn.py:162-187 under unet_no_grad=True)."""
 
     @staticmethod
-    def forward(ctx, feats, builtup, idx, n_dev, n, head_in, *params):
-        sd = {f"head.{i}.{t}": p for (i, t), p in zip(((0, "weight"), (0, "bias"), (2, "weight"), (2, "bias"),
-                                                      (4, "weight"), (4, "bias"), (6, "weight"), (6, "bias")), params)}
-        hpack = weights.pack_head(sd)                      # fp32 pack: used by the backward's recompute
-        if USE_TENSOR_CORE_HEAD:
-            dens, scale_sel, pop = ops.head_sparse_forward(weights.pack_head_tc(sd), feats, builtup, idx, n_dev, n, tc=True)
+    def forward(ctx, feats, builtup, idx, n_dev, n, head_in, hpack, tcpack, *params):
+        # hpack / tcpack: the packed head weights (weights.pack_head / pack_head_tc of `params`), built by the caller BEFORE it waits for
+        # the selected-pixel count, so that their small launches overlap the DDA passes instead of following the host sync
+        if tcpack is not None:
+            dens, scale_sel, pop = ops.head_sparse_forward(tcpack, feats, builtup, idx, n_dev, n, tc=True)
         else:
             dens, scale_sel, pop = ops.head_sparse_forward(hpack, feats, builtup, idx, n_dev, n)
         ctx.save_for_backward(hpack, feats, builtup if builtup is not None else torch.empty(0, device=feats.device),
@@ -66,7 +66,7 @@ class _SparseHeadFn(torch.autograd.Function):
             gpack = ops.head_sparse_backward(hpack, feats, builtup, idx, n_dev, ctx.n, g_pop, 0.0, g_sel)
         g = weights.unpack_head_grad(gpack, ctx.head_in)
         grads = tuple(g[f"head.{i}.{t}"] for i in (0, 2, 4, 6) for t in ("weight", "bias"))
-        return (g_feats, None, None, None, None, None) + grads
+        return (g_feats, None, None, None, None, None, None, None) + grads
 
 
 class POPCORN(nn.Module):
@@ -205,7 +205,13 @@ class POPCORN(nn.Module):
     # ------------------------------------------------------------------------------------------
     def forward(self, inputs, train=False, padding=True, return_features=True,
                 encoder_no_grad=False, unet_no_grad=False, sparse=False):
-        """See model/popcorn.py:100-193.  ``train`` and ``return_features`` are accepted and unused, as there."""
+        """See model/popcorn.py:100-193.  ``train`` and ``return_features`` are accepted and unused, as there.
+
+        Region ids: ``admin_mask`` holds integral ids (float32 in the reference's samples, data/PopulationDataset.py:445; -1 = collate
+        padding, 0 = background) that float32 represents exactly, i.e. |id| <= 2**24, and ``census_idx`` integers in the same range.
+        Every path compares them as the reference does (``admin_mask == census_idx``): the kernels take int32 / float32 copies of these
+        exactly-representable values, so the dense, sparse and autograd paths select the same pixels.  POPCORN_CHECK_IDS=1 verifies
+        the precondition (one pass + host sync) and raises ValueError on fractional or out-of-range ids."""
         X = inputs["input"]
         if X.dim() != 4:
             raise ValueError("Input tensor must have shape (batch_size, channels, height, width)")
@@ -219,6 +225,10 @@ class POPCORN(nn.Module):
         if builtup.dtype != torch.float32 or not builtup.is_contiguous():
             builtup = builtup.float().contiguous()
 
+        if _CHECK_IDS and "admin_mask" in inputs.keys():
+            am = inputs["admin_mask"]
+            if am.is_floating_point() and not bool(((am == am.round()) & (am.abs() <= 2 ** 24)).all()):
+                raise ValueError("admin_mask must hold integral region ids with |id| <= 2**24 (float32-exact)")
         aux = {}
         if sparse:
             sparsity_mask, _ = self.get_sparsity_mask(inputs)
@@ -246,14 +256,19 @@ class POPCORN(nn.Module):
                 idx = torch.arange(B * H * W, dtype=torch.int32, device=X.device)
                 n_dev = torch.full((1,), B * H * W, dtype=torch.int32, device=X.device)
                 n = B * H * W
-            else:
-                n = int(n_dev.item())      # the reference's boolean indexing synchronises here as well
             params = self._head_params()
+            with torch.no_grad():          # weight packs first: their launches queue behind the DDA passes while the host waits for n
+                hsd = {f"head.{i}.{t}": p for (i, t), p in zip(((0, "weight"), (0, "bias"), (2, "weight"), (2, "bias"),
+                                                               (4, "weight"), (4, "bias"), (6, "weight"), (6, "bias")), params)}
+                hpack = weights.pack_head(hsd)                       # fp32 pack: the backward recomputes the forward from it
+                tcpack = weights.pack_head_tc(hsd) if USE_TENSOR_CORE_HEAD else None
+            if sparse:
+                n = int(n_dev.item())      # the reference's boolean indexing synchronises here as well
             if need_grad:
-                pop_sel, dens, scale_sel = _SparseHeadFn.apply(feats, bu, idx, n_dev, n, self.head_input_dim, *params)
+                pop_sel, dens, scale_sel = _SparseHeadFn.apply(feats, bu, idx, n_dev, n, self.head_input_dim, hpack, tcpack, *params)
             else:
                 with torch.no_grad():
-                    pop_sel, dens, scale_sel = _SparseHeadFn.apply(feats, bu, idx, n_dev, n, self.head_input_dim, *params)
+                    pop_sel, dens, scale_sel = _SparseHeadFn.apply(feats, bu, idx, n_dev, n, self.head_input_dim, hpack, tcpack, *params)
             popdensemap = dens
             if self.occupancymodel:
                 aux["scale"] = scale_sel if sparse else scale_sel.view(B, H, W)

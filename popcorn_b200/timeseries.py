@@ -118,6 +118,10 @@ class TimeSeriesEngine:
                 raise ValueError(f"frame {t} belongs to this rank (frame group {self.frame_group}) but was not supplied")
             out = self.engine.run(fr, ids, R, row_offset=row_offset, group=row_group)
             m, s = out["map"], out["std"]
+            if s is not None:
+                # a pixel seen once (one member, no tile overlap) has no ensemble std: the engine's map holds run_eval.py's raw sum of
+                # squares there (its division is masked by count > 1, :140-154); the notebook's torch.std of one sample is NaN
+                s = torch.where(out["count"] == 1, torch.full((), float("nan"), device=s.device), s)     # never-visited frame pixels stay 0
             totals[t] = m.sum(dtype=torch.float64)
             if self.row_shard == 0 or self.F == 1:
                 sums[t] = out["sums"]              # all-reduced inside the frame group: one copy per group enters the frame-axis sum

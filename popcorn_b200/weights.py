@@ -115,21 +115,39 @@ def _split_tf32(w: torch.Tensor):
     return hi, w - hi
 
 
+_SWIZZLE_DST = {}
+
+
+def _swizzle_dst(K: int, device) -> torch.Tensor:
+    """Flat destination index of every element of a [64, ceil(K/32)*32] matrix in the swizzled image (cached per K and device: the
+    census train step re-packs the head every iteration, the index arithmetic does not change)."""
+    key = (K, str(device))
+    dst = _SWIZZLE_DST.get(key)
+    if dst is None:
+        N = 64
+        katoms = (K + 31) // 32
+        n = torch.arange(N, device=device).view(N, 1)
+        k = torch.arange(katoms * 32, device=device).view(1, -1)
+        kk = k % 32
+        pos = (((kk // 4) ^ (n % 8)) * 4 + kk % 4)
+        dst = ((k // 32) * (N * 32) + n * 32 + pos).reshape(-1)
+        _SWIZZLE_DST[key] = dst
+    return dst
+
+
 def _swizzle_k_major_128b(w: torch.Tensor) -> torch.Tensor:
     """[N=64, K] fp32 -> flat image [ceil(K/32)][64 rows][32 floats]: row n of a 32-float K-atom is 128 B, its eight
     16-byte chunks XOR-swizzled with (n % 8) (Swizzle<3,4,3>); 8-row groups are 1024 B apart (the descriptor's SBO)."""
     N, K = w.shape
     assert N == 64
     katoms = (K + 31) // 32
-    wp = torch.zeros(N, katoms * 32, dtype=w.dtype, device=w.device)
-    wp[:, :K] = w
-    n = torch.arange(N, device=w.device).view(N, 1)
-    k = torch.arange(katoms * 32, device=w.device).view(1, -1)
-    kk = k % 32
-    pos = (((kk // 4) ^ (n % 8)) * 4 + kk % 4)
-    dst = (k // 32) * (N * 32) + n * 32 + pos
-    out = torch.zeros(katoms * N * 32, dtype=w.dtype, device=w.device)
-    out[dst.reshape(-1)] = wp.reshape(-1)
+    if katoms * 32 != K:
+        wp = torch.zeros(N, katoms * 32, dtype=w.dtype, device=w.device)
+        wp[:, :K] = w
+    else:
+        wp = w
+    out = torch.empty(katoms * N * 32, dtype=w.dtype, device=w.device)
+    out[_swizzle_dst(K, w.device)] = wp.reshape(-1)          # a permutation of all elements (padding columns carry zeros)
     return out
 
 

@@ -145,7 +145,8 @@ def test_cpu_tensors_are_rejected_loudly(sd):
 @pytest.mark.parametrize("cin,cout", [(2, 8), (4, 8), (8, 16), (16, 16), (32, 8)])
 def test_conv_tc_weight_image_layout(cin, cout):
     """Host packer of the tcgen05 conv weights (include/popcorn_b200.h "Tensor-core weight section"): de-swizzling the
-    image gives back the 16-row weight windows (Cout 16: [W_ky2|W_ky1|W_ky0]; Cout 8: X0..X3) with hi + lo == w exactly, hi a TF32 number, zero rows/columns as padding."""
+    image gives back the rows [W_ky2 | W_ky1 | W_ky0] (Cout rows each: 48 for Cout 16, 24 for Cout 8) with hi + lo == w exactly, hi a
+    TF32 number, zero columns as padding."""
     L = _lib.lib()
     g = torch.Generator().manual_seed(cin * 31 + cout)
     w = torch.randn(cout, cin, 3, 3, generator=g)
@@ -156,7 +157,7 @@ def test_conv_tc_weight_image_layout(cin, cout):
     _lib.check(L.pc_conv_tc_pack_layer(flat.data_ptr(), cin, cout, img.data_ptr()))
     krow = (3 * cin + 7) // 8 * 8
     katoms = (krow + 31) // 32
-    nrows = 64 if cout == 8 else 48
+    nrows = 3 * cout
     mat = katoms * nrows * 32
     assert n % 64 == 0 and n >= 2 * mat + 16
     mats = img[:2 * mat].view(2, katoms, nrows, 32)
@@ -168,12 +169,8 @@ def test_conv_tc_weight_image_layout(cin, cout):
     hi, lo = de[0], de[1]
     want = torch.zeros(nrows, katoms * 32)
     wk = lambda ky: w[:, :, ky, :].permute(0, 2, 1).reshape(cout, 3 * cin)        # [co][kx*cin+ci]
-    if cout == 16:      # [W_ky2 | W_ky1 | W_ky0]
-        for ky in range(3):
-            want[16 * (2 - ky): 16 * (2 - ky) + 16, :3 * cin] = wk(ky)
-    else:               # X0 = [W_ky2 | W_ky1], X1 = [0 | W_ky2], X2 = [W_ky0 | 0], X3 = [W_ky1 | W_ky0]
-        for r0, ky in ((0, 2), (8, 1), (24, 2), (32, 0), (48, 1), (56, 0)):
-            want[r0: r0 + 8, :3 * cin] = wk(ky)
+    for ky in range(3):     # [W_ky2 | W_ky1 | W_ky0]
+        want[cout * (2 - ky): cout * (2 - ky) + cout, :3 * cin] = wk(ky)
     assert torch.equal(hi + lo, want)
     assert torch.equal(hi.view(torch.int32) & 0x1FFF, torch.zeros_like(hi, dtype=torch.int32))
     assert torch.equal(img[2 * mat: 2 * mat + cout], b) and float(img[2 * mat + cout: 2 * mat + 16].abs().sum()) == 0

@@ -491,7 +491,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="popcorn_b200", choices=["popcorn_b200", "reference"])
-    ap.add_argument("--rows-per-strip", type=int, default=2)
+    ap.add_argument("--rows-per-strip", type=int, default=3, help="tile-rows per merged window (first and last strip: 1, see --edge-strip-rows)")
+    ap.add_argument("--edge-strip-rows", type=int, default=1, help="tile-rows of the first and of the last strip of a rank")
     ap.add_argument("--no-merge", action="store_true", help="run the reference's 2048^2 tile grid tile by tile")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
@@ -502,6 +503,7 @@ def main():
     ap.add_argument("--per-window-upload", action="store_true",
                     help="e2e: upload every window separately (halo rows cross PCIe twice) instead of each raw row once")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not bind the rank to its GPU's NUMA node")
+    ap.add_argument("--no-e2e-pipeline", action="store_true", help="e2e: synchronise after every raster instead of prefetching the next one")
     ap.add_argument("--skip-ensemble", action="store_true")
     ap.add_argument("--skip-gpu-baseline", action="store_true")
     ap.add_argument("--skip-alone", action="store_true", help="N>1: skip the one-rank-alone run of rank 0's slab")
@@ -546,7 +548,8 @@ def main():
     balance = not args.no_balance
     upload_once = not args.per_window_upload
     eng = ct.CountryEngine([model], H, W, merge=not args.no_merge, rows_per_strip=args.rows_per_strip, rank=rank, world=world,
-                           first_strip_rows=1, balance=balance, upload_once=upload_once)     # short first strip: a streamed run starts computing after a small upload
+                           first_strip_rows=args.edge_strip_rows, last_strip_rows=args.edge_strip_rows, balance=balance,
+                           upload_once=upload_once)     # short first / last strips: compute starts after a small upload, little map left to ship at the end
     i0, i1 = eng.in_rows
     lo, hi = eng.out_rows
     raster = synth_raster_slab(i1 - i0, W, i0, dev)
@@ -635,21 +638,41 @@ def main():
         del raster
         torch.cuda.empty_cache()
 
-        def step_e2e():
+        pipelined = upload_once and not args.no_e2e_pipeline
+        sums_host = [torch.empty(R, dtype=torch.float64, pin_memory=True) for _ in range(8)]
+        k_slot = [0]
+
+        def step_e2e(more: bool):
+            """One raster through the public API: host bands in, host map + census sums out.  Pipelined (default): the NEXT raster's
+            upload is queued (prefetch) before this step's result is read, and the tail of this step's map download overlaps the next
+            step's first windows — how a stream of rasters (seasonal frames, successive countries) runs; every step's copies still
+            happen inside the timed region, and the region ends with all downloads complete."""
             with torch.no_grad():
                 o = eng.run(host_raster, ids, R, row_offset=i0, map_out=host_map)    # finished strips stream back during compute
-                s = o["sums"].cpu()
-            eng.wait_download()
-            torch.cuda.synchronize()
+                if pipelined and more:
+                    eng.prefetch(host_raster, i0)
+                if pipelined:      # the step's result: census sums -> pinned host memory, asynchronously (read after the region's final sync)
+                    s = sums_host[k_slot[0] % len(sums_host)]
+                    k_slot[0] += 1
+                    s.copy_(o["sums"], non_blocking=True)
+                else:
+                    s = o["sums"].cpu()
+            if not pipelined:
+                eng.wait_download()
+                torch.cuda.synchronize()
             return s
 
-        step_e2e()
+        step_e2e(False)
+        eng.wait_download()
         barrier()
         t0 = time.perf_counter()
-        k_e2e = max(2, min(args.steps, 3))
-        for _ in range(k_e2e):
-            s_host = step_e2e()
-        barrier()
+        k_e2e = max(3, min(args.steps, 5))
+        if pipelined:
+            eng.prefetch(host_raster, i0)
+        for k_ in range(k_e2e):
+            s_host = step_e2e(k_ + 1 < k_e2e)
+        eng.wait_download()
+        barrier()                                  # barrier() synchronises the device: every step's sums and map rows are on the host now
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
@@ -699,6 +722,7 @@ def main():
                "d2h_bytes_per_step": int(d2h.item()), "steps": k_e2e,
                "api": "popcorn_b200.country.CountryEngine.run(RawRaster(pinned uint16 S2 + float32 S1), map_out=pinned host map) + sums.cpu()",
                "upload": "once_per_row" if upload_once else "per_window", "numa": numa_info,
+               "pipelined": pipelined, "pipeline_note": "double-buffered input slabs: raster k+1 uploads while raster k computes; all copies inside the timed region" if pipelined else None,
                "host_input": "raw on-disk dtypes: S2 uint16 x4 (file band order) + S1 float32 x2 = 16 B/px; converted + normalised on the device"}
         del host_raster, host_s2, host_s1, host_map
     else:

@@ -53,11 +53,29 @@ def grid_origins(n: int, patch: int = PATCH, overlap: int = OVERLAP) -> List[int
     return list(range(0, n - patch, patch - 2 * overlap))
 
 
+def strip_sizes(n_rows: int, rows_per_strip: int, first_strip_rows: Optional[int] = None, last_strip_rows: Optional[int] = None) -> List[int]:
+    """Tile-rows per merged strip: a short first strip (a streamed run starts computing after a small upload), `rows_per_strip` in
+    the middle (long kernels, little halo recompute), a short last strip (little map left to ship when the compute ends)."""
+    sizes, left = [], n_rows
+    if first_strip_rows and left > 0:
+        k = min(first_strip_rows, left)
+        sizes.append(k)
+        left -= k
+    tail = min(last_strip_rows, left) if (last_strip_rows and left > 0) else 0
+    left -= tail
+    while left > 0:
+        k = min(rows_per_strip, left)
+        sizes.append(k)
+        left -= k
+    if tail:
+        sizes.append(tail)
+    return sizes
+
+
 def plan_windows(H: int, W: int, patch: int = PATCH, overlap: int = OVERLAP, merge: bool = True,
-                 rows_per_strip: int = 2, first_strip_rows: Optional[int] = None) -> List[Window]:
+                 rows_per_strip: int = 2, first_strip_rows: Optional[int] = None, last_strip_rows: Optional[int] = None) -> List[Window]:
     """All windows covering the raster the way get_patch_indices does (PopulationDataset.py:294-316).
-    first_strip_rows: tile-rows of the FIRST merged strip (default rows_per_strip) — a short first strip lets a streamed
-    run start computing after a small upload instead of waiting for a whole strip."""
+    first_strip_rows / last_strip_rows: tile-rows of the first / last merged strip (default rows_per_strip), see strip_sizes."""
     if H < patch or W < patch:
         raise ValueError(f"raster {H}x{W} is smaller than the inference patch {patch}")
     xs, ys = grid_origins(H, patch, overlap), grid_origins(W, patch, overlap)
@@ -75,8 +93,7 @@ def plan_windows(H: int, W: int, patch: int = PATCH, overlap: int = OVERLAP, mer
         return wins
     width = (ys[-1] + patch) if ys else 0
     starts, i0 = [], 0
-    while i0 < len(xs):
-        k = min(first_strip_rows if (i0 == 0 and first_strip_rows) else rows_per_strip, len(xs) - i0)
+    for k in strip_sizes(len(xs), rows_per_strip, first_strip_rows, last_strip_rows):
         starts.append((i0, k))
         i0 += k
     for i0, k in starts:
@@ -225,7 +242,7 @@ class CountryEngine:
     def __init__(self, models, H: int, W: int, patch: int = PATCH, overlap: int = OVERLAP, merge: bool = True,
                  rows_per_strip: int = 2, rank: int = 0, world: int = 1, want_scale: bool = True,
                  want_std: bool = True, first_strip_rows: Optional[int] = None, balance: bool = False,
-                 balance_unit: int = 256, upload_once: bool = False):
+                 balance_unit: int = 256, upload_once: bool = False, last_strip_rows: Optional[int] = None):
         self.models = list(models) if isinstance(models, (list, tuple)) else [models]
         self.H, self.W, self.patch, self.overlap = H, W, patch, overlap
         self.rank, self.world = rank, world
@@ -233,7 +250,8 @@ class CountryEngine:
         self.upload_once = upload_once      # opt-in: host RawRaster rows cross PCIe once (see _run_resident)
         merge = merge and can_merge(patch, overlap)      # otherwise fall back to the reference tile grid
         self.merged = merge
-        all_w = plan_windows(H, W, patch, overlap, merge, rows_per_strip if merge else 1, first_strip_rows if merge else None)
+        all_w = plan_windows(H, W, patch, overlap, merge, rows_per_strip if merge else 1, first_strip_rows if merge else None,
+                             last_strip_rows if merge else None)
         n_rows = len(grid_origins(H, patch, overlap))
         if balance and world > 1:     # opt-in: unit-row granularity instead of whole strips (plan_balanced_shards)
             if not merge:
@@ -298,6 +316,8 @@ class CountryEngine:
         ev.record(torch.cuda.current_stream(dev))
         self._d2h_stream.wait_event(ev)
         ops.copy_d2h(map_out[r0:r1], self._maps[0][r0:r1], self._d2h_stream.cuda_stream)
+        if self._maps[0].is_cuda:
+            self._maps[0].record_stream(self._d2h_stream)      # the next run re-allocates the maps: this block is not reused before the copy is done
 
     def run(self, raster: torch.Tensor, ids: Optional[torch.Tensor], R: int, row_offset: int = 0,
             group=None, finalize: bool = True, map_out: Optional[torch.Tensor] = None, reduce: bool = True):
@@ -315,7 +335,8 @@ class CountryEngine:
                 raise ValueError("map_out needs finalize=True")
             if map_out.is_cuda or (map_out.numel() and not map_out.is_pinned()) or tuple(map_out.shape) != (self.out_rows[1] - self.out_rows[0], self.W):
                 raise ValueError("map_out must be a pinned host tensor of the owned map shape")
-        self.wait_download()                      # a previous run's download must not race the maps' re-allocation
+        # a previous run's download may still be in flight: its map block is protected by record_stream (_ship_rows), and copies into
+        # the same host buffer stay ordered on the download stream — so consecutive runs pipeline (prefetch() + run() + run() ...)
         self._map_out, self._shipped = map_out, 0
         dev = torch.device("cuda", torch.cuda.current_device())
         maps = self.alloc_maps(dev)
@@ -432,29 +453,38 @@ class CountryEngine:
         px = sum(w.h * w.w for w in wins)
         self.h2d_bytes = px * (4 * raster.s2.element_size() + 2 * 4) if raw else px * 6 * 4
 
-    def _run_resident(self, raster: "RawRaster", row_offset: int, dev, chunk_rows: int = 512):
-        """Host RawRaster -> device, every input row ONCE: the rank's rows are copied in row chunks (copy stream, in row
-        order) into device slabs that keep the on-disk dtypes (16 B/px: Uganda on 8 GPUs = 5 GB per rank), and each window
-        is converted + normalised from the slab as soon as the chunks it needs have landed.  The window-by-window upload
-        of _run_streamed sends the overlapping halos and the right-column windows again (1.18-1.20x the unique rows),
-        which is what bounds the end-to-end rate once 8 GPUs share the host's PCIe complex."""
+    def _slab_set(self, k: int, raster: "RawRaster", dev):
+        """Device slabs (on-disk dtypes, this rank's input rows) of buffer set k, allocated once and kept across runs."""
+        i0, i1 = self.in_rows
+        rows, W = i1 - i0, self.W
+        if not hasattr(self, "_slabs"):
+            self._slabs = [None, None]
+            self._slab_free = [None, None]      # event: the last ingest kernel that read set k has been queued
+        cur = self._slabs[k]
+        if cur is None or cur[0].dtype != raster.s2.dtype or cur[0].shape != (4, rows, W):
+            self._slabs[k] = (torch.empty(4, rows, W, dtype=raster.s2.dtype, device=dev), torch.empty(2, rows, W, dtype=torch.float32, device=dev))
+            self._slab_free[k] = None
+        return self._slabs[k]
+
+    def _upload_slabs(self, k: int, raster: "RawRaster", row_offset: int, dev, chunk_rows: int):
+        """Queue the upload of this rank's raw rows into slab set k on the copy stream, in row order; -> one 'landed' event per chunk."""
         if not raster.is_pinned():
             raise RuntimeError("host rasters must be pinned (torch.Tensor.pin_memory) for the streamed path")
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=dev)
         cs, main = self._copy_stream, torch.cuda.current_stream(dev)
-        wins = self.windows
         i0, i1 = self.in_rows
         rows, W = i1 - i0, self.W
         if i0 - row_offset < 0 or i1 - row_offset > raster.shape[1] or raster.shape[2] != W:
             raise ValueError("raster does not hold this rank's input rows")
-        d2 = torch.empty(4, rows, W, dtype=raster.s2.dtype, device=dev)
-        d1 = torch.empty(2, rows, W, dtype=torch.float32, device=dev)
+        d2, d1 = self._slab_set(k, raster, dev)
         start = torch.cuda.Event()
-        start.record(main)                         # the slabs' memory may still be read by earlier work of this stream
+        start.record(main)                         # first use: the slabs' memory may still be read by earlier work of this stream
         landed = []
         with torch.cuda.stream(cs):
             cs.wait_event(start)
+            if self._slab_free[k] is not None:
+                cs.wait_event(self._slab_free[k])  # the previous run on this set has consumed it
             for a in range(0, rows, chunk_rows):
                 b = min(rows, a + chunk_rows)
                 h0 = i0 - row_offset + a
@@ -463,16 +493,56 @@ class CountryEngine:
                 ev = torch.cuda.Event()
                 ev.record(cs)
                 landed.append(ev)
+        return landed
+
+    def prefetch(self, raster: "RawRaster", row_offset: int = 0, chunk_rows: int = 512):
+        """Start uploading the NEXT raster (pinned host RawRaster, upload_once engines) while the current run still computes: the
+        copies go to the other slab set on the copy stream; the next ``run(raster, ...)`` with the same object picks them up.
+        A stream of rasters (seasonal frames, successive countries) then pays the upload bubble once, not per raster."""
+        if not (isinstance(raster, RawRaster) and not raster.is_cuda and self.upload_once):
+            raise ValueError("prefetch() needs a pinned host RawRaster and an engine built with upload_once=True")
+        if not self.windows:
+            return
+        dev = torch.device("cuda", torch.cuda.current_device())
+        k = 1 - getattr(self, "_slab_cur", 1)
+        landed = self._upload_slabs(k, raster, row_offset, dev, chunk_rows)
+        self._prefetched = (raster, row_offset, k, landed, chunk_rows)
+
+    def _run_resident(self, raster: "RawRaster", row_offset: int, dev, chunk_rows: int = 512):
+        """Host RawRaster -> device, every input row ONCE: the rank's rows are copied in row chunks (copy stream, in row
+        order) into device slabs that keep the on-disk dtypes (16 B/px: Uganda on 8 GPUs = 5 GB per rank), and each window
+        is converted + normalised from the slab as soon as the chunks it needs have landed.  The window-by-window upload
+        of _run_streamed sends the overlapping halos and the right-column windows again (1.18-1.20x the unique rows),
+        which is what bounds the end-to-end rate once 8 GPUs share the host's PCIe complex.  Two slab sets alternate, so
+        ``prefetch()`` can upload the next raster during this run."""
+        main = torch.cuda.current_stream(dev)
+        wins = self.windows
+        i0, i1 = self.in_rows
+        rows, W = i1 - i0, self.W
+        pf = getattr(self, "_prefetched", None)
+        if pf is not None and pf[0] is raster and pf[1] == row_offset:
+            _, _, k, landed, chunk_rows = pf
+        else:
+            k = 1 - getattr(self, "_slab_cur", 1)
+            landed = self._upload_slabs(k, raster, row_offset, dev, chunk_rows)
+        self._prefetched = None
+        self._slab_cur = k
+        d2, d1 = self._slabs[k]
         mh, mw = max(w.h for w in wins), max(w.w for w in wins)
-        xnorm = torch.empty(6 * mh * mw, dtype=torch.float32, device=dev)
-        for k, win in enumerate(wins):
+        if getattr(self, "_xnorm", None) is None or self._xnorm.numel() < 6 * mh * mw or self._xnorm.device != dev:
+            self._xnorm = torch.empty(6 * mh * mw, dtype=torch.float32, device=dev)
+        xnorm = self._xnorm
+        for k_w, win in enumerate(wins):
             r0 = win.y0 - i0
             main.wait_event(landed[(r0 + win.h - 1) // chunk_rows])        # copies are in row order on one stream
             x = xnorm[: 6 * win.h * win.w].view(6, win.h, win.w)
             ops.ingest_normalize(d2[:, r0: r0 + win.h, win.x0: win.x0 + win.w], d1[:, r0: r0 + win.h, win.x0: win.x0 + win.w],
                                  x, raster.s2_plane_map, raster.stats)
             self._forward_window(x[None], win)
-            self._after_window(k, dev)
+            self._after_window(k_w, dev)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self._slab_free[k] = ev                    # a later upload into this set waits for the last ingest kernel
         self.h2d_bytes = rows * W * (4 * raster.s2.element_size() + 2 * 4)
 
 

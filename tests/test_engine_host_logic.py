@@ -193,3 +193,34 @@ def test_time_series_frames_x_row_strips_over_gloo(world, T):
             assert abs(float(totals[t]) - want) < 1e-6 * want
             assert torch.allclose(sums[t], wants[t][3], rtol=1e-9)
         assert abs(stot - float(season.double().sum())) < 1e-6 * float(season.double().sum())
+
+
+def test_prefetch_pipelines_consecutive_rasters(monkeypatch, world_data):
+    """CountryEngine.prefetch(): the next raster is uploaded into the other slab set while the current one is (logically) still
+    computing; run() on the prefetched object uploads nothing again and gives the result of a fresh engine."""
+    H, W, ps, ov, R, s2_file, s1, norm, ids, (want_map, _, want_cnt, want_sums) = world_data
+    log = fd.install(monkeypatch)
+    eng = ct.CountryEngine([fd.FakeModel()], H, W, ps, ov, merge=True, rows_per_strip=3, first_strip_rows=1, last_strip_rows=1,
+                           upload_once=True)
+    lo, hi = eng.out_rows
+    a = ct.RawRaster(s2_file.clone(), s1.clone())
+    b = ct.RawRaster(s2_file.clone(), (s1 * 0.5).contiguous())
+    out_a = eng.run(a, ids[lo:hi].contiguous(), R)
+    map_a, sums_a = out_a["map"].clone(), out_a["sums"].clone()
+    assert torch.allclose(map_a, want_map[lo:hi], rtol=1e-6, atol=1e-6) and torch.allclose(sums_a, want_sums, rtol=1e-9)
+    del log[:]
+    eng.prefetch(b)
+    up = sum(e[1] for e in log if e[0] == "h2d")
+    assert up == H * W * 16                       # the whole raster went up at prefetch time, into the OTHER slab set
+    del log[:]
+    out_b = eng.run(b, ids[lo:hi].contiguous(), R)
+    assert sum(e[1] for e in log if e[0] == "h2d") == 0, "run() must use the prefetched slabs"
+    fresh = ct.CountryEngine([fd.FakeModel()], H, W, ps, ov, merge=True, rows_per_strip=2, upload_once=True)
+    ref_b = fresh.run(ct.RawRaster(s2_file.clone(), (s1 * 0.5).contiguous()), ids[lo:hi].contiguous(), R)
+    assert torch.equal(out_b["map"], ref_b["map"]) and torch.equal(out_b["count"], ref_b["count"])
+    assert torch.allclose(out_b["sums"], ref_b["sums"], rtol=1e-12)
+    # a raster that was not prefetched is uploaded by run() itself, again into the set that is free
+    del log[:]
+    out_a2 = eng.run(a, ids[lo:hi].contiguous(), R)
+    assert sum(e[1] for e in log if e[0] == "h2d") == H * W * 16
+    assert torch.equal(out_a2["map"], map_a)

@@ -86,3 +86,36 @@ def test_upload_once_equals_the_per_window_upload(model, world, rank):
     assert torch.equal(b[3], b[0].cpu())
     assert torch.allclose(a[2], b[2], rtol=1e-6)
     assert b[4] == (i1 - i0) * W * 16 and b[4] < a[4]
+
+
+def test_prefetched_runs_pipeline_and_match(model):
+    """prefetch() + run() + run(): consecutive rasters through double-buffered slabs, the previous map still downloading while the
+    next raster computes — same maps / sums / host copies as isolated runs."""
+    H, W, ps, ov = 900, 456, 128, 32
+    ids = po.synthetic_regions(H, W, 30).cuda()
+    rasters = []
+    for seed in (35, 36, 37):
+        s2_file, s1 = po.synthetic_raw(H, W, seed=seed)
+        rasters.append(ct.RawRaster(s2_file.pin_memory(), s1.pin_memory()))
+    ref = []
+    with torch.no_grad():
+        for r in rasters:
+            e = ct.CountryEngine([model], H, W, ps, ov, merge=True, rows_per_strip=2, upload_once=True)
+            lo, hi = e.out_rows
+            o = e.run(r, ids[lo:hi].contiguous(), 31)
+            ref.append((o["map"].clone(), o["sums"].clone()))
+        eng = ct.CountryEngine([model], H, W, ps, ov, merge=True, rows_per_strip=3, first_strip_rows=1, last_strip_rows=1, upload_once=True)
+        lo, hi = eng.out_rows
+        hosts = [torch.full((hi - lo, W), float("nan")).pin_memory() for _ in rasters]
+        eng.prefetch(rasters[0])
+        outs = []
+        for k, r in enumerate(rasters):
+            o = eng.run(r, ids[lo:hi].contiguous(), 31, map_out=hosts[k])
+            if k + 1 < len(rasters):
+                eng.prefetch(rasters[k + 1])
+            outs.append((o["map"], o["sums"]))          # no synchronisation between the rasters
+        eng.wait_download()
+        torch.cuda.synchronize()
+    for k in range(len(rasters)):
+        assert torch.equal(outs[k][0], ref[k][0]) and torch.equal(hosts[k], ref[k][0].cpu())
+        assert torch.allclose(outs[k][1], ref[k][1], rtol=1e-6)

@@ -130,7 +130,9 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
     constexpr unsigned FULL = 0xffffffffu;
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment as an OFFSET into the shared array: a pointer that went through uintptr_t arithmetic loses its address space
+    // and every access through it compiles to a generic LD/ST (the conv stagers' 24 loads per pixel: ~400 of their ~500 cycles per row)
+    uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const ConvJob& job = p.jobs[blockIdx.y];
     const int tid = threadIdx.x, lane = tid & 31, warp = uniform_warp_idx();
     const float* bias = reinterpret_cast<const float*>(sm + G::OFF_BIAS);

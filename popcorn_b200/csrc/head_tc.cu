@@ -77,7 +77,9 @@ constexpr int TC2_SMEM_BYTES = (OFF_PART2 + 1024 + 1024) > 116 * 1024 ? (OFF_PAR
 template <int K1, bool SPARSE>
 __global__ void __launch_bounds__(HTHREADS, 1) head_tc_kernel(const __grid_constant__ HeadArgs a) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment as an OFFSET into the shared array: a pointer that went through uintptr_t arithmetic loses its address space
+    // and every access through it compiles to a generic LD/ST (the conv stagers' 24 loads per pixel: ~400 of their ~500 cycles per row)
+    uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const float* vec = reinterpret_cast<const float*>(sm + OFF_VEC);
     const float* b1 = vec, *b2 = vec + 64, *b3 = vec + 128, *w4 = vec + 192, *b4 = vec + 256;
     const uint32_t bars = smem_u32(sm + OFF_BARS2);

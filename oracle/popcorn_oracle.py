@@ -244,11 +244,11 @@ def train_loss_terms(output: dict, y: Tensor, scale_regularization: float = 0.01
     return terms
 
 
-def head_grad_terms(sd: Dict[str, Tensor], inputs: dict, y: Tensor, grid=None, **fw):
-    """Oracle gradients of the census train step w.r.t. head.*: (total {name: grad}, [per-term {name: grad}], output).
-    One forward; the terms of train_loss_terms are back-propagated one by one (test infrastructure)."""
-    names = [k for k in sd if k.startswith("head.")]
-    sdg = {k: (v.clone().requires_grad_(True) if k.startswith("head.") else v) for k, v in sd.items()}
+def grad_terms(sd: Dict[str, Tensor], inputs: dict, y: Tensor, keys, grid=None, **fw):
+    """Oracle gradients of the census train step w.r.t. the tensors named in `keys`: (total {name: grad}, [per-term {name: grad}],
+    output).  One forward; the terms of train_loss_terms are back-propagated one by one (test infrastructure)."""
+    names = list(keys)
+    sdg = {k: (v.clone().requires_grad_(True) if k in names else v) for k, v in sd.items()}
     out = forward(sdg, inputs, sparse=True, grid=grid, **fw)
     terms = train_loss_terms(out, y)
     per = []
@@ -257,6 +257,11 @@ def head_grad_terms(sd: Dict[str, Tensor], inputs: dict, y: Tensor, grid=None, *
         per.append({k: (torch.zeros_like(sdg[k]) if gi is None else gi) for k, gi in zip(names, g)})
     total = {k: sum(p[k] for p in per) for k in names}
     return total, per, out
+
+
+def head_grad_terms(sd: Dict[str, Tensor], inputs: dict, y: Tensor, grid=None, **fw):
+    """grad_terms for the head parameters (the census step with unet_no_grad=True, run_train.py:201-230)."""
+    return grad_terms(sd, inputs, y, [k for k in sd if k.startswith("head.")], grid=grid, **fw)
 
 
 def grad_parity_errors(got: Dict[str, Tensor], total: Dict[str, Tensor], per) -> Tuple[float, float]:

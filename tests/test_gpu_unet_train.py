@@ -7,7 +7,7 @@ import torch
 
 from popcorn_b200.model import unet_train
 from oracle import popcorn_oracle as po
-from util import TOL_REGION, build_model, golden_state_dict, max_rel
+from util import TOL_GRAD, TOL_REGION, build_model, golden_state_dict, max_rel
 
 pytestmark = pytest.mark.gpu
 torch.backends.cudnn.allow_tf32 = False
@@ -40,25 +40,27 @@ def test_unet_finetune_gradients_match_autograd_of_the_reference_restatement(sha
     po.train_loss(out, y.cuda()).backward()
 
     keys = ["unetmodel." + k for k in unet_train.trainable_keys()] + [k for k in sd if k.startswith("head.")]
-    sdg = {k: (v.clone().requires_grad_(True) if k in keys else v) for k, v in sd.items()}
-    ref = po.forward(sdg, {"input": x, "admin_mask": admin, "census_idx": cidx}, padding=False, sparse=True, grid=grid,
-                     encoder_no_grad=encoder_no_grad)
-    po.train_loss(ref, y).backward()
+    total, per, ref = po.grad_terms(sd, {"input": x, "admin_mask": admin, "census_idx": cidx}, y, keys, grid=grid, padding=False,
+                                    encoder_no_grad=encoder_no_grad)
 
     assert max_rel(out["popcount"], ref["popcount"], floor_frac=1.0) < TOL_REGION
     params = dict(model.named_parameters())
     encoder = ("inc.", "down_seq.")
-    checked = 0
+    checked, got = 0, {}
     for k in keys:
-        g, r = params[k].grad, sdg[k].grad
+        g, r = params[k].grad, total[k]
         if encoder_no_grad and k.startswith("unetmodel.") and any(e in k for e in encoder):
             assert g is None or float(g.abs().max()) == 0.0, k
-            assert r is None
+            assert float(r.abs().max()) == 0.0
             continue
-        assert g is not None and r is not None, k
+        assert g is not None, k
         assert g.shape == r.shape, k
-        assert max_rel(g, r, floor_frac=2e-2) < 2e-2, (k, float((g.cpu() - r).abs().max()), float(r.abs().max()))
+        got[k] = g
         checked += 1
+    # errors against the gradient scale of the loss terms (oracle.grad_parity_errors; these batches of a few thousand pixels are
+    # exposed to single ReLU-knee flips, hence the element-wise bar of 2x)
+    e_norm, e_elem = po.grad_parity_errors(got, total, per)
+    assert e_norm < TOL_GRAD and e_elem < 2 * TOL_GRAD, (e_norm, e_elem)
     assert checked >= (24 if encoder_no_grad else 48)
     # BN affine parameters are frozen by freeze_bn_layers (networks.py:184-189): no gradient
     assert all(p.grad is None for n, p in params.items() if n.startswith("unetmodel.") and n.split(".")[-2] in ("1", "4"))

@@ -18,6 +18,28 @@
 
 namespace pc {
 
+#ifndef PC_HEAD_SPIN
+#define PC_HEAD_SPIN 0           // 1: poll the hand-off barriers with mbarrier.test_wait instead of the suspending try_wait
+#endif
+#if PC_HEAD_SPIN
+#define HEAD_WAIT mbar_wait
+#else
+#define HEAD_WAIT mbar_wait_sleep
+#endif
+#ifndef PC_HEAD_EXP
+#define PC_HEAD_EXP 0            // timing experiments (results wrong on purpose): 1 = no feature loads, 2 = no output stores, 4 = no builtup load
+#endif
+#ifndef PC_HEAD_PROBE
+#define PC_HEAD_PROBE 0          // 1: CTA 0 accumulates per-role cycle counters (development only)
+#endif
+#if PC_HEAD_PROBE
+__device__ long long g_head_dbg[32];
+#define HP_T(v) const long long v = clock64()
+#define HP_ADD(slot, a, b) do { if (blockIdx.x == 0) hp_acc[slot] += (b) - (a); } while (0)
+#else
+#define HP_T(v)
+#define HP_ADD(slot, a, b)
+#endif
 constexpr int TM = 128;          // pixels per tile
 constexpr int HT = 256;          // threads per CTA: two warps per TMEM lane quarter
 constexpr uint32_t IDESC = umma_idesc_tf32(128, 64);
@@ -48,16 +70,16 @@ __device__ __forceinline__ void issue_layer(uint32_t tD, uint32_t tAhi, uint32_t
 
 // hidden-layer epilogue of one thread: its 32 columns of D -> relu(D + bias) -> (hi, lo) -> A operand of the next layer
 __device__ __forceinline__ void epilogue_hidden(uint32_t tD, uint32_t tAhi, uint32_t tAlo, const float* bias) {
-    uint32_t v[2][16];
-#pragma unroll
-    for (int q = 0; q < 2; ++q) tmem_ld16(tD + 16 * q, v[q]);      // both loads in flight, one wait
-    tc_wait_ld();
+    // 16 columns at a time, hi split in place: 32 live registers (the kernel is capped at 96 by its 17 warps: registers are
+    // allocated per four warps, 65 536 / 640 threads)
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-        uint32_t hi[16], lo[16];
+        uint32_t v[16], lo[16];
+        tmem_ld16(tD + 16 * q, v);
+        tc_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) split_tf32(fmaxf(__uint_as_float(v[q][i]) + bias[16 * q + i], 0.f), hi[i], lo[i]);
-        tmem_st16(tAhi + 16 * q, hi);
+        for (int i = 0; i < 16; ++i) split_tf32(fmaxf(__uint_as_float(v[i]) + bias[16 * q + i], 0.f), v[i], lo[i]);
+        tmem_st16(tAhi + 16 * q, v);
         tmem_st16(tAlo + 16 * q, lo);
     }
 }
@@ -74,7 +96,7 @@ constexpr int OFF_TMEM2 = OFF_BARS2 + 32;
 constexpr int OFF_PART2 = OFF_TMEM2 + 16;        // float[2][128]
 constexpr int TC2_SMEM_BYTES = (OFF_PART2 + 1024 + 1024) > 116 * 1024 ? (OFF_PART2 + 1024 + 1024) : 116 * 1024;   // > half an SM: one CTA per SM
 
-template <int K1, bool SPARSE>
+template <int K1, bool SPARSE, bool SMALL>
 __global__ void __launch_bounds__(HTHREADS, 1) head_tc_kernel(const __grid_constant__ HeadArgs a) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment as an OFFSET into the shared array: a pointer that went through uintptr_t arithmetic loses its address space
@@ -123,27 +145,34 @@ __global__ void __launch_bounds__(HTHREADS, 1) head_tc_kernel(const __grid_const
         float* part = reinterpret_cast<float*>(sm + OFF_PART2) + 128 * c;
         uint32_t ph = 0;                                 // phase counter of both barriers of this context
 
-        struct Px { long long i; bool valid; int b; long long boff, ooff, ioff; };
-        auto locate = [&](long long tile, long long& foff) {
-            Px q;
-            q.i = tile * TM + px;
-            q.valid = tile < ntiles && q.i < total;
-            q.b = 0; q.boff = 0; q.ooff = 0; q.ioff = 0; foff = 0;
-            if (q.valid) {
-                const long long p = SPARSE ? (long long)__ldg(a.idx + q.i) : q.i;
-                q.b = (int)(p / HW);
-                const long long r = p - (long long)q.b * HW;
-                if (SPARSE) {
-                    foff = q.b * a.f_bs + r; q.boff = p; q.ooff = p;
-                } else {
-                    const int y = (int)(r / a.W), x = (int)(r - (long long)y * a.W);
-                    foff = q.b * a.f_bs + (long long)y * a.f_rs + x;
-                    q.boff = q.b * a.bu_bs + (long long)y * a.bu_rs + x;
-                    q.ooff = q.b * a.o_bs + (long long)y * a.o_rs + x;
-                    q.ioff = q.b * a.id_bs + (long long)y * a.id_rs + x;
-                }
+        // Between the phases of a tile only the pixel's linear index travels in registers; (image, row, column) and the tensor offsets
+        // are re-derived where they are used.  32-bit divisions whenever the batch has fewer than 2^31 pixels (always, for the sparse
+        // index list): the 64-bit software division costs ~150 instructions and registers the epilogues need.
+        // SMALL (chosen by the host: fewer than 2^31 pixels in the batch — always, for the sparse index list) selects 32-bit divisions
+        // at compile time: as a run-time select the compiler evaluated BOTH sides, i.e. two ~150-instruction 64-bit software
+        // divisions per call and three calls per tile and thread.
+        struct Pos { int b, y, x; long long r; };
+        auto decompose = [&](long long p) {
+            Pos q;
+            if (SMALL) { q.b = (int)((uint32_t)p / (uint32_t)HW); q.r = (long long)((uint32_t)p - (uint32_t)q.b * (uint32_t)HW); }
+            else { q.b = (int)(p / HW); q.r = p - (long long)q.b * HW; }
+            q.y = 0; q.x = 0;
+            if (!SPARSE) {
+                if (SMALL) q.y = (int)((uint32_t)q.r / (uint32_t)a.W);
+                else q.y = (int)(q.r / a.W);
+                q.x = (int)(q.r - (long long)q.y * a.W);
             }
             return q;
+        };
+        auto pixel_of = [&](long long tile, bool& valid) -> long long {     // linear pixel index (dense) / compacted position's pixel (sparse)
+            const long long i = tile * TM + px;
+            valid = tile < ntiles && i < total;
+            if (!valid) return 0;
+            return SPARSE ? (long long)__ldg(a.idx + i) : i;
+        };
+        auto feat_offset = [&](long long p) -> long long {
+            const Pos q = decompose(p);
+            return SPARSE ? q.b * a.f_bs + q.r : q.b * a.f_bs + (long long)q.y * a.f_rs + q.x;
         };
         auto hand_over = [&]() {                         // TMEM writes of this warp are done -> one arrival on a_ready[c]
             tc_wait_st();
@@ -151,21 +180,24 @@ __global__ void __launch_bounds__(HTHREADS, 1) head_tc_kernel(const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive(a_ready(c));
         };
-        auto wait_d = [&]() { mbar_wait_sleep(d_ready(c), ph & 1u); ++ph; tc_fence_after(); };
+        auto wait_d = [&]() { HEAD_WAIT(d_ready(c), ph & 1u); ++ph; tc_fence_after(); };
 
-        float fcur[CH], fnext[CH];
-        long long foff0;
+#if PC_HEAD_PROBE
+        long long hp_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+        float fcur[CH];        // ONE register set: consumed at the top of a tile, refilled (next tile) while layer 2 runs — no copy, a
+                               // MOV of a register an outstanding load still has to fill would wait for DRAM
         long long tile = 2ll * blockIdx.x + c;
-        Px cur = locate(tile, foff0);
+        bool valid;
+        long long p_cur = pixel_of(tile, valid);
+        {
+            const long long foff0 = valid ? feat_offset(p_cur) : 0;
 #pragma unroll
-        for (int k = 0; k < CH; ++k) fcur[k] = (cur.valid && stager) ? __ldg(a.feats + foff0 + (long long)(c_lo + k) * a.f_cs) : 0.f;
+            for (int k = 0; k < CH; ++k) fcur[k] = (valid && stager) ? __ldg(a.feats + foff0 + (long long)(c_lo + k) * a.f_cs) : 0.f;
+        }
 
 #pragma unroll 1
         for (; tile < ntiles; tile += stride) {
-            const long long i = cur.i;
-            const bool valid = cur.valid;
-            const int b = cur.b;
-            const long long boff = cur.boff, ooff = cur.ooff, ioff = cur.ioff;
             // ---- layer-1 A operand: this pixel's features (this thread's channel half), split, into TMEM ----
             if (stager) {
 #pragma unroll
@@ -177,58 +209,95 @@ __global__ void __launch_bounds__(HTHREADS, 1) head_tc_kernel(const __grid_const
                     tmem_st8(tAlo + lane_off + c_lo + c0, lo);
                 }
             }
+            HP_T(h0);
             hand_over();                                 // -> issuer: layer 1 of this tile may run
-            // ---- prefetch the next tile's features while the UMMAs run ----
-            long long foffn;
-            const Px nxt = locate(tile + stride, foffn);
-#pragma unroll
-            for (int k = 0; k < CH; ++k) fnext[k] = (nxt.valid && stager) ? __ldg(a.feats + foffn + (long long)(c_lo + k) * a.f_cs) : 0.f;
+            HP_T(h1);
             wait_d();
+            HP_T(h2);
             epilogue_hidden(tD + lane_off + col_off, tAhi + lane_off + col_off, tAlo + lane_off + col_off, b1 + col_off);
+            HP_T(g0);
             hand_over();
+            HP_T(g1);
+            HP_ADD(8, h2, g0); HP_ADD(9, g0, g1);
+            // ---- while layer 2's UMMAs run (this warp would only wait): locate the next tile, start loading its features, and fetch
+            //      THIS tile's builtup score, so that neither the address arithmetic nor a DRAM round trip sits between two UMMA phases
+            bool valid_n;
+            const long long p_nxt = pixel_of(tile + stride, valid_n);
+            {
+                const long long foffn = valid_n ? feat_offset(p_nxt) : 0;
+#pragma unroll
+                for (int k = 0; k < CH; ++k) fcur[k] = (valid_n && stager) ? ((PC_HEAD_EXP & 1) ? (float)(foffn & 7) : __ldg(a.feats + foffn + (long long)(c_lo + k) * a.f_cs)) : 0.f;
+            }
+            HP_T(g2);
+            HP_ADD(10, g1, g2);
+            float bu_cur = 1.f;
+            if (half == 0 && valid && a.builtup) {
+                const Pos q = decompose(p_cur);
+                bu_cur = (PC_HEAD_EXP & 4) ? (float)q.x : __ldg(a.builtup + (SPARSE ? p_cur : q.b * a.bu_bs + (long long)q.y * a.bu_rs + q.x));
+            }
+            HP_T(h3);
             wait_d();
+            HP_T(h4);
             epilogue_hidden(tD + lane_off + col_off, tAhi + lane_off + col_off, tAlo + lane_off + col_off, b2 + col_off);
             hand_over();
+            HP_T(h5);
             wait_d();
+            HP_T(h6);
+            HP_ADD(0, h0, h1); HP_ADD(1, h1, h2); HP_ADD(2, h2, h3); HP_ADD(3, h3, h4); HP_ADD(4, h4, h5); HP_ADD(5, h5, h6); HP_ADD(7, h6 - 1, h6);
             // ---- output layer on the CUDA cores: o = b4 + sum_n relu(D3[n] + b3[n]) * w4[n]; each thread sums its 32 hidden
             //      units, the upper half hands its partial sum over through shared memory ----
             float o = 0.f;
             {
-                uint32_t v[2][16];
-                tmem_ld16(tD + lane_off + col_off, v[0]);
-                tmem_ld16(tD + lane_off + col_off + 16, v[1]);
-                tc_wait_ld();
 #pragma unroll
-                for (int q = 0; q < 2; ++q)
+                for (int q = 0; q < 2; ++q) {
+                    uint32_t v[16];
+                    tmem_ld16(tD + lane_off + col_off + 16 * q, v);
+                    tc_wait_ld();
 #pragma unroll
                     for (int k = 0; k < 16; ++k)
-                        o = fmaf(fmaxf(__uint_as_float(v[q][k]) + b3[col_off + 16 * q + k], 0.f), w4[col_off + 16 * q + k], o);
+                        o = fmaf(fmaxf(__uint_as_float(v[k]) + b3[col_off + 16 * q + k], 0.f), w4[col_off + 16 * q + k], o);
+                }
             }
             tc_fence_before();   // D is overwritten by the next tile's layer-1 UMMAs, which follow this context's next hand_over
+            HP_T(f0);
             if (half == 1) part[px] = o;
             asm volatile("bar.sync %0, %1;" ::"r"(1 + c), "r"(HWORK) : "memory");      // the 8 warps of this context only
+            HP_T(f1);
+            HP_ADD(11, h6, f0); HP_ADD(12, f0, f1);
             if (half == 0) {
                 const float s = fmaxf(b4[0] + o + part[px], 0.f);
                 float d = 0.f; int bin = -1;
                 if (valid) {
-                    d = a.builtup ? s * __ldg(a.builtup + boff) : s;
+                    const Pos q = decompose(p_cur);
+                    const long long ooff = SPARSE ? p_cur : q.b * a.o_bs + (long long)q.y * a.o_rs + q.x;
+                    d = a.builtup ? s * bu_cur : s;
+                    if (!(PC_HEAD_EXP & 2) || d == 123.456f) {
                     a.dens[ooff] = d;
-                    if (SPARSE) { if (a.scale_sel) a.scale_sel[i] = s; }
+                    if (SPARSE) { if (a.scale_sel) a.scale_sel[tile * TM + px] = s; }
                     else if (a.scale) a.scale[ooff] = s;
+                    }
                     if (a.sums) {
-                        if (SPARSE) bin = b;
-                        else if (a.census_idx) bin = (a.ids == nullptr || __ldg(a.ids + ioff) == __ldg(a.census_idx + b)) ? b : -1;
+                        const long long ioff = SPARSE ? 0 : q.b * a.id_bs + (long long)q.y * a.id_rs + q.x;
+                        if (SPARSE) bin = q.b;
+                        else if (a.census_idx) bin = (a.ids == nullptr || __ldg(a.ids + ioff) == __ldg(a.census_idx + q.b)) ? q.b : -1;
                         else if (a.ids) { const int id = __ldg(a.ids + ioff); bin = (id >= 0 && id < a.R) ? id : -1; }
-                        else bin = b;
+                        else bin = q.b;
                     }
                 }
                 if (a.sums) bin_add(a.sums, bin, d);
             }
+            HP_T(f2);
             asm volatile("bar.sync %0, %1;" ::"r"(1 + c), "r"(HWORK) : "memory");      // part[] may be rewritten by the next tile
-            cur = nxt;
-#pragma unroll
-            for (int k = 0; k < CH; ++k) fcur[k] = fnext[k];
+            HP_T(f3);
+            HP_ADD(13, f1, f2); HP_ADD(14, f2, f3);
+            p_cur = p_nxt;
+            valid = valid_n;
+            HP_T(h7);
+            HP_ADD(6, h6, h7);
         }
+#if PC_HEAD_PROBE
+        if (blockIdx.x == 0 && tid == 0) for (int q = 0; q < 16; ++q) g_head_dbg[q] = hp_acc[q];
+#endif
     } else if (elect_one()) {
         // =========================== UMMA issuer: strict alternation between the two contexts ===========================
         long long n[2];
@@ -238,22 +307,34 @@ __global__ void __launch_bounds__(HTHREADS, 1) head_tc_kernel(const __grid_const
         }
         const long long rounds = n[0] > n[1] ? n[0] : n[1];
         uint32_t ph[2] = {0, 0};
+#if PC_HEAD_PROBE
+        long long hp_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
 #pragma unroll 1
         for (long long k = 0; k < rounds; ++k) {
-#pragma unroll
+#pragma unroll 1
             for (int layer = 0; layer < 3; ++layer) {
-#pragma unroll
+                // not unrolled over the contexts / layers: six inlined copies of issue_layer need more descriptor registers than the
+                // kernel's 96 and the issuing thread then reloads spilled operands from local memory between two UMMAs
+#pragma unroll 1
                 for (int c = 0; c < 2; ++c) {
                     if (k >= n[c]) continue;
                     const uint32_t tD = tbase + 256u * c, tAhi = tD + 64, tAlo = tD + 128;
-                    mbar_wait_sleep(a_ready(c), ph[c] & 1u); ++ph[c];
+                    HP_T(i0);
+                    HEAD_WAIT(a_ready(c), ph[c] & 1u); ++ph[c];
                     tc_fence_after();
+                    HP_T(i1);
                     if (layer == 0) issue_layer<K1>(tD, tAhi, tAlo, sW + OFF_W1HI, sW + OFF_W1LO, d_ready(c));
                     else if (layer == 1) issue_layer<HN>(tD, tAhi, tAlo, sW + OFF_W2HI, sW + OFF_W2LO, d_ready(c));
                     else issue_layer<HN>(tD, tAhi, tAlo, sW + OFF_W3HI, sW + OFF_W3LO, d_ready(c));
+                    HP_T(i2);
+                    HP_ADD(layer == 0 ? 0 : 2, i0, i1); HP_ADD(layer == 0 ? 1 : 3, i1, i2); HP_ADD(7, i2 - 1, i2);
                 }
             }
         }
+#if PC_HEAD_PROBE
+            if (blockIdx.x == 0) for (int q = 0; q < 8; ++q) g_head_dbg[16 + q] = hp_acc[q];
+#endif
     }
 
     tc_fence_before();
@@ -261,9 +342,9 @@ __global__ void __launch_bounds__(HTHREADS, 1) head_tc_kernel(const __grid_const
     if (warp == 16) tmem_dealloc(tbase, 512);
 }
 
-template <int K1, bool SPARSE>
-static int launch_head_tc(const HeadArgs& a, long long total_bound, cudaStream_t st) {
-    auto k = head_tc_kernel<K1, SPARSE>;
+template <int K1, bool SPARSE, bool SMALL>
+static int launch_head_tc_impl(const HeadArgs& a, long long total_bound, cudaStream_t st) {
+    auto k = head_tc_kernel<K1, SPARSE, SMALL>;
     PC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES));
     long long tiles = (total_bound + TM - 1) / TM;
     const int maxg = num_sms();              // persistent: one CTA per SM (it owns all 512 TMEM columns), two tile contexts each
@@ -278,11 +359,25 @@ static int launch_head_tc(const HeadArgs& a, long long total_bound, cudaStream_t
     return 0;
 }
 
+template <int K1, bool SPARSE>
+static int launch_head_tc(const HeadArgs& a, long long total_bound, cudaStream_t st) {
+    const long long HW = SPARSE ? a.HW : (long long)a.H * a.W;
+    const bool small = total_bound < 0x7fffffffll && HW * (SPARSE ? 1 : a.B) < 0x7fffffffll && HW < 0x7fffffffll;
+    return small ? launch_head_tc_impl<K1, SPARSE, true>(a, total_bound, st) : launch_head_tc_impl<K1, SPARSE, false>(a, total_bound, st);
+}
+
 }  // namespace pc
 
 using namespace pc;
 
 extern "C" int pc_head_tc_pack_bytes(void) { return TC_PACK_BYTES; }
+#if PC_HEAD_PROBE
+extern "C" int pc_debug_head_counters(long long* out32) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out32, pc::g_head_dbg, sizeof(long long) * 32);
+    return 0;
+}
+#endif
 
 extern "C" int pc_head_dense_forward_tc(const void* tcpack, int head_in, const float* feats, long long f_bstride,
                                         long long f_cstride, int f_rstride, const float* builtup, long long bu_bstride,

@@ -28,7 +28,7 @@ def bench_name(kernel: str):
     m = re.search(r"convt2x2_kernel<(\d+)>", k)
     if m:
         return f"convt2x2<{m[1]}>"
-    m = re.search(r"head_tc_kernel<(\d+),\(?(?:bool\))?(\d+|true|false)>", k)
+    m = re.search(r"head_tc_kernel<(?:\(int\))?(\d+),(?:\(bool\))?(\d+|true|false)[,>]", k)
     if m:
         return "head_tc<sparse>" if m[2] in ("1", "true") else "head_tc<dense>"
     for pat, name in (("head_backward_kernel", "head_backward"), ("head_bwd_reduce", "head_backward"), ("accumulate_kernel", "accumulate"),

@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(HTHREADS, 1) head_tc_kernel(const __grid_const
         const int c_lo = K1 >= 16 ? half * CH : 0;
         const uint32_t lane_off = (uint32_t)((wl & 3) * 32) << 16;     // a warp may touch TMEM lanes 32*(warp%4) .. +31
         const uint32_t tD = tbase + 256u * c, tAhi = tD + 64, tAlo = tD + 128;
+        const uint32_t tA1hi = tD + 192, tA1lo = tD + 208;      // layer-1 operand (features) of the NEXT tile: own columns, staged early
         const uint32_t col_off = (uint32_t)(32 * half);
         float* part = reinterpret_cast<float*>(sm + OFF_PART2) + 128 * c;
         uint32_t ph = 0;                                 // phase counter of both barriers of this context
@@ -196,21 +197,24 @@ __global__ void __launch_bounds__(HTHREADS, 1) head_tc_kernel(const __grid_const
             for (int k = 0; k < CH; ++k) fcur[k] = (valid && stager) ? __ldg(a.feats + foff0 + (long long)(c_lo + k) * a.f_cs) : 0.f;
         }
 
-#pragma unroll 1
-        for (; tile < ntiles; tile += stride) {
-            // ---- layer-1 A operand: this pixel's features (this thread's channel half), split, into TMEM ----
+        // layer-1 A operand: this pixel's features (this thread's channel half), split, into the context's A1 columns
+        auto stage_features = [&]() {
             if (stager) {
 #pragma unroll
                 for (int c0 = 0; c0 < CH; c0 += 8) {
                     uint32_t hi[8], lo[8];
 #pragma unroll
                     for (int k = 0; k < 8; ++k) split_tf32(fcur[c0 + k], hi[k], lo[k]);
-                    tmem_st8(tAhi + lane_off + c_lo + c0, hi);
-                    tmem_st8(tAlo + lane_off + c_lo + c0, lo);
+                    tmem_st8(tA1hi + lane_off + c_lo + c0, hi);
+                    tmem_st8(tA1lo + lane_off + c_lo + c0, lo);
                 }
             }
+        };
+        if (tile < ntiles) { stage_features(); hand_over(); }      // first tile of this context: layer 1 may run
+
+#pragma unroll 1
+        for (; tile < ntiles; tile += stride) {
             HP_T(h0);
-            hand_over();                                 // -> issuer: layer 1 of this tile may run
             HP_T(h1);
             wait_d();
             HP_T(h2);
@@ -240,6 +244,10 @@ __global__ void __launch_bounds__(HTHREADS, 1) head_tc_kernel(const __grid_const
             HP_T(h4);
             epilogue_hidden(tD + lane_off + col_off, tAhi + lane_off + col_off, tAlo + lane_off + col_off, b2 + col_off);
             hand_over();
+            // ---- while layer 3's UMMAs run: the NEXT tile's features (loaded during layer 2) go into the A1 columns, which no UMMA in
+            //      flight reads; the issuer learns about them only after this tile's accumulator has been read (below)
+            const bool more = tile + stride < ntiles;
+            if (more) stage_features();
             HP_T(h5);
             wait_d();
             HP_T(h6);
@@ -258,7 +266,8 @@ __global__ void __launch_bounds__(HTHREADS, 1) head_tc_kernel(const __grid_const
                         o = fmaf(fmaxf(__uint_as_float(v[k]) + b3[col_off + 16 * q + k], 0.f), w4[col_off + 16 * q + k], o);
                 }
             }
-            tc_fence_before();   // D is overwritten by the next tile's layer-1 UMMAs, which follow this context's next hand_over
+            // D has been read and the next tile's A1 is staged: layer 1 of the next tile may run NOW, under this tile's combine + stores
+            if (more) hand_over(); else tc_fence_before();
             HP_T(f0);
             if (half == 1) part[px] = o;
             asm volatile("bar.sync %0, %1;" ::"r"(1 + c), "r"(HWORK) : "memory");      // the 8 warps of this context only
@@ -324,7 +333,7 @@ __global__ void __launch_bounds__(HTHREADS, 1) head_tc_kernel(const __grid_const
                     HEAD_WAIT(a_ready(c), ph[c] & 1u); ++ph[c];
                     tc_fence_after();
                     HP_T(i1);
-                    if (layer == 0) issue_layer<K1>(tD, tAhi, tAlo, sW + OFF_W1HI, sW + OFF_W1LO, d_ready(c));
+                    if (layer == 0) issue_layer<K1>(tD, tD + 192, tD + 208, sW + OFF_W1HI, sW + OFF_W1LO, d_ready(c));
                     else if (layer == 1) issue_layer<HN>(tD, tAhi, tAlo, sW + OFF_W2HI, sW + OFF_W2LO, d_ready(c));
                     else issue_layer<HN>(tD, tAhi, tAlo, sW + OFF_W3HI, sW + OFF_W3LO, d_ready(c));
                     HP_T(i2);

@@ -71,13 +71,27 @@ constexpr int TCN = 16;            // UMMA N (output channels, zero-padded)
 #ifndef PC_TC_ND8
 #define PC_TC_ND8 8                // accumulator ring depth (output rows in flight) of the Cout = 8 kernels
 #endif
-constexpr int NGROUP = 2;          // stager groups / epilogue groups (4 warps each: one per TMEM lane quarter)
-constexpr int WS_THREADS = (4 * NGROUP * 2 + 3) * 32;    // stagers + epilogue + 2 MMA warps + TMA warp
-constexpr int W_EPI0 = 4 * NGROUP, W_MMA = 8 * NGROUP, W_TMA = 8 * NGROUP + 2;
-constexpr int TMEM_ALL = 512;
+// Occupancy: <8,0,8,store> and <8,0,8,dot> run TWO CTAs per SM (15 warps each: 2 stager groups, ONE epilogue group, 2 MMA warps, TMA;
+// 256 TMEM columns) — two complete pipelines whose hand-off latencies interleave, the same remedy as the head's two tile contexts:
+// 9.8 -> 7.9 and 12.0 -> 11.5 ms per bench step.  Measured and NOT adopted for <8,0,8,pool> (+10 %: one epilogue group does the pooling,
+// 64-register cap spills), <8,0,16> (+5 %) and <8,8,8> (+26 %: only two A buffers fit 256 columns); those keep one 19-warp CTA.
+// PC_TC_OCC2 bit 0: store / dot, bit 1: pool, bit 2: <8,0,16>, bit 3: <8,8,8> (A/B builds).
+#ifndef PC_TC_OCC2
+#define PC_TC_OCC2 1
+#endif
+__host__ __device__ constexpr int tc_occ(int cin_a, int cin_b, int cout, int epi) {
+    return (cin_a == 8 && cin_b == 0 && cout == 8 && (epi == EPI_STORE || epi == EPI_DOT) && (PC_TC_OCC2 & 1)) ? 2
+         : (cin_a == 8 && cin_b == 0 && cout == 8 && epi == EPI_POOL && (PC_TC_OCC2 & 2)) ? 2
+         : (cin_a == 8 && cin_b == 0 && cout == 16 && (PC_TC_OCC2 & 4)) ? 2
+         : (cin_a == 8 && cin_b == 8 && cout == 8 && (PC_TC_OCC2 & 8)) ? 2 : 1;
+}
 
-template <int CIN, int COUT>
+template <int CIN, int COUT, int OCC = 1>
 struct TcGeom {
+    static constexpr int TMEM_COLS = 512 / OCC;                 // tensor-memory columns of one CTA
+    static constexpr int NEG = OCC == 2 ? 1 : 2;                // epilogue groups (4 warps each: one per TMEM lane quarter)
+    static constexpr int THREADS = (8 + 4 * NEG + 3) * 32;      // 2 stager groups + epilogue groups + 2 MMA warps + TMA warp
+    static constexpr int W_EPI0 = 8, W_MMA = 8 + 4 * NEG, W_TMA = W_MMA + 2;
     static constexpr int SLOTW = COUT == 8 ? 8 : 16;            // accumulator columns per output row
     static constexpr int ND = COUT == 8 ? PC_TC_ND8 : 8;        // accumulator ring: output rows in flight
     // MMA issue: two issuers that own alternate output row pairs (more UMMAs in flight per SM: one thread sustains one UMMA per
@@ -93,7 +107,7 @@ struct TcGeom {
     static constexpr int OFF_BIAS = 2 * BMAT;                   // matrices: [hi, lo]
     static constexpr int IMG_BYTES = OFF_BIAS + 64;             // + bias[16]
     static constexpr int A_COLS = 2 * KROW;                     // one A buffer: hi at [0, KROW), lo at [KROW, 2*KROW)
-    static constexpr int NA_FIT = (TMEM_ALL - ND * SLOTW) / A_COLS;
+    static constexpr int NA_FIT = (TMEM_COLS - ND * SLOTW) / A_COLS;
     static constexpr int NA = NA_FIT >= 8 ? 8 : NA_FIT >= 4 ? 4 : 2;   // A buffers (power of two): Cin 8 -> 8 (four row pairs in flight:
                                                                 // the stagers run ahead of the UMMAs of the two batches before), Cin 16 -> 4, Cin 32 -> 2
     static constexpr int D_COL0 = NA * A_COLS;                  // accumulator slots of 16 columns
@@ -106,11 +120,11 @@ struct TcGeom {
     static constexpr int OFF_CTW = (OFF_TMEM + 16 + 15) / 16 * 16;  // EPI_CONVT: [COUT][4][COUT] + bias[COUT] floats of the transposed conv
     static constexpr int CTW_FLOATS = COUT * 4 * COUT + COUT;
     static constexpr int SMEM_NEED = OFF_CTW + CTW_FLOATS * 4 + 1024;
-    // > half of the SM's shared memory: exactly one CTA per SM (it owns all 512 TMEM columns)
-    static constexpr int SMEM_BYTES = SMEM_NEED > 116 * 1024 ? SMEM_NEED : 116 * 1024;
+    // OCC 1: > half of the SM's shared memory, i.e. exactly one CTA per SM (it owns all 512 TMEM columns); OCC 2: what it needs
+    static constexpr int SMEM_BYTES = OCC == 2 ? SMEM_NEED : (SMEM_NEED > 116 * 1024 ? SMEM_NEED : 116 * 1024);
     static_assert(NA_FIT >= 2, "TMEM budget");
-    static_assert(D_COL0 % 16 == 0 && D_COL0 + ND * SLOTW <= TMEM_ALL, "accumulator ring placement");
-    static_assert(STAGE_BYTES % 128 == 0 && SMEM_BYTES <= 227 * 1024, "shared memory layout");
+    static_assert(D_COL0 % 16 == 0 && D_COL0 + ND * SLOTW <= TMEM_COLS, "accumulator ring placement");
+    static_assert(STAGE_BYTES % 128 == 0 && SMEM_BYTES * OCC <= 226 * 1024, "shared memory layout");
 };
 
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -122,10 +136,11 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
 }
 
 template <int CIN_A, int CIN_B, int COUT, int EPI>
-__global__ void __launch_bounds__(WS_THREADS, 1)
+__global__ void __launch_bounds__((TcGeom<CIN_A + CIN_B, COUT, tc_occ(CIN_A, CIN_B, COUT, EPI)>::THREADS), tc_occ(CIN_A, CIN_B, COUT, EPI))
 conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
     constexpr int CIN = CIN_A + CIN_B;
-    using G = TcGeom<CIN, COUT>;
+    using G = TcGeom<CIN, COUT, tc_occ(CIN_A, CIN_B, COUT, EPI)>;
+    constexpr int WS_THREADS = G::THREADS, W_EPI0 = G::W_EPI0, W_MMA = G::W_MMA, W_TMA = G::W_TMA, NGROUP = G::NEG, TMEM_ALL = G::TMEM_COLS;
     constexpr int NA = G::NA, NS = G::NS, NP = NA / 2, ND = G::ND, NDP = ND / 2;
     constexpr unsigned FULL = 0xffffffffu;
 
@@ -630,7 +645,8 @@ static int conv_tc_rows() {
 
 template <int CIN_A, int CIN_B, int COUT, int EPI>
 static int launch_tc_impl(TcConvParams& p, int njobs, cudaStream_t st) {
-    using G = TcGeom<CIN_A + CIN_B, COUT>;
+    using G = TcGeom<CIN_A + CIN_B, COUT, tc_occ(CIN_A, CIN_B, COUT, EPI)>;
+    constexpr int OCC = tc_occ(CIN_A, CIN_B, COUT, EPI);
     static const int cat = [] {
         char nm[64];
         snprintf(nm, sizeof(nm), "conv3x3_tc<%d,%d,%d,%s>", CIN_A, CIN_B, COUT, EPI == EPI_STORE ? "store" : EPI == EPI_POOL ? "pool" : EPI == EPI_DOT ? "dot" : "convt");
@@ -638,7 +654,7 @@ static int launch_tc_impl(TcConvParams& p, int njobs, cudaStream_t st) {
     }();
     auto k = conv3x3_tc_kernel<CIN_A, CIN_B, COUT, EPI>;
     PC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES));
-    int per_job = num_sms() / njobs;                                  // persistent CTAs of one job, one CTA per SM
+    int per_job = OCC * num_sms() / njobs;                            // persistent CTAs of one job, OCC CTAs per SM
     if (per_job < 1) per_job = 1;
     p.tiles_x = cdiv(p.W, TCM);
     p.TR = conv_tc_rows();
@@ -649,7 +665,7 @@ static int launch_tc_impl(TcConvParams& p, int njobs, cudaStream_t st) {
     if (per_job > ntiles) per_job = ntiles;
     {
         ProfScope prof(cat, st, (double)p.H * p.W * njobs);
-        k<<<dim3(per_job, njobs), WS_THREADS, G::SMEM_BYTES, st>>>(p);
+        k<<<dim3(per_job, njobs), G::THREADS, G::SMEM_BYTES, st>>>(p);
     }
     PC_LAUNCH_CHECK();
     return 0;

@@ -11,6 +11,8 @@
 //   ConvTranspose2d k2 s2 = convt_dgrad_kernel, convt_wgrad_kernel.
 // All tensors are fp32 planes with explicit strides; gradients w.r.t. the FOLDED weights come back in the packed
 // layouts of include/popcorn_b200.h and are unfolded to (W, b, gamma, beta) on the host (tiny tensors).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace pc {
@@ -41,6 +43,8 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const __grid_constant__
     const int ty = blockIdx.x / a.tiles_x, tx = blockIdx.x - ty * a.tiles_x;
     const int x0 = tx * WT, y0 = ty * WT;
     // ---- stage the input tile with a 1-px halo (zero outside the virtual image; reflect / channel map / concat as the forward loader)
+    // unrolled: eight independent global loads in flight per thread (the tile is latency-bound otherwise: one DRAM round trip per iteration)
+#pragma unroll 8
     for (int i = tid; i < cin * (WT + 2) * (WT + 2); i += 256) {
         const int c = i / ((WT + 2) * (WT + 2)), r = (i / (WT + 2)) % (WT + 2), col = i % (WT + 2);
         const int vy = y0 - 1 + r, vx = x0 - 1 + col;
@@ -63,6 +67,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const __grid_constant__
         }
         xs[(c * (WT + 2) + r) * WIP + col] = v;
     }
+#pragma unroll 8
     for (int i = tid; i < cout * WT * WT; i += 256) {
         const int c = i / (WT * WT), r = (i / WT) % WT, col = i % WT;
         const int vy = y0 + r, vx = x0 + col;
@@ -109,6 +114,124 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const __grid_constant__
         } else {
             const int c_o = i - NW;                 // bias: the ci == 0 threads saw every pixel once
             for (int g = 0; g < G; ++g) s += red[(g * NP + c_o) * 10 + 9];
+        }
+        out[i] = s;
+    }
+}
+
+// Register-tiled wgrad (round 2): one CTA = one 32x32 tile; a thread owns ONE input channel and EIGHT output channels, i.e. 72 weight
+// accumulators (+ 8 bias sums), and walks its share of the tile's pixels with a sliding 3x3 window of the input: 3 scalar LDS + 2
+// LDS.128 (the pixel's eight gradients, stored [row][col][cout]) for 72 FMAs — the first version's (ci, co)-pair threads issued 4 LDS
+// per 9 FMAs and ran at ~1/8 of the FP32 pipe.  The pixels are split over G = 256 / (cin * cout/8) thread groups (rows; for the thin
+// first layer also column blocks); the groups' partials are summed in a fixed order through shared memory (the staging buffers are
+// reused), then written as this tile's partial in the packed layout.  Bitwise reproducible: no atomics anywhere.
+constexpr int WG_ACC = 80;         // floats a thread contributes: 9 taps x 8 output channels + 8 bias sums
+
+__global__ void __launch_bounds__(256) conv_wgrad2_kernel(const __grid_constant__ WgradArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    const int cin = a.cin_a + a.cin_b, cout = a.cout;
+    const int NO = cout >> 3;                       // output-channel octets
+    const int NP = cin * NO;                        // owner slots (<= 64)
+    const int G = 256 / NP;                         // pixel groups (>= 4)
+    float* xs = sm;                                 // [cin][34][WIP]
+    float* gs = xs + cin * (WT + 2) * WIP;          // [32][32][cout]
+    const int tid = threadIdx.x;
+    const int ty = blockIdx.x / a.tiles_x, tx = blockIdx.x - ty * a.tiles_x;
+    const int x0 = tx * WT, y0 = ty * WT;
+    // ---- stage the input tile with a 1-px halo (zero outside the virtual image; reflect / channel map / concat as the forward loader)
+#pragma unroll 4
+    for (int i = tid; i < cin * (WT + 2) * (WT + 2); i += 256) {
+        const int c = i / ((WT + 2) * (WT + 2)), r = (i / (WT + 2)) % (WT + 2), col = i % (WT + 2);
+        const int vy = y0 - 1 + r, vx = x0 - 1 + col;
+        float v = 0.f;
+        if (vy >= 0 && vy < a.H && vx >= 0 && vx < a.W) {
+            if (c < a.cin_a) {
+                int sy = vy - a.a_oy, sx = vx - a.a_ox;
+                bool ok = true;
+                if (a.a_reflect) {
+                    sy = sy < 0 ? -sy : sy; sy = sy >= a.a_H ? 2 * (a.a_H - 1) - sy : sy;
+                    sx = sx < 0 ? -sx : sx; sx = sx >= a.a_W ? 2 * (a.a_W - 1) - sx : sx;
+                } else ok = sy >= 0 && sy < a.a_H && sx >= 0 && sx < a.a_W;
+                int plane = c;
+                if (a.cin_a <= 4) plane = (a.a_chmap >> (8 * c)) & 0xff;
+                if (ok) v = __ldg(a.a + plane * a.a_cs + (long long)sy * a.a_rs + sx);
+            } else {
+                const int sy = vy - a.b_oy, sx = vx - a.b_ox;
+                if (sy >= 0 && sy < a.b_H && sx >= 0 && sx < a.b_W) v = __ldg(a.b + (c - a.cin_a) * a.b_cs + (long long)sy * a.b_rs + sx);
+            }
+        }
+        xs[(c * (WT + 2) + r) * WIP + col] = v;
+    }
+#pragma unroll 4
+    for (int i = tid; i < cout * WT * WT; i += 256) {          // coalesced along the image row, transposed into [r][col][c]
+        const int c = i / (WT * WT), r = (i / WT) % WT, col = i % WT;
+        const int vy = y0 + r, vx = x0 + col;
+        gs[(r * WT + col) * cout + c] = (vy < a.H && vx < a.W) ? __ldg(a.g + c * a.g_cs + (long long)vy * a.g_rs + vx) : 0.f;
+    }
+    __syncthreads();
+    const int slot = tid % NP, grp = tid / NP;
+    const int ci = slot / NO, oct = slot - ci * NO;
+    float acc[9][8];
+    float accb[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+        accb[o] = 0.f;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) acc[t][o] = 0.f;
+    }
+    if (grp < G) {
+        // pixel share of this group: whole rows while there are at most 32 groups, else one row and a column block
+        int r0, r1, c0, c1;
+        if (G <= WT) { const int rows = WT / G; r0 = grp * rows; r1 = r0 + rows; c0 = 0; c1 = WT; }
+        else { const int cs = G / WT, cw = WT / cs; r0 = grp % WT; r1 = r0 + 1; c0 = (grp / WT) * cw; c1 = c0 + cw; }
+        const float* xc = xs + ci * (WT + 2) * WIP;
+        for (int r = r0; r < r1; ++r) {
+            const float* x0r = xc + r * WIP + c0;     // input rows r, r+1, r+2 hold image rows y-1, y, y+1; column c0 = image column x-1
+            const float* x1r = x0r + WIP;
+            const float* x2r = x1r + WIP;
+            const float4* gp = reinterpret_cast<const float4*>(gs + (r * WT + c0) * cout + 8 * oct);
+            float w0 = x0r[0], w1 = x0r[1], m0 = x1r[0], m1 = x1r[1], s0 = x2r[0], s1 = x2r[1];
+#pragma unroll 2
+            for (int c = 0; c < c1 - c0; ++c) {
+                const float w2 = x0r[c + 2], m2 = x1r[c + 2], s2 = x2r[c + 2];
+                const float4 ga = gp[(c * cout) >> 2], gb = gp[((c * cout) >> 2) + 1];
+                const float gv[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+                const float xv[9] = {w0, w1, w2, m0, m1, m2, s0, s1, s2};
+#pragma unroll
+                for (int t = 0; t < 9; ++t)
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) acc[t][o] = fmaf(xv[t], gv[o], acc[t][o]);
+#pragma unroll
+                for (int o = 0; o < 8; ++o) accb[o] += gv[o];
+                w0 = w1; w1 = w2; m0 = m1; m1 = m2; s0 = s1; s1 = s2;
+            }
+        }
+    }
+    __syncthreads();                                  // the staging buffers become the reduction buffer
+    float* red = sm;                                  // [G][NP][WG_ACC]
+    if (grp < G) {
+        float* rp = red + (grp * NP + slot) * WG_ACC;
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+#pragma unroll
+            for (int o = 0; o < 8; ++o) rp[t * 8 + o] = acc[t][o];
+#pragma unroll
+        for (int o = 0; o < 8; ++o) rp[72 + o] = accb[o];
+    }
+    __syncthreads();
+    // ---- fixed-order sum over the groups, written in the packed layout [ci][tap][co] (+ bias[co]) ----
+    const int NW = cin * 9 * cout;
+    float* out = a.partial + (long long)blockIdx.x * (NW + cout);
+    for (int i = tid; i < NW + cout; i += 256) {
+        float s = 0.f;
+        if (i < NW) {
+            const int c_i = i / (9 * cout), t = (i / cout) % 9, c_o = i % cout;
+            const int sl = c_i * NO + (c_o >> 3), e = t * 8 + (c_o & 7);
+            for (int g = 0; g < G; ++g) s += red[(g * NP + sl) * WG_ACC + e];
+        } else {
+            const int c_o = i - NW;                 // bias: the ci == 0 threads saw every pixel once
+            const int sl = c_o >> 3, e = 72 + (c_o & 7);
+            for (int g = 0; g < G; ++g) s += red[(g * NP + sl) * WG_ACC + e];
         }
         out[i] = s;
     }
@@ -260,14 +383,23 @@ extern "C" int pc_conv3x3_wgrad(const float* a, int cin_a, long long a_cs, int a
     A.g = g; A.g_cs = g_cs; A.g_rs = g_rs; A.cout = cout; A.H = H; A.W = W; A.tiles_x = cdiv(W, WT);
     A.partial = reinterpret_cast<float*>(round_up((long long)(uintptr_t)workspace, 256));
     const int tiles = A.tiles_x * cdiv(H, WT);
-    const int G = 256 / (cin * cout);
-    const int smem = (cin * (WT + 2) * WIP + cout * WGP + G * cin * cout * 10) * 4;
     cudaStream_t st = (cudaStream_t)stream;
-    PC_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    {
+    static const bool v1 = [] { const char* e = getenv("POPCORN_WGRAD_V1"); return e && atoi(e) != 0; }();
+    if (v1) {                                          // the first version (one (ci, co) pair per thread), kept for A/B runs
+        const int G = 256 / (cin * cout);
+        const int smem = (cin * (WT + 2) * WIP + cout * WGP + G * cin * cout * 10) * 4;
+        PC_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         static const int cat = prof_register("conv3x3_wgrad");
         ProfScope prof(cat, st, (double)H * W);
         conv_wgrad_kernel<<<tiles, 256, smem, st>>>(A);
+    } else {
+        const int stage = cin * (WT + 2) * WIP + cout * WT * WT;          // floats: input tile + transposed gradient tile
+        const int red = 256 * WG_ACC;                                     // floats: every thread's 80 partials (G * NP == 256 slots at most)
+        const int smem = (stage > red ? stage : red) * 4;
+        PC_CUDA(cudaFuncSetAttribute(conv_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        static const int cat = prof_register("conv3x3_wgrad");
+        ProfScope prof(cat, st, (double)H * W);
+        conv_wgrad2_kernel<<<tiles, 256, smem, st>>>(A);
     }
     PC_LAUNCH_CHECK();
     const int n = cin * 9 * cout + cout;

@@ -133,38 +133,54 @@ def _convt_wgrad(x, gu, grad_pack, accumulate):
                "pc_convt2x2_wgrad")
 
 
-class _StreamWeights:
-    """Folded forward packs, dgrad packs and the BN scale of one stream (rebuilt on every forward: the weights move)."""
+def _bn_constants(cache: dict, sd: Dict[str, torch.Tensor], full: str, slot: int):
+    """(s, c) with BN(eval)(y) = y * s + c for the frozen BatchNorm that follows conv `slot` (s = gamma / sqrt(var + eps),
+    c = beta - mean * s), computed once in fp64 and cached as fp32 ON THE NETWORK OBJECT (`cache`): the layers are frozen on every
+    forward (freeze_bn_layers), so the constants only change when a checkpoint is loaded (the entry carries the tensors' versions)."""
+    ts = [sd[f"{full}.{slot + 1}.{n}"] for n in ("weight", "bias", "running_mean", "running_var")]
+    sig = tuple((t.data_ptr(), t._version) for t in ts)
+    hit = cache.get((full, slot))
+    if hit is None or hit[0] != sig:
+        g, beta, mean, var = (t.detach().double() for t in ts)
+        s = g / torch.sqrt(var + BN_EPS)
+        hit = (sig, s.float(), (beta - mean * s).float())
+        cache[(full, slot)] = hit
+    return hit[1], hit[2]
 
-    def __init__(self, sd: Dict[str, torch.Tensor], stream: str, params: Dict[str, torch.Tensor]):
+
+class _StreamWeights:
+    """Folded forward packs, dgrad packs and the BN scale of one stream (rebuilt on every forward: the weights move).  fp32 folding with
+    cached BN constants: a handful of launches per layer instead of the ~15 of a float64 round trip (the step is host-bound)."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], stream: str, params: Dict[str, torch.Tensor], bn_cache: dict):
         self.fwd, self.dgrad, self.scale, self.shape = {}, {}, {}, {}
+        self._dgrad_packs = {}
         for li, (kind, pfx, slot) in enumerate(_LAYERS):
             full = f"{stream}.{pfx}"
             if kind == "conv":
-                W = params[f"{full}.{slot}.weight"].detach().double()         # [cout, cin, 3, 3]
-                b = params[f"{full}.{slot}.bias"].detach().double()
-                g = sd[f"{full}.{slot + 1}.weight"].detach().double()
-                beta = sd[f"{full}.{slot + 1}.bias"].detach().double()
-                mean = sd[f"{full}.{slot + 1}.running_mean"].detach().double()
-                var = sd[f"{full}.{slot + 1}.running_var"].detach().double()
-                s = g / torch.sqrt(var + BN_EPS)
-                Wf = (W * s.view(-1, 1, 1, 1)).permute(1, 2, 3, 0).contiguous()     # [cin, ky, kx, cout]
-                bf = (b - mean) * s + beta
-                self.fwd[li] = torch.cat([Wf.reshape(-1), bf]).float().contiguous()
-                Wd = Wf.flip(1, 2).permute(3, 1, 2, 0).contiguous().float()          # [cout, ky', kx', cin]: dgrad as a forward conv
-                self.dgrad[li] = Wd
-                self.scale[li] = s.float()
+                W = params[f"{full}.{slot}.weight"].detach()                   # [cout, cin, 3, 3]
+                b = params[f"{full}.{slot}.bias"].detach()
+                s, c = _bn_constants(bn_cache, sd, full, slot)
+                Wf = (W * s.view(-1, 1, 1, 1)).permute(1, 2, 3, 0)             # [cin, ky, kx, cout] (view)
+                self.fwd[li] = torch.cat([Wf.reshape(-1), torch.addcmul(c, b, s)])
+                self.dgrad[li] = Wf.flip(1, 2).permute(3, 1, 2, 0)             # [cout, ky', kx', cin]: dgrad as a forward conv (view)
+                self.scale[li] = s
                 self.shape[li] = tuple(W.shape)
             else:
-                T = params[f"{full}.weight"].detach().float()                         # [cin, cout, 2, 2]
-                b = params[f"{full}.bias"].detach().float()
-                self.fwd[li] = torch.cat([T.permute(0, 2, 3, 1).reshape(-1), b]).contiguous()
+                T = params[f"{full}.weight"].detach()                          # [cin, cout, 2, 2]
+                b = params[f"{full}.bias"].detach()
+                self.fwd[li] = torch.cat([T.permute(0, 2, 3, 1).reshape(-1), b])
                 self.shape[li] = tuple(T.shape)
 
     def dgrad_pack(self, li: int, lo: int = 0, hi: int | None = None) -> torch.Tensor:
-        """dgrad weights of layer li as a forward pack [cout_fwd][9][cin_fwd[lo:hi]] + zero bias."""
-        Wd = self.dgrad[li][..., lo:hi].contiguous()
-        return torch.cat([Wd.reshape(-1), torch.zeros(Wd.shape[-1], device=Wd.device)]).contiguous()
+        """dgrad weights of layer li as a forward pack [cout_fwd][9][cin_fwd[lo:hi]] + zero bias (built once per step and slice)."""
+        key = (li, lo, hi)
+        pack = self._dgrad_packs.get(key)
+        if pack is None:
+            Wd = self.dgrad[li][..., lo:hi]
+            pack = torch.cat([Wd.reshape(-1), torch.zeros(Wd.shape[-1], device=Wd.device, dtype=Wd.dtype)])
+            self._dgrad_packs[key] = pack
+        return pack
 
 
 def _chmap(C: int, s: int) -> int:
@@ -192,7 +208,9 @@ class UNetFeaturesFn(torch.autograd.Function):
             x = x.contiguous()
         sids = [i for i, on in enumerate((S1, S2)) if on]
         feats = torch.empty(B, 8 * len(sids), H, W, dtype=torch.float32, device=dev)
-        weights = {s: _StreamWeights(sd, _STREAMS[s], pdict) for s in sids}
+        if not hasattr(net, "_bn_const_cache"):
+            net._bn_const_cache = {}
+        weights = {s: _StreamWeights(sd, _STREAMS[s], pdict, net._bn_const_cache) for s in sids}
         saved = []
         for bi in range(B):
             for si, s in enumerate(sids):

@@ -226,3 +226,11 @@ def test_product_package_never_imports_the_oracle():
     for f in root.rglob("*.py"):
         src = f.read_text()
         assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_numa_cpulist_parsing_and_binding_is_harmless_without_a_gpu():
+    from popcorn_b200 import numa
+    assert numa.parse_cpulist("0-3,8,10-11") == {0, 1, 2, 3, 8, 10, 11}
+    assert numa.parse_cpulist("") == set()
+    info = numa.bind_to_gpu_node(0)            # no CUDA device here: reports "not bound", never raises
+    assert info["bound"] is False

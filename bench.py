@@ -711,14 +711,20 @@ def main():
                 res_bw[mode] = {"h2d_gbs_all_ranks": (2 * nb_up * world / sec / 1e9) if mode != "d2h" else 0.0,
                                 "d2h_gbs_all_ranks": (2 * nb_dn * world / sec / 1e9) if mode != "h2d" else 0.0}
             up, dn = res_bw["h2d"]["h2d_gbs_all_ranks"], res_bw["d2h"]["d2h_gbs_all_ranks"]
-            t_px = max(16.0 / (up * 1e9), 4.0 / (dn * 1e9))          # full duplex: the slower direction bounds a pixel
+            upc, dnc = res_bw["both"]["h2d_gbs_all_ranks"], res_bw["both"]["d2h_gbs_all_ranks"]
+            # a steady stream of rasters moves 16 B/px up and 4 B/px down AT THE SAME TIME: the bound uses the rates measured with both
+            # directions active (the 4:1 byte ratio of the probe equals the path's)
+            t_px = max(16.0 / (upc * 1e9), 4.0 / (dnc * 1e9))
             pcie = {"h2d_gbs_all_ranks_alone": up, "d2h_gbs_all_ranks_alone": dn, "concurrent": res_bw["both"],
                     "bound_px_per_s": 1.0 / t_px,
-                    "note": "every rank copying at once; bound = 16 B/px up, 4 B/px down over these links (full duplex)"}
+                    "note": "every rank copying at once; bound = 16 B/px up and 4 B/px down over these links with both directions active"}
             del hb_up, hb_dn, db_up, db_dn
         except Exception as ex:
             pcie = {"error": repr(ex)[:200]}
-        e2e = {"value": H * W / (float(tt.item()) / k_e2e), "unit": UNIT, "host_links": pcie, "h2d_bytes_per_step": int(h2d.item()),
+        e2e_value = H * W / (float(tt.item()) / k_e2e)
+        if pcie and pcie.get("bound_px_per_s"):
+            pcie["e2e_frac_of_bound"] = e2e_value / pcie["bound_px_per_s"]
+        e2e = {"value": e2e_value, "unit": UNIT, "host_links": pcie, "h2d_bytes_per_step": int(h2d.item()),
                "d2h_bytes_per_step": int(d2h.item()), "steps": k_e2e,
                "api": "popcorn_b200.country.CountryEngine.run(RawRaster(pinned uint16 S2 + float32 S1), map_out=pinned host map) + sums.cpu()",
                "upload": "once_per_row" if upload_once else "per_window", "numa": numa_info,

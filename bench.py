@@ -854,20 +854,24 @@ def main():
             j0, j1 = tse.in_rows
             frame = synth_raster_slab(j1 - j0, Ws, j0, dev, seed=99) if j1 > j0 else torch.empty(6, 0, Ws, device=dev)
             frames = {t_: frame for t_ in tse.my_frames}    # same cost as independent draws; keeps 30 GB of generation out
+            runs = []
             with torch.no_grad():
                 tse.run(frames, None, 0, row_offset=j0)
-                barrier()
-                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a0.record()
-                o = tse.run(frames, None, 0, row_offset=j0)
-                a1.record()
-                barrier()
-            tms = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+                for _ in range(3):
+                    barrier()
+                    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a0.record()
+                    o = tse.run(frames, None, 0, row_offset=j0)
+                    a1.record()
+                    barrier()
+                    tms = torch.tensor([a0.elapsed_time(a1)], dtype=torch.float64, device=dev)
+                    if world > 1:
+                        dist.all_reduce(tms, op=dist.ReduceOp.MAX)       # a run takes as long as its slowest rank
+                    runs.append(float(tms.item()))
+            tms = torch.tensor([sorted(runs)[1]], dtype=torch.float64, device=dev)      # median of three whole-series runs
             tseries = {"workload": f"switzerland_shaped_{Hs}x{Ws}_x{T}_seasonal_frames_over_{world}_gpus",
                        "partition": tse.describe(), "ms": float(tms.item()), "value": T * Hs * Ws / (float(tms.item()) * 1e-3), "unit": UNIT,
-                       "season_total": float(o["season_total"].item()), "frames": T,
+                       "season_total": float(o["season_total"].item()), "frames": T, "runs_ms": runs,
                        "note": "per-frame tiled inference + season mean/std/totals on the device (popcorn_b200.timeseries); inputs resident in HBM"}
             del frame, frames, o, tse
             torch.cuda.empty_cache()

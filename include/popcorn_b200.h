@@ -66,8 +66,9 @@ int pc_dda_pack_floats(void);
 int pc_dda_pack_offset(int stream, int layer);
 
 /* Tensor-core weight section (csrc/conv_tc.cu): the ten 3x3 conv layers of each stream again, as tcgen05 B
- * operands — per layer [ky][hi|lo] matrices W_ky[co (16 rows, zero-padded)][k = kx*cin + ci] in the UMMA K-major
- * SWIZZLE_128B layout, each weight split w = hi + lo (hi = top 19 bits: exact TF32) for 3xTF32, then bias[16].
+ * operands — per layer [hi|lo] matrices with rows [W_ky2 | W_ky1 | W_ky0] (3*Cout rows: row Cout*(2-ky) + co, k = kx*cin + ci,
+ * K padded to 32-float atoms) in the UMMA K-major SWIZZLE_128B layout, each weight split w = hi + lo (hi = top 19 bits: exact
+ * TF32) for 3xTF32, then bias[16].
  * It is appended to the fp32 pack at float offset pc_dda_tc_pack_base() (the fp32 pack rounded up to 256 B) and is
  * pc_dda_tc_pack_floats() long; pc_dda_tc_pack converts a HOST fp32 pack into a HOST image (pure host code).
  * pc_dda_forward uses the tensor-core kernels when the pack it is given is long enough to hold the section. */
@@ -131,6 +132,25 @@ int pc_head_sparse_forward_tc(const void* tcpack, int head_in, const float* feat
                               long long f_cstride, const float* builtup, const int32_t* idx, const int32_t* n_dev,
                               long long n_max, long long HW, float* dens, float* scale_sel, double* popcount,
                               pc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * pc_infer_tile_fused — the whole dense inference of one tile batch in ONE call:
+ *   builtup pass (reflect 14, building_extractor, fusion logits, sigmoid) -> feature pass (unetmodel, pad-to-64 rule of
+ *   add_padding) -> tcgen05 occupancy head -> relu x builtup -> optional census partial sums.
+ * Replaces: POPCORN.forward in eval mode, model/popcorn.py:100-193, as run_eval.py:109 calls it (padding=False).
+ *   bext_pack / unet_pack  device DDA packs WITH the tensor-core section (pc_dda_pack_floats .. + pc_dda_tc_pack), `pack_floats` long
+ *   head_tcpack            pc_head_tc_pack_bytes() image
+ *   x [B,6|2|4,H,W] fp32 view; dens / scale [B,H,W] (scale may be NULL); builtup [B,1,H,W] (output; contiguous)
+ *   ids / census_idx / sums / R: as pc_head_dense_forward (all NULL / 0: no census sums)
+ *   workspace: pc_infer_tile_workspace_bytes(B, C, H, W) = DDA activations of the larger (reflect-padded) pass + the feature map.
+ * "Fused" at the boundary: one call, no host round trip and no allocation between the three launch groups; the activations still
+ * travel layer by layer through the workspace (DESIGN.md §5 explains why the layers are not merged into one kernel).
+ * --------------------------------------------------------------------------------------------- */
+size_t pc_infer_tile_workspace_bytes(int B, int C, int H, int W);
+int pc_infer_tile_fused(const float* bext_pack, const float* unet_pack, long long pack_floats, const void* head_tcpack,
+                        const float* x, int B, int C, int H, int W, long long x_bstride, long long x_cstride, int x_rstride,
+                        float* dens, float* scale, float* builtup, const int32_t* ids, const int32_t* census_idx,
+                        double* sums, int R, void* workspace, size_t workspace_bytes, pc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Sparse occupancy head (training path).

@@ -43,6 +43,8 @@ SIGNATURES = {
     "pc_head_dense_forward_tc": (_i, [_vp, _i, _vp, _ll, _ll, _i, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _ll, _i, _vp, _ll, _i,
                                       _vp, _vp, _i, _vp]),
     "pc_head_sparse_forward_tc": (_i, [_vp, _i, _vp, _ll, _ll, _vp, _vp, _vp, _ll, _ll, _vp, _vp, _vp, _vp]),
+    "pc_infer_tile_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "pc_infer_tile_fused": (_i, [_vp, _vp, _ll, _vp, _vp, _i, _i, _i, _i, _ll, _ll, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
     "pc_compact_workspace_bytes": (_sz, [_ll]),
     "pc_sparse_mask_compact": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pc_head_sparse_forward": (_i, [_vp, _i, _vp, _ll, _ll, _vp, _vp, _vp, _ll, _ll, _vp, _vp, _vp, _vp]),

@@ -146,3 +146,53 @@ extern "C" int pc_test_fma_peak(int use_x2, int iters, int blocks_per_sm, float*
     PC_LAUNCH_CHECK();
     return grid * 256;
 }
+
+
+// ---- pc_infer_tile_fused: builtup pass + feature pass + dense head behind one entry point -------------------------------------
+static void feature_pads(int H, int W, int* top, int* bot, int* left, int* right) {   // add_padding(force=False), popcorn.py:247-256
+    *top = *bot = *left = *right = 0;
+    if (H % 32 != 0) { const int t = 64 - H % 64; *top = t / 2; *bot = t - t / 2; }
+    if (W % 32 != 0) { const int t = 64 - W % 64; *left = t / 2; *right = t - t / 2; }
+}
+
+extern "C" size_t pc_infer_tile_workspace_bytes(int B, int C, int H, int W) {
+    if (B < 1 || H < 1 || W < 1 || !(C == 6 || C == 2 || C == 4)) return 0;
+    int t, b, l, r;
+    feature_pads(H, W, &t, &b, &l, &r);
+    const size_t w1 = pc_dda_workspace_bytes(B, C, H + 28, W + 28);
+    const size_t w2 = pc_dda_workspace_bytes(B, C, H + t + b, W + l + r);
+    const int nf = C == 6 ? 16 : 8;
+    return (w1 > w2 ? w1 : w2) + (size_t)B * nf * H * W * sizeof(float) + 512;
+}
+
+extern "C" int pc_infer_tile_fused(const float* bext_pack, const float* unet_pack, long long pack_floats, const void* head_tcpack,
+                                   const float* x, int B, int C, int H, int W, long long x_bstride, long long x_cstride,
+                                   int x_rstride, float* dens, float* scale, float* builtup, const int32_t* ids,
+                                   const int32_t* census_idx, double* sums, int R, void* workspace, size_t workspace_bytes,
+                                   pc_stream_t stream) {
+    PC_CHECK_ARG(bext_pack && unet_pack && head_tcpack && x && dens && builtup && workspace, "null pointer");
+    PC_CHECK_ARG(C == 6 || C == 2 || C == 4, "input channels must be 6, 2 or 4");
+    PC_CHECK_ARG(B >= 1 && H >= 29 && W >= 29, "tile smaller than the reflect padding");
+    const size_t need = pc_infer_tile_workspace_bytes(B, C, H, W);
+    if (workspace_bytes < need) {
+        pc::set_error("pc_infer_tile_fused: workspace %zu < required %zu", workspace_bytes, need);
+        return PC_ERR_WORKSPACE;
+    }
+    int t, b, l, r;
+    feature_pads(H, W, &t, &b, &l, &r);
+    const int nf = C == 6 ? 16 : 8;
+    const size_t feat_bytes = (size_t)B * nf * H * W * sizeof(float);
+    char* base = reinterpret_cast<char*>(pc::round_up((long long)(uintptr_t)workspace, 256));
+    float* feats = reinterpret_cast<float*>(base);
+    void* dda_ws = base + pc::round_up((long long)feat_bytes, 256);
+    const size_t dda_bytes = workspace_bytes - (size_t)((char*)dda_ws - (char*)workspace);
+    const long long hw = (long long)H * W;
+    int rc = pc_dda_forward(bext_pack, pack_floats, x, B, C, H, W, x_bstride, x_cstride, x_rstride, 14, 14, 14, 14, PC_DDA_BUILTUP,
+                            builtup, hw, hw, W, dda_ws, dda_bytes, stream);
+    if (rc) return rc;
+    rc = pc_dda_forward(unet_pack, pack_floats, x, B, C, H, W, x_bstride, x_cstride, x_rstride, t, b, l, r, PC_DDA_FEATURES, feats,
+                        (long long)nf * hw, hw, W, dda_ws, dda_bytes, stream);
+    if (rc) return rc;
+    return pc_head_dense_forward_tc(head_tcpack, nf, feats, (long long)nf * hw, hw, W, builtup, hw, W, B, H, W, dens, scale, hw, W,
+                                    ids, hw, W, census_idx, sums, R, stream);
+}

@@ -21,6 +21,7 @@ from .dda import STAGE1_FEATS, load_checkpoint
 # forward head on tcgen05 (3xTF32, csrc/head_tc.cu) unless POPCORN_HEAD_TC=0 selects the fp32 SIMT kernel (csrc/head.cu)
 USE_TENSOR_CORE_HEAD = os.environ.get("POPCORN_HEAD_TC", "1") != "0"
 _CHECK_IDS = os.environ.get("POPCORN_CHECK_IDS", "0") == "1"
+FUSED_EVAL = os.environ.get("POPCORN_FUSED_EVAL", "1") != "0"      # eval forward through pc_infer_tile_fused (one library call)
 
 
 class _SparseHeadFn(torch.autograd.Function):
@@ -218,6 +219,26 @@ class POPCORN(nn.Module):
         if not X.is_cuda:
             raise RuntimeError("popcorn_b200.POPCORN runs on CUDA (sm_100a) tensors only; there is no CPU fallback")
 
+        if _CHECK_IDS and "admin_mask" in inputs.keys():
+            am = inputs["admin_mask"]
+            if am.is_floating_point() and not bool(((am == am.round()) & (am.abs() <= 2 ** 24)).all()):
+                raise ValueError("admin_mask must hold integral region ids with |id| <= 2**24 (float32-exact)")
+        # eval fast path: builtup pass + feature pass + tcgen05 head + census partials behind ONE library call (pc_infer_tile_fused)
+        B, _, H, W = X.shape
+        if (USE_TENSOR_CORE_HEAD and FUSED_EVAL and not sparse and not padding and not torch.is_grad_enabled() and self.occupancymodel
+                and ("building_counts" not in inputs.keys() or self.sentinelbuildings) and H >= 29 and W >= 29):
+            self.unetmodel.freeze_bn_layers()
+            sums = torch.zeros(B, dtype=torch.float64, device=X.device)
+            if "admin_mask" in inputs.keys():
+                ids = inputs["admin_mask"].to(torch.int32).contiguous()
+                cidx = inputs["census_idx"].to(device=X.device, dtype=torch.int32).contiguous()
+            else:
+                ids, cidx = None, torch.zeros(B, dtype=torch.int32, device=X.device)       # bin = batch index, all pixels
+            dens, scale, builtup = ops.infer_tile_fused(self._dda_pack("building_extractor"), self._dda_pack("unetmodel"),
+                                                        self._head_pack(tc=True), X, ids, cidx, sums, want_scale=True)
+            inputs["building_counts"] = builtup
+            return {"popcount": sums.float(), "popdensemap": dens, "scale": scale, "builtup_score": builtup, "occupancy": scale}
+
         # builtup score (popcorn.py:112-115)
         if "building_counts" not in inputs.keys() or self.sentinelbuildings:
             inputs["building_counts"] = self.create_building_score(inputs)
@@ -225,10 +246,6 @@ class POPCORN(nn.Module):
         if builtup.dtype != torch.float32 or not builtup.is_contiguous():
             builtup = builtup.float().contiguous()
 
-        if _CHECK_IDS and "admin_mask" in inputs.keys():
-            am = inputs["admin_mask"]
-            if am.is_floating_point() and not bool(((am == am.round()) & (am.abs() <= 2 ** 24)).all()):
-                raise ValueError("admin_mask must hold integral region ids with |id| <= 2**24 (float32-exact)")
         aux = {}
         if sparse:
             sparsity_mask, _ = self.get_sparsity_mask(inputs)

@@ -123,6 +123,36 @@ def dda_forward(wpack: torch.Tensor, x: torch.Tensor, pads=(0, 0, 0, 0), mode: i
 
 
 @_device_guard
+def infer_tile_fused(bext_pack: torch.Tensor, unet_pack: torch.Tensor, head_tcpack: torch.Tensor, x: torch.Tensor,
+                     ids: Optional[torch.Tensor] = None, census_idx: Optional[torch.Tensor] = None,
+                     sums: Optional[torch.Tensor] = None, want_scale: bool = True):
+    """Dense eval forward of a tile batch in one library call (pc_infer_tile_fused): -> (dens [B,H,W], scale [B,H,W]|None,
+    builtup [B,1,H,W]); `sums` (float64) is updated in place as in head_dense_forward."""
+    _need_cuda(bext_pack, unet_pack, head_tcpack, x, ids, census_idx, sums)
+    L = _lib.lib()
+    if x.dim() != 4:
+        raise ValueError("Input tensor must have shape (batch_size, channels, height, width)")
+    if x.dtype != torch.float32 or x.stride(3) != 1:
+        x = x.float().contiguous()
+    B, Cc, H, W = x.shape
+    assert bext_pack.numel() == unet_pack.numel()
+    dens = torch.empty(B, H, W, dtype=torch.float32, device=x.device)
+    scale = torch.empty_like(dens) if want_scale else None
+    builtup = torch.empty(B, 1, H, W, dtype=torch.float32, device=x.device)
+    if ids is not None:
+        assert ids.dtype == torch.int32 and ids.is_contiguous() and tuple(ids.shape) == (B, H, W)
+    if sums is not None:
+        assert sums.dtype == torch.float64 and sums.is_contiguous()
+    need = L.pc_infer_tile_workspace_bytes(B, Cc, H, W)
+    buf = _ws.get(need, x.device)
+    _lib.check(L.pc_infer_tile_fused(bext_pack.data_ptr(), unet_pack.data_ptr(), bext_pack.numel(), head_tcpack.data_ptr(),
+                                     x.data_ptr(), B, Cc, H, W, x.stride(0), x.stride(1), x.stride(2), dens.data_ptr(), _ptr(scale),
+                                     builtup.data_ptr(), _ptr(ids), _ptr(census_idx), _ptr(sums), 0 if sums is None else sums.numel(),
+                                     buf.data_ptr(), buf.numel(), _stream()), "pc_infer_tile_fused")
+    return dens, scale, builtup
+
+
+@_device_guard
 def head_dense_forward(hpack, feats, builtup, ids=None, census_idx=None, sums=None, want_scale=True, tc=False):
     """feats [B,Cin,H,W], builtup [B,1,H,W]|None -> (dens [B,H,W], scale [B,H,W]|None); sums (float64) updated in place.
     tc=True: `hpack` is the tcgen05 weight image (weights.pack_head_tc) and the tensor-core kernel runs."""

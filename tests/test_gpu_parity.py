@@ -284,3 +284,29 @@ def test_bench_sized_window_3840x16384_crops_vs_oracle(model, sd):
                            po.building_score(sd, crop)[0, 0][F_:-F_, F_:-F_]) < 1e-3
         assert worst < TOL_PIXEL, worst
         assert torch.equal(dens, scale * bu[:, 0])
+
+
+@pytest.mark.parametrize("shape", [(1, 64, 96), (2, 75, 101), (1, 130, 70)])
+def test_fused_eval_entry_point_equals_the_three_separate_calls(model, shape):
+    """pc_infer_tile_fused (builtup pass + feature pass + head + census partials in one C-ABI call) against the same
+    work issued as pc_dda_forward x 2 + pc_head_dense_forward_tc from Python: bit-identical outputs, with and without census ids."""
+    from popcorn_b200.model import popcorn as pm
+    B, H, W = shape
+    x = po.synthetic_input(H, W, seed=H + W, B=B).cuda()
+    admin = (torch.arange(B * H * W).view(B, H, W) % 3).float().cuda()
+    cidx = torch.tensor([1] * B).cuda()
+    outs = []
+    for fused in (True, False):
+        pm.FUSED_EVAL = fused
+        try:
+            with torch.no_grad():
+                a = model({"input": x}, padding=False)
+                b = model({"input": x, "admin_mask": admin, "census_idx": cidx}, padding=False)
+        finally:
+            pm.FUSED_EVAL = True
+        outs.append((a, b))
+    for k in ("popdensemap", "scale", "builtup_score", "popcount"):
+        assert torch.equal(outs[0][0][k], outs[1][0][k]), k
+        assert torch.equal(outs[0][1][k], outs[1][1][k]), k
+    ref = po.forward(golden_state_dict(), {"input": x.cpu(), "admin_mask": admin.cpu(), "census_idx": cidx.cpu()}, padding=False)
+    assert max_rel(outs[0][1]["popcount"], ref["popcount"], floor_frac=1.0) < TOL_REGION

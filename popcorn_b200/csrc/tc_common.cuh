@@ -112,6 +112,9 @@ __device__ __forceinline__ uint32_t mbar_test(uint32_t mbar, uint32_t parity) {
     return done;
 }
 // mbarrier.try_wait suspends the thread in hardware for a bounded time instead of busy-polling shared memory
+#ifndef PC_WAIT_NS
+#define PC_WAIT_NS 0                 // > 0: back off with nanosleep between failed probes (A/B: power / clocks vs hand-off latency)
+#endif
 __device__ __forceinline__ void mbar_wait_sleep(uint32_t mbar, uint32_t parity) {
     for (uint32_t spin = 0;; ++spin) {
         uint32_t done;
@@ -120,6 +123,7 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t mbar, uint32_t parity) 
                      : "r"(mbar), "r"(parity)
                      : "memory");
         if (done) return;
+        if (PC_WAIT_NS > 0) __nanosleep(PC_WAIT_NS);
         if (spin > (1u << 24)) __trap();     // a protocol mistake must fault, never hang the GPU
     }
 }

@@ -123,6 +123,10 @@ int pc_head_dense_forward(const float* hpack, int head_in, const float* feats, l
  * pc_head_sparse_forward, except that `tcpack` is the pc_head_tc_pack_bytes()-byte weight image built by
  * popcorn_b200.weights.pack_head_tc (hi/lo split, K-major SWIZZLE_128B). */
 int pc_head_tc_pack_bytes(void);
+/* Operand format the library's tensor-core kernels were built for (csrc/tc_common.cuh PC_TC_F16): 0 = TF32 halves (4-byte elements,
+ * 32 per 128-byte swizzle row), 1 = fp16 halves (2-byte elements, 64 per row).  Both weight images (pc_dda_tc_pack, pack_head_tc) keep
+ * their sizes and section offsets; only the element format inside a matrix differs. */
+int pc_tc_operand_format(void);
 int pc_head_dense_forward_tc(const void* tcpack, int head_in, const float* feats, long long f_bstride,
                              long long f_cstride, int f_rstride, const float* builtup, long long bu_bstride,
                              int bu_rstride, int B, int H, int W, float* dens, float* scale, long long o_bstride,

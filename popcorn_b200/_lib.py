@@ -40,6 +40,7 @@ SIGNATURES = {
     "pc_head_dense_forward": (_i, [_vp, _i, _vp, _ll, _ll, _i, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _ll, _i, _vp, _ll, _i,
                                    _vp, _vp, _i, _vp]),
     "pc_head_tc_pack_bytes": (_i, []),
+    "pc_tc_operand_format": (_i, []),
     "pc_head_dense_forward_tc": (_i, [_vp, _i, _vp, _ll, _ll, _i, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _ll, _i, _vp, _ll, _i,
                                       _vp, _vp, _i, _vp]),
     "pc_head_sparse_forward_tc": (_i, [_vp, _i, _vp, _ll, _ll, _vp, _vp, _vp, _ll, _ll, _vp, _vp, _vp, _vp]),

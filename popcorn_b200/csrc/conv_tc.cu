@@ -30,6 +30,7 @@
 //
 // Replaces model/DDA_model/utils/networks.py:253-271 (DoubleConv: Conv2d 3x3 pad 1 + BatchNorm2d(eval) + ReLU),
 // :284-295 (MaxPool2d in Down), :318 (skip concat), :323-330 (OutConv) and popcorn.py:317-320.
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -79,6 +80,9 @@ constexpr int TCN = 16;            // UMMA N (output channels, zero-padded)
 #ifndef PC_TC_OCC2
 #define PC_TC_OCC2 1
 #endif
+#ifndef PC_TC_PAIRS16
+#define PC_TC_PAIRS16 1            // <8,8,8> (Cin 16, Cout 8): 1 = two issuers with pair ownership, 0 = one issuer with 3-row windows
+#endif
 __host__ __device__ constexpr int tc_occ(int cin_a, int cin_b, int cout, int epi) {
     return (cin_a == 8 && cin_b == 0 && cout == 8 && (epi == EPI_STORE || epi == EPI_DOT) && (PC_TC_OCC2 & 1)) ? 2
          : (cin_a == 8 && cin_b == 0 && cout == 8 && epi == EPI_POOL && (PC_TC_OCC2 & 2)) ? 2
@@ -97,11 +101,12 @@ struct TcGeom {
     // MMA issue: two issuers that own alternate output row pairs (more UMMAs in flight per SM: one thread sustains one UMMA per
     // ~24 clk in this pipeline, the tensor pipe takes one per 9-13), or ONE issuer with 3-row windows (fewer, wider UMMAs).
     // Measured per layer shape (profiles/r2_conv_pipeline.md): windows win for Cin 8 and Cin 32, pairs for Cin 16 and for Cout 16.
-    static constexpr bool TWO_ISSUERS = COUT == 16 || CIN == 16;
+    static constexpr bool TWO_ISSUERS = COUT == 16 || (CIN == 16 && PC_TC_PAIRS16);
     static constexpr int BROWS = COUT == 8 ? 24 : 48;           // rows of a B matrix: [W_ky2 | W_ky1 | W_ky0] x Cout (see conv_tc_pack_layer)
-    static constexpr int KROW = (3 * CIN + 7) / 8 * 8;          // A columns per half (hi | lo) of one input row
-    static constexpr int KSTEPS = KROW / 8;
-    static constexpr int KATOMS = (KROW + 31) / 32;             // 32-float swizzle atoms along K
+    // A columns (32-bit) per half (hi | lo) of one input row: one per K element (TF32) or one per two (fp16, K padded to 16)
+    static constexpr int KROW = PC_TC_F16 ? (3 * CIN + 15) / 16 * 8 : (3 * CIN + 7) / 8 * 8;
+    static constexpr int KSTEPS = KROW / 8;                     // one UMMA consumes 8 columns = 32 B of K either way
+    static constexpr int KATOMS = (KROW + 31) / 32;             // 128-byte swizzle atoms along K
     static constexpr int BATOM = BROWS * 128;                   // bytes of one K-atom
     static constexpr int BMAT = KATOMS * BATOM;                 // bytes of one swizzled [BROWS x KROW] matrix
     static constexpr int OFF_BIAS = 2 * BMAT;                   // matrices: [hi, lo]
@@ -246,9 +251,12 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
                 if ((warp & 3) == 0 && lane == 0) TCP_TRACE(group, B, 3);
                 const float* st = stage0 + s * (G::STAGE_BYTES / 4);
                 const uint32_t tA = tbase + (uint32_t)(2 * pb + group) * G::A_COLS + lane_off;
-                auto load_split = [&](int col, uint32_t& hi, uint32_t& lo) {                 // A column = kx * CIN + ci
-                    const float val = (col < 3 * CIN) ? ((PC_TC_EXP & 4) ? (float)(col + px) : st[(col % CIN) * TC_BOXW + col / CIN]) : 0.f;
-                    split_tf32(val, hi, lo);
+                auto a_elem = [&](int k) {                                                   // A element k = kx * CIN + ci
+                    return (k < 3 * CIN) ? ((PC_TC_EXP & 4) ? (float)(k + px) : st[(k % CIN) * TC_BOXW + k / CIN]) : 0.f;
+                };
+                auto load_split = [&](int col, uint32_t& hi, uint32_t& lo) {
+                    if (PC_TC_F16) split_f16x2(a_elem(2 * col), a_elem(2 * col + 1), hi, lo);
+                    else split_tf32(a_elem(col), hi, lo);
                 };
 #if PC_TC_ST16
                 // 16-column tcgen05.st (64 B per lane and instruction): the .x8 form sustains only ~126 B/clk per SM here
@@ -263,6 +271,7 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
                         tmem_st16(tA + G::KROW + 16 * j, lo);
                     }
                 } else {                                            // KROW = 24: [hi 0..23 | lo 0..23] = 48 contiguous columns, three stores
+                    static_assert(G::KROW % 16 == 0 || G::KROW == 24, "stager store shapes");
                     uint32_t w[48];
 #pragma unroll
                     for (int q = 0; q < 24; ++q) load_split(q, w[q], w[24 + q]);
@@ -446,7 +455,7 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
             //   pair b   (rows 2b, 2b+1)  : row 2b-1 -> N=16 (row 2b) with block ky0;   row 2b -> N=32 with B blocks [ky1, ky0]
             const int q = warp - W_MMA;
             const uint32_t sW = smem_u32(sm);
-            constexpr uint32_t ID16 = umma_idesc_tf32(TCM, TCN), ID32 = umma_idesc_tf32(TCM, 2 * TCN);
+            constexpr uint32_t ID16 = tc_idesc(TCM, TCN), ID32 = tc_idesc(TCM, 2 * TCN);
             const uint64_t bd_hi = make_bdesc(sW), bd_lo = make_bdesc(sW + G::BMAT);
             constexpr uint64_t BLK = (uint64_t)((TCN * 128) >> 4);              // one 16-row block of B, in descriptor address units
             auto issue = [&](uint32_t d, uint32_t tAhi, uint64_t boff, uint32_t idesc) {
@@ -455,9 +464,9 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
                 for (int j = 0; j < G::KSTEPS; ++j) {
                     const uint64_t koff = boff + (uint64_t)(((j >> 2) * G::BATOM + (j & 3) * 32) >> 4);   // address field: 16-byte units
                     if (PC_TC_EXP & 1) continue;
-                    umma_tf32_ts(d, tAhi + 8 * j, bd_hi + koff, idesc, 1u);
-                    umma_tf32_ts(d, tAlo + 8 * j, bd_hi + koff, idesc, 1u);
-                    umma_tf32_ts(d, tAhi + 8 * j, bd_lo + koff, idesc, 1u);
+                    umma_ts(d, tAhi + 8 * j, bd_hi + koff, idesc, 1u);
+                    umma_ts(d, tAlo + 8 * j, bd_hi + koff, idesc, 1u);
+                    umma_ts(d, tAhi + 8 * j, bd_lo + koff, idesc, 1u);
                 }
             };
             int B = 0, P0 = 0;
@@ -492,7 +501,7 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
                         }
                     } else if (G::TWO_ISSUERS) {
                         // Cout 8, pair ownership: 8-column slots, a pair = 16 columns; B rows [W_ky2 | W_ky1 | W_ky0] (8 each)
-                        constexpr uint32_t ID8 = umma_idesc_tf32(TCM, 8);
+                        constexpr uint32_t ID8 = tc_idesc(TCM, 8);
                         constexpr uint64_t BLK8 = (uint64_t)((8 * 128) >> 4);   // one 8-row block of B, in descriptor address units
                         if ((Pl & 1) == q) {
                             if (b >= 1) {
@@ -511,7 +520,7 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
                         // one N = 24 UMMA per k-step and split term against B = [W_ky2 | W_ky1 | W_ky0] (12.5 clk on the tensor pipe,
                         // where two N = 16 UMMAs cost 19: tools/probe/umma_n_probe.cu — M = 128 accepts N = 8 / 24 on sm_100a).  The
                         // window is clipped at the tile's first / last row and split in two where the 8-row ring wraps.
-                        constexpr uint32_t ID8 = umma_idesc_tf32(TCM, 8), ID24 = umma_idesc_tf32(TCM, 24);
+                        constexpr uint32_t ID8 = tc_idesc(TCM, 8), ID24 = tc_idesc(TCM, 24);
                         constexpr uint64_t BLK8 = (uint64_t)((8 * 128) >> 4);   // one 8-row block of B, in descriptor address units
                         const int nrows = 2 * npairs;
                         auto window = [&](int i, uint32_t tA) {
@@ -569,8 +578,10 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
 // ---------------------------------------------------------------------------------------------------
 static int tc_brows(int cout) { return cout == 8 ? 24 : 48; }
 
+static int tc_krow(int cin) { return PC_TC_F16 ? (3 * cin + 15) / 16 * 8 : (3 * cin + 7) / 8 * 8; }   // TcGeom::KROW
+
 static int tc_geom_img_floats(int cin, int cout) {
-    const int krow = (3 * cin + 7) / 8 * 8, katoms = (krow + 31) / 32;
+    const int krow = tc_krow(cin), katoms = (krow + 31) / 32;
     return (2 * katoms * tc_brows(cout) * 128 + 64) / 4;
 }
 
@@ -580,7 +591,7 @@ int conv_tc_layer_floats(int cin, int cout) { return (int)round_up(tc_geom_img_f
 //   rows [W_ky2 | W_ky1 | W_ky0] (row cout*(2-ky) + co): 48 rows for cout 16, 24 for cout 8 — the issuers address 8- or 16-row
 //   aligned windows of it for one, two or three adjacent output rows (conv3x3_tc_kernel).
 void conv_tc_pack_layer(const float* flat, int cin, int cout, float* img) {
-    const int krow = (3 * cin + 7) / 8 * 8, katoms = (krow + 31) / 32;
+    const int krow = tc_krow(cin), katoms = (krow + 31) / 32;
     const int rows = tc_brows(cout);
     const int mat = katoms * rows * 32;                 // floats per matrix
     const int total = conv_tc_layer_floats(cin, cout);
@@ -594,19 +605,31 @@ void conv_tc_pack_layer(const float* flat, int cin, int cout, float* img) {
             for (int kx = 0; kx < 3; ++kx)
                 for (int ci = 0; ci < cin; ++ci) {
                     const float w = flat[((ci * 3 + ky) * 3 + kx) * cout + co];
+                    const int n = r0 + co;
+                    const int k = kx * cin + ci;
+#if PC_TC_F16
+                    // fp16 halves, 64 per 128-byte row of an atom; Swizzle<3,4,3>: 16-byte chunk (8 halves) ^= row % 8
+                    const __half hi = __float2half_rn(w);
+                    const __half lo = __float2half_rn(w - __half2float(hi));
+                    const int atom = k / 64, kk = k % 64;
+                    const int pos = (((kk / 8) ^ (n % 8)) * 8) + kk % 8;
+                    const int idx = atom * (rows * 64) + n * 64 + pos;
+                    __half* himg = reinterpret_cast<__half*>(img);
+                    himg[idx] = hi;
+                    himg[2 * mat + idx] = lo;                                // mat counts floats: the lo matrix starts 2 * mat halves in
+#else
                     uint32_t bits;
                     memcpy(&bits, &w, 4);
                     bits &= 0xFFFFE000u;
                     float hi;
                     memcpy(&hi, &bits, 4);
                     const float lo = w - hi;
-                    const int n = r0 + co;
-                    const int k = kx * cin + ci;
                     const int atom = k / 32, kk = k % 32;
                     const int pos = (((kk / 4) ^ (n % 8)) * 4) + kk % 4;      // Swizzle<3,4,3>: 16-B chunk ^= row % 8
                     const int idx = atom * (rows * 32) + n * 32 + pos;
                     img[idx] = hi;
                     img[mat + idx] = lo;
+#endif
                 }
     }
     for (int n = 0; n < cout; ++n) img[2 * mat + n] = flat[cin * 9 * cout + n];

@@ -42,7 +42,7 @@ __device__ long long g_head_dbg[32];
 #endif
 constexpr int TM = 128;          // pixels per tile
 constexpr int HT = 256;          // threads per CTA: two warps per TMEM lane quarter
-constexpr uint32_t IDESC = umma_idesc_tf32(128, 64);
+constexpr uint32_t IDESC = tc_idesc(128, 64);       // kind::tf32 or kind::f16 (PC_TC_F16, tc_common.cuh)
 
 // byte offsets inside the packed TC weight image (host: weights.pack_head_tc)
 constexpr int OFF_W1HI = 0, OFF_W1LO = 8192, OFF_W2HI = 16384, OFF_W2LO = 32768, OFF_W3HI = 49152, OFF_W3LO = 65536;
@@ -53,17 +53,18 @@ constexpr int OFF_TMEM = OFF_MBAR + 8;         // 4-byte TMEM base address slot
 constexpr int OFF_PART = OFF_TMEM + 8;         // float[128]: output-layer partial dot of the upper-half warps
 constexpr int TC_SMEM_BYTES = OFF_PART + 512 + 1024;   // + slack to align the base to 1024 B
 
-// one hidden layer's UMMAs: D[128x64] = A[128xK] * W[64xK]^T, K in steps of 8, three split terms per step
+// one hidden layer's UMMAs: D[128x64] = A[128xK] * W[64xK]^T, K in steps of 8 (TF32) or 16 (fp16) = 8 TMEM columns of A and 32 bytes
+// of a B row either way, three split terms per step
 template <int K>
 __device__ __forceinline__ void issue_layer(uint32_t tD, uint32_t tAhi, uint32_t tAlo, uint32_t sWhi, uint32_t sWlo,
                                             uint32_t mbar) {
 #pragma unroll
-    for (int j = 0; j < K / 8; ++j) {
-        const uint32_t koff = (uint32_t)((j >> 2) * 8192 + (j & 3) * 32);   // 32-float swizzle atoms along K
+    for (int j = 0; j < (PC_TC_F16 ? (K + 15) / 16 : K / 8); ++j) {
+        const uint32_t koff = (uint32_t)((j >> 2) * 8192 + (j & 3) * 32);   // 128-byte swizzle atoms along K
         const uint64_t bhi = make_bdesc(sWhi + koff), blo = make_bdesc(sWlo + koff);
-        umma_tf32_ts(tD, tAhi + 8 * j, bhi, IDESC, j > 0 ? 1u : 0u);
-        umma_tf32_ts(tD, tAlo + 8 * j, bhi, IDESC, 1u);
-        umma_tf32_ts(tD, tAhi + 8 * j, blo, IDESC, 1u);
+        umma_ts(tD, tAhi + 8 * j, bhi, IDESC, j > 0 ? 1u : 0u);
+        umma_ts(tD, tAlo + 8 * j, bhi, IDESC, 1u);
+        umma_ts(tD, tAhi + 8 * j, blo, IDESC, 1u);
     }
     umma_commit(mbar);
 }
@@ -74,13 +75,25 @@ __device__ __forceinline__ void epilogue_hidden(uint32_t tD, uint32_t tAhi, uint
     // allocated per four warps, 65 536 / 640 threads)
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-        uint32_t v[16], lo[16];
+        uint32_t v[16];
         tmem_ld16(tD + 16 * q, v);
         tc_wait_ld();
+#if PC_TC_F16
+        // fp16 halves: hidden units (2i, 2i+1) share a column — the thread's 32 units become 16 + 16 columns (tAhi / tAlo point at them)
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            split_f16x2(fmaxf(__uint_as_float(v[2 * i]) + bias[16 * q + 2 * i], 0.f), fmaxf(__uint_as_float(v[2 * i + 1]) + bias[16 * q + 2 * i + 1], 0.f),
+                        hi[i], lo[i]);
+        tmem_st8(tAhi + 8 * q, hi);
+        tmem_st8(tAlo + 8 * q, lo);
+#else
+        uint32_t lo[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) split_tf32(fmaxf(__uint_as_float(v[i]) + bias[16 * q + i], 0.f), v[i], lo[i]);
         tmem_st16(tAhi + 16 * q, v);
         tmem_st16(tAlo + 16 * q, lo);
+#endif
     }
 }
 
@@ -90,11 +103,20 @@ __device__ __forceinline__ void epilogue_hidden(uint32_t tD, uint32_t tAhi, uint
 // context's UMMAs instead of the two drifting into the same phase.  Hand-offs are mbarriers: workers -> issuer a_ready[c]
 // (8 warp arrivals), issuer -> workers d_ready[c] (tcgen05.commit).
 constexpr int HWORK = 256;                       // worker threads per context
-constexpr int HTHREADS = 2 * HWORK + 32;
+#ifndef PC_HEAD_NCTX
+#define PC_HEAD_NCTX (PC_TC_F16 ? 3 : 2)   // tile contexts per CTA: three fit the tensor memory with fp16 operands (160 columns each)
+#endif
+constexpr int NCTX = PC_HEAD_NCTX;
+constexpr int HTHREADS = NCTX * HWORK + 32;
+// tensor-memory columns of one context: accumulator D | A_hi | A_lo of the hidden layers | A1_hi | A1_lo (layer-1 features of the next tile)
+constexpr uint32_t A_COLS = PC_TC_F16 ? 32 : 64, A1_COLS = PC_TC_F16 ? 8 : 16;
+constexpr uint32_t C_AHI = 64, C_ALO = C_AHI + A_COLS, C_A1HI = C_ALO + A_COLS, C_A1LO = C_A1HI + A1_COLS;
+constexpr uint32_t CTX_COLS = (C_A1LO + A1_COLS + 31) / 32 * 32;
+static_assert(NCTX * CTX_COLS <= 512 && NCTX >= 2 && NCTX <= 4, "tensor-memory budget of the tile contexts");
 constexpr int OFF_BARS2 = OFF_MBAR;              // a_ready[2], d_ready[2]
-constexpr int OFF_TMEM2 = OFF_BARS2 + 32;
-constexpr int OFF_PART2 = OFF_TMEM2 + 16;        // float[2][128]
-constexpr int TC2_SMEM_BYTES = (OFF_PART2 + 1024 + 1024) > 116 * 1024 ? (OFF_PART2 + 1024 + 1024) : 116 * 1024;   // > half an SM: one CTA per SM
+constexpr int OFF_TMEM2 = OFF_BARS2 + 64;
+constexpr int OFF_PART2 = OFF_TMEM2 + 16;        // float[NCTX][128]
+constexpr int TC2_SMEM_BYTES = (OFF_PART2 + 512 * NCTX + 1024) > 116 * 1024 ? (OFF_PART2 + 512 * NCTX + 1024) : 116 * 1024;   // > half an SM: one CTA per SM
 
 template <int K1, bool SPARSE, bool SMALL>
 __global__ void __launch_bounds__(HTHREADS, 1) head_tc_kernel(const __grid_constant__ HeadArgs a) {
@@ -106,16 +128,15 @@ __global__ void __launch_bounds__(HTHREADS, 1) head_tc_kernel(const __grid_const
     const float* b1 = vec, *b2 = vec + 64, *b3 = vec + 128, *w4 = vec + 192, *b4 = vec + 256;
     const uint32_t bars = smem_u32(sm + OFF_BARS2);
     auto a_ready = [&](int c) { return bars + 8u * (uint32_t)c; };
-    auto d_ready = [&](int c) { return bars + 16u + 8u * (uint32_t)c; };
+    auto d_ready = [&](int c) { return bars + 8u * NCTX + 8u * (uint32_t)c; };
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + OFF_TMEM2);
     const int tid = threadIdx.x, warp = uniform_warp_idx();
 
     for (int i = tid; i < TC_PACK_BYTES / 16; i += HTHREADS)
         reinterpret_cast<int4*>(sm)[i] = __ldg(reinterpret_cast<const int4*>(a.pack) + i);
-    if (warp == 16) tmem_alloc(smem_u32(tmem_slot), 512);
+    if (warp == 8 * NCTX) tmem_alloc(smem_u32(tmem_slot), 512);
     if (tid == 0) {
-        mbar_init(a_ready(0), 8); mbar_init(a_ready(1), 8);
-        mbar_init(d_ready(0), 1); mbar_init(d_ready(1), 1);
+        for (int c = 0; c < NCTX; ++c) { mbar_init(a_ready(c), 8); mbar_init(d_ready(c), 1); }
         mbar_init_fence();
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // weight image (generic stores) -> visible to UMMA
@@ -128,9 +149,9 @@ __global__ void __launch_bounds__(HTHREADS, 1) head_tc_kernel(const __grid_const
     const long long HW = SPARSE ? a.HW : (long long)a.H * a.W;
     const long long total = SPARSE ? (long long)__ldg(a.n_dev) : HW * a.B;
     const long long ntiles = (total + TM - 1) / TM;
-    const long long stride = 2ll * gridDim.x;                       // tiles are dealt to (CTA, context) round-robin
+    const long long stride = (long long)NCTX * gridDim.x;                       // tiles are dealt to (CTA, context) round-robin
 
-    if (warp < 16) {
+    if (warp < 8 * NCTX) {
         // =========================== workers of context c ===========================
         const int c = warp >> 3;
         const int wl = warp & 7, lane = tid & 31;
@@ -140,9 +161,10 @@ __global__ void __launch_bounds__(HTHREADS, 1) head_tc_kernel(const __grid_const
         const bool stager = K1 >= 16 || half == 0;
         const int c_lo = K1 >= 16 ? half * CH : 0;
         const uint32_t lane_off = (uint32_t)((wl & 3) * 32) << 16;     // a warp may touch TMEM lanes 32*(warp%4) .. +31
-        const uint32_t tD = tbase + 256u * c, tAhi = tD + 64, tAlo = tD + 128;
-        const uint32_t tA1hi = tD + 192, tA1lo = tD + 208;      // layer-1 operand (features) of the NEXT tile: own columns, staged early
-        const uint32_t col_off = (uint32_t)(32 * half);
+        const uint32_t tD = tbase + CTX_COLS * c, tAhi = tD + C_AHI, tAlo = tD + C_ALO;
+        const uint32_t tA1hi = tD + C_A1HI, tA1lo = tD + C_A1LO;      // layer-1 operand (features) of the NEXT tile: own columns, staged early
+        const uint32_t col_off = (uint32_t)(32 * half);                 // this thread's accumulator columns = hidden units
+        const uint32_t acol_off = PC_TC_F16 ? col_off / 2 : col_off;    // ... and where they go in the next layer's A operand
         float* part = reinterpret_cast<float*>(sm + OFF_PART2) + 128 * c;
         uint32_t ph = 0;                                 // phase counter of both barriers of this context
 
@@ -188,7 +210,7 @@ __global__ void __launch_bounds__(HTHREADS, 1) head_tc_kernel(const __grid_const
 #endif
         float fcur[CH];        // ONE register set: consumed at the top of a tile, refilled (next tile) while layer 2 runs — no copy, a
                                // MOV of a register an outstanding load still has to fill would wait for DRAM
-        long long tile = 2ll * blockIdx.x + c;
+        long long tile = (long long)NCTX * blockIdx.x + c;
         bool valid;
         long long p_cur = pixel_of(tile, valid);
         {
@@ -199,6 +221,20 @@ __global__ void __launch_bounds__(HTHREADS, 1) head_tc_kernel(const __grid_const
 
         // layer-1 A operand: this pixel's features (this thread's channel half), split, into the context's A1 columns
         auto stage_features = [&]() {
+#if PC_TC_F16
+            if (stager) {                                // CH = 8 channels -> 4 columns of fp16 pairs; K1 = 8 pads K to 16 with 4 zero columns
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { split_f16x2(fcur[2 * k], fcur[2 * k + 1], hi[k], lo[k]); hi[4 + k] = 0u; lo[4 + k] = 0u; }
+                if (K1 >= 16) {
+                    tmem_st4(tA1hi + lane_off + c_lo / 2, reinterpret_cast<uint32_t(&)[4]>(hi[0]));
+                    tmem_st4(tA1lo + lane_off + c_lo / 2, reinterpret_cast<uint32_t(&)[4]>(lo[0]));
+                } else {
+                    tmem_st8(tA1hi + lane_off, hi);
+                    tmem_st8(tA1lo + lane_off, lo);
+                }
+            }
+#else
             if (stager) {
 #pragma unroll
                 for (int c0 = 0; c0 < CH; c0 += 8) {
@@ -209,6 +245,7 @@ __global__ void __launch_bounds__(HTHREADS, 1) head_tc_kernel(const __grid_const
                     tmem_st8(tA1lo + lane_off + c_lo + c0, lo);
                 }
             }
+#endif
         };
         if (tile < ntiles) { stage_features(); hand_over(); }      // first tile of this context: layer 1 may run
 
@@ -218,7 +255,7 @@ __global__ void __launch_bounds__(HTHREADS, 1) head_tc_kernel(const __grid_const
             HP_T(h1);
             wait_d();
             HP_T(h2);
-            epilogue_hidden(tD + lane_off + col_off, tAhi + lane_off + col_off, tAlo + lane_off + col_off, b1 + col_off);
+            epilogue_hidden(tD + lane_off + col_off, tAhi + lane_off + acol_off, tAlo + lane_off + acol_off, b1 + col_off);
             HP_T(g0);
             hand_over();
             HP_T(g1);
@@ -242,7 +279,7 @@ __global__ void __launch_bounds__(HTHREADS, 1) head_tc_kernel(const __grid_const
             HP_T(h3);
             wait_d();
             HP_T(h4);
-            epilogue_hidden(tD + lane_off + col_off, tAhi + lane_off + col_off, tAlo + lane_off + col_off, b2 + col_off);
+            epilogue_hidden(tD + lane_off + col_off, tAhi + lane_off + acol_off, tAlo + lane_off + acol_off, b2 + col_off);
             hand_over();
             // ---- while layer 3's UMMAs run: the NEXT tile's features (loaded during layer 2) go into the A1 columns, which no UMMA in
             //      flight reads; the issuer learns about them only after this tile's accumulator has been read (below)
@@ -309,13 +346,14 @@ __global__ void __launch_bounds__(HTHREADS, 1) head_tc_kernel(const __grid_const
 #endif
     } else if (elect_one()) {
         // =========================== UMMA issuer: strict alternation between the two contexts ===========================
-        long long n[2];
-        for (int c = 0; c < 2; ++c) {
-            const long long first = 2ll * blockIdx.x + c;
+        long long n[NCTX], rounds = 0;
+        uint32_t ph[NCTX];
+        for (int c = 0; c < NCTX; ++c) {
+            const long long first = (long long)NCTX * blockIdx.x + c;
             n[c] = first < ntiles ? (ntiles - first + stride - 1) / stride : 0;
+            rounds = n[c] > rounds ? n[c] : rounds;
+            ph[c] = 0;
         }
-        const long long rounds = n[0] > n[1] ? n[0] : n[1];
-        uint32_t ph[2] = {0, 0};
 #if PC_HEAD_PROBE
         long long hp_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
@@ -326,14 +364,14 @@ __global__ void __launch_bounds__(HTHREADS, 1) head_tc_kernel(const __grid_const
                 // not unrolled over the contexts / layers: six inlined copies of issue_layer need more descriptor registers than the
                 // kernel's 96 and the issuing thread then reloads spilled operands from local memory between two UMMAs
 #pragma unroll 1
-                for (int c = 0; c < 2; ++c) {
+                for (int c = 0; c < NCTX; ++c) {
                     if (k >= n[c]) continue;
-                    const uint32_t tD = tbase + 256u * c, tAhi = tD + 64, tAlo = tD + 128;
+                    const uint32_t tD = tbase + CTX_COLS * c, tAhi = tD + C_AHI, tAlo = tD + C_ALO;
                     HP_T(i0);
                     HEAD_WAIT(a_ready(c), ph[c] & 1u); ++ph[c];
                     tc_fence_after();
                     HP_T(i1);
-                    if (layer == 0) issue_layer<K1>(tD, tD + 192, tD + 208, sW + OFF_W1HI, sW + OFF_W1LO, d_ready(c));
+                    if (layer == 0) issue_layer<K1>(tD, tD + C_A1HI, tD + C_A1LO, sW + OFF_W1HI, sW + OFF_W1LO, d_ready(c));
                     else if (layer == 1) issue_layer<HN>(tD, tAhi, tAlo, sW + OFF_W2HI, sW + OFF_W2LO, d_ready(c));
                     else issue_layer<HN>(tD, tAhi, tAlo, sW + OFF_W3HI, sW + OFF_W3LO, d_ready(c));
                     HP_T(i2);
@@ -348,7 +386,7 @@ __global__ void __launch_bounds__(HTHREADS, 1) head_tc_kernel(const __grid_const
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 16) tmem_dealloc(tbase, 512);
+    if (warp == 8 * NCTX) tmem_dealloc(tbase, 512);
 }
 
 template <int K1, bool SPARSE, bool SMALL>
@@ -357,7 +395,7 @@ static int launch_head_tc_impl(const HeadArgs& a, long long total_bound, cudaStr
     PC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES));
     long long tiles = (total_bound + TM - 1) / TM;
     const int maxg = num_sms();              // persistent: one CTA per SM (it owns all 512 TMEM columns), two tile contexts each
-    int grid = (int)((tiles + 1) / 2 < maxg ? (tiles + 1) / 2 : maxg);
+    int grid = (int)((tiles + NCTX - 1) / NCTX < maxg ? (tiles + NCTX - 1) / NCTX : maxg);
     if (grid < 1) grid = 1;
     {
         static const int cat = prof_register(SPARSE ? "head_tc<sparse>" : "head_tc<dense>");
@@ -380,6 +418,7 @@ static int launch_head_tc(const HeadArgs& a, long long total_bound, cudaStream_t
 using namespace pc;
 
 extern "C" int pc_head_tc_pack_bytes(void) { return TC_PACK_BYTES; }
+extern "C" int pc_tc_operand_format(void) { return PC_TC_F16; }
 #if PC_HEAD_PROBE
 extern "C" int pc_debug_head_counters(long long* out32) {
     cudaDeviceSynchronize();

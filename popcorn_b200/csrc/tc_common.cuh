@@ -9,6 +9,15 @@
 #pragma once
 #include "common.cuh"
 
+// Operand format of the split products D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo (both tensor-core kernels):
+//   0: TF32 halves (kind::tf32, K = 8 per UMMA, one TMEM column per A element)
+//   1: fp16 halves (kind::f16, K = 16 per UMMA, two A elements per TMEM column): the same 11 + 11 significand bits in half the
+//      tcgen05.st bytes and half the UMMAs (conv Cin = 8: two thirds, its K = 24 pads to 32); accuracy through the whole path:
+//      tools/precision_split_study.py / profiles/r2_split_precision_study.txt
+#ifndef PC_TC_F16
+#define PC_TC_F16 1
+#endif
+
 namespace pc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -32,6 +41,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(uint32_t M, uint32_t N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// kind::f16 with fp16 operands (A = B = F16: format 0), fp32 accumulation: K = 16 per instruction at the rate kind::tf32 has for K = 8
+__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N) {
+    return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
 // start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major, 1) | SBO>>4 [32,46) = 1024 B between 8-row groups |
 // version 1 [46,48) | layout SWIZZLE_128B = 2 [61,64)
@@ -48,6 +62,22 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
         ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
         : "memory");
 }
+// the same with fp16 operands: a 32-bit TMEM column of A holds K elements 2c (low half) and 2c+1 (high half)
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}\n"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
+        : "memory");
+}
+#if PC_TC_F16
+#define umma_ts umma_f16_ts
+__host__ __device__ constexpr uint32_t tc_idesc(uint32_t M, uint32_t N) { return umma_idesc_f16(M, N); }
+#else
+#define umma_ts umma_tf32_ts
+__host__ __device__ constexpr uint32_t tc_idesc(uint32_t M, uint32_t N) { return umma_idesc_tf32(M, N); }
+#endif
 __device__ __forceinline__ void umma_commit(uint32_t mbar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
 }
@@ -82,6 +112,9 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
                  ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
                    "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
                  : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
 }
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
@@ -164,6 +197,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
     hi = __float_as_uint(x) & 0xFFFFE000u;
     lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+// (x0, x1) = hi + lo with fp16 halves packed as f16x2 (x0 in the low half): 11 + 11 significand bits like the TF32 split, in half the
+// operand bytes.  fp16 keeps 5 exponent bits: lo parts below 6e-5 are subnormal (absolute error <= 3e-8, tools/precision_split_study.py)
+// and |x| > 65504 saturates instead of overflowing to inf (hi = 65504, lo = the rest, up to 131008).
+__device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+    float h0, h1;
+    asm("{\n\t.reg .b16 a, b;\n\tmov.b32 {a, b}, %2;\n\tcvt.f32.f16 %0, a;\n\tcvt.f32.f16 %1, b;\n\t}" : "=f"(h0), "=f"(h1) : "r"(hi));
+    const float r0 = x0 - h0, r1 = x1 - h1;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
 }
 
 }  // namespace pc

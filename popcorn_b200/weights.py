@@ -151,12 +151,49 @@ def _swizzle_k_major_128b(w: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def _split_f16(w: torch.Tensor):
+    """w = hi + lo with fp16 halves (11 + 11 significand bits like the TF32 split; |w| > 65504 saturates)."""
+    w = w.clamp(-65504.0, 65504.0)
+    hi = w.to(torch.float16)
+    return hi, (w - hi.float()).clamp(-65504.0, 65504.0).to(torch.float16)
+
+
+def _swizzle_k_major_128b_f16(h: torch.Tensor, slot_floats: int) -> torch.Tensor:
+    """[64, K <= 64] fp16 -> one 128-byte-row atom [64 rows][64 halves], 16-byte chunks (8 halves) XOR-swizzled with (n % 8), returned
+    as a float32 view padded with zeros to the matrix's slot in the image (the slots keep their TF32 sizes)."""
+    N, K = h.shape
+    assert N == 64 and K <= 64
+    key = ("f16", K, str(h.device))
+    dst = _SWIZZLE_DST.get(key)
+    if dst is None:
+        n = torch.arange(N, device=h.device).view(N, 1)
+        k = torch.arange(K, device=h.device).view(1, -1)
+        dst = (n * 64 + ((k // 8) ^ (n % 8)) * 8 + k % 8).reshape(-1)
+        _SWIZZLE_DST[key] = dst
+    out = torch.zeros(2 * slot_floats, dtype=torch.float16, device=h.device)
+    out[dst] = h.reshape(-1)
+    return out.view(torch.float32)
+
+
+def tc_operand_format() -> int:
+    """0 = TF32 halves, 1 = fp16 halves: what the loaded library's tensor-core kernels multiply (pc_tc_operand_format)."""
+    from . import _lib
+    return int(_lib.lib().pc_tc_operand_format())
+
+
 def pack_head_tc(sd: Dict[str, torch.Tensor]) -> torch.Tensor:
     """Weight image of csrc/head_tc.cu (byte offsets OFF_* there): W1hi W1lo (8 KB each, K padded to 32), W2hi W2lo
-    W3hi W3lo (16 KB each), then b1 b2 b3 w4 (64 floats each) and b4 (+3 pad).  float32 tensor of 20 740 elements."""
+    W3hi W3lo (16 KB each), then b1 b2 b3 w4 (64 floats each) and b4 (+3 pad).  float32 tensor of 20 740 elements.
+    The matrices hold TF32 or fp16 halves, whichever the library was built for (tc_operand_format)."""
     parts = []
+    f16 = tc_operand_format() == 1
     for i in (0, 2, 4):
         w = sd[f"head.{i}.weight"].detach().float().flatten(1)             # [64 out, K in]  == UMMA B operand, K-major
+        if f16:
+            hi, lo = _split_f16(w)
+            slot = 2048 if i == 0 else 4096
+            parts += [_swizzle_k_major_128b_f16(hi, slot), _swizzle_k_major_128b_f16(lo, slot)]
+            continue
         hi, lo = _split_tf32(w)
         parts += [_swizzle_k_major_128b(hi), _swizzle_k_major_128b(lo)]
     parts += [sd[f"head.{i}.bias"].detach().float() for i in (0, 2, 4)]

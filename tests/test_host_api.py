@@ -145,9 +145,10 @@ def test_cpu_tensors_are_rejected_loudly(sd):
 @pytest.mark.parametrize("cin,cout", [(2, 8), (4, 8), (8, 16), (16, 16), (32, 8)])
 def test_conv_tc_weight_image_layout(cin, cout):
     """Host packer of the tcgen05 conv weights (include/popcorn_b200.h "Tensor-core weight section"): de-swizzling the
-    image gives back the rows [W_ky2 | W_ky1 | W_ky0] (Cout rows each: 48 for Cout 16, 24 for Cout 8) with hi + lo == w exactly, hi a
-    TF32 number, zero columns as padding."""
+    image gives back the rows [W_ky2 | W_ky1 | W_ky0] (Cout rows each: 48 for Cout 16, 24 for Cout 8), zero columns as padding, with
+    hi + lo == w exactly and hi a TF32 number (operand format 0), or fp16 halves with |hi + lo - w| <= 2^-21 |w| (format 1)."""
     L = _lib.lib()
+    f16 = L.pc_tc_operand_format() == 1
     g = torch.Generator().manual_seed(cin * 31 + cout)
     w = torch.randn(cout, cin, 3, 3, generator=g)
     b = torch.randn(cout, generator=g)
@@ -155,25 +156,67 @@ def test_conv_tc_weight_image_layout(cin, cout):
     n = L.pc_conv_tc_layer_floats(cin, cout)
     img = torch.full((n,), float("nan"))
     _lib.check(L.pc_conv_tc_pack_layer(flat.data_ptr(), cin, cout, img.data_ptr()))
-    krow = (3 * cin + 7) // 8 * 8
+    krow = (3 * cin + 15) // 16 * 8 if f16 else (3 * cin + 7) // 8 * 8       # 32-bit A columns per half = TcGeom::KROW
     katoms = (krow + 31) // 32
     nrows = 3 * cout
-    mat = katoms * nrows * 32
+    mat = katoms * nrows * 32                                        # floats per matrix
     assert n % 64 == 0 and n >= 2 * mat + 16
-    mats = img[:2 * mat].view(2, katoms, nrows, 32)
+    E = 64 if f16 else 32                                            # elements per 128-byte row of a swizzle atom
+    mats = (img[:2 * mat].view(torch.float16).float() if f16 else img[:2 * mat]).view(2, katoms, nrows, E)
     rows = torch.arange(nrows).view(nrows, 1)
-    kk = torch.arange(32).view(1, 32)
-    pos = ((kk // 4) ^ (rows % 8)) * 4 + kk % 4                     # Swizzle<3,4,3>
-    de = torch.gather(mats, 3, pos.expand(2, katoms, nrows, 32))    # de[h][atom][n][kk]
-    de = de.permute(0, 2, 1, 3).reshape(2, nrows, katoms * 32)      # [hi|lo][row][k]
+    kk = torch.arange(E).view(1, E)
+    per = E // 8                                                     # elements per 16-byte chunk
+    pos = ((kk // per) ^ (rows % 8)) * per + kk % per                # Swizzle<3,4,3>: 16-byte chunk ^= row % 8
+    de = torch.gather(mats, 3, pos.expand(2, katoms, nrows, E))      # de[h][atom][n][kk]
+    de = de.permute(0, 2, 1, 3).reshape(2, nrows, katoms * E)        # [hi|lo][row][k]
     hi, lo = de[0], de[1]
-    want = torch.zeros(nrows, katoms * 32)
+    want = torch.zeros(nrows, katoms * E)
     wk = lambda ky: w[:, :, ky, :].permute(0, 2, 1).reshape(cout, 3 * cin)        # [co][kx*cin+ci]
     for ky in range(3):     # [W_ky2 | W_ky1 | W_ky0]
         want[cout * (2 - ky): cout * (2 - ky) + cout, :3 * cin] = wk(ky)
-    assert torch.equal(hi + lo, want)
-    assert torch.equal(hi.view(torch.int32) & 0x1FFF, torch.zeros_like(hi, dtype=torch.int32))
+    if f16:
+        assert torch.equal(hi, want.half().float())
+        assert float(((hi.double() + lo.double()) - want.double()).abs().max()) <= 2.0 ** -21 * float(want.abs().max())
+        assert float((hi + lo)[:, 3 * cin:].abs().sum()) == 0
+    else:
+        assert torch.equal(hi + lo, want)
+        assert torch.equal(hi.view(torch.int32) & 0x1FFF, torch.zeros_like(hi, dtype=torch.int32))
     assert torch.equal(img[2 * mat: 2 * mat + cout], b) and float(img[2 * mat + cout: 2 * mat + 16].abs().sum()) == 0
+
+
+def test_head_tc_weight_image_layout():
+    """weights.pack_head_tc: the three [64 x K] matrices sit at the byte offsets csrc/head_tc.cu names (W1hi 0, W1lo 8192, W2hi 16384,
+    W2lo 32768, W3hi 49152, W3lo 65536, vectors at 81920) in the library's operand format, K-major SWIZZLE_128B, and hi + lo gives the
+    weight back (exactly for TF32 halves, to 2^-21 for fp16 halves)."""
+    from popcorn_b200 import weights
+    sd = po.random_state_dict(seed=5)
+    img = weights.pack_head_tc(sd)
+    L = _lib.lib()
+    assert img.numel() * 4 == L.pc_head_tc_pack_bytes() == 82960
+    f16 = L.pc_tc_operand_format() == 1
+    E = 64 if f16 else 32
+    per = E // 8
+    rows = torch.arange(64).view(64, 1)
+    kk = torch.arange(E).view(1, E)
+    pos = ((kk // per) ^ (rows % 8)) * per + kk % per
+    for i, off_hi, off_lo in ((0, 0, 8192), (2, 16384, 32768), (4, 49152, 65536)):
+        w = sd[f"head.{i}.weight"].flatten(1)
+        K = w.shape[1]
+        katoms = (K + E - 1) // E
+        halves = []
+        for off in (off_hi, off_lo):
+            raw = img[off // 4: off // 4 + katoms * 2048]                       # one atom = 64 rows x 128 B
+            m = (raw.view(torch.float16).float() if f16 else raw).view(katoms, 64, E)
+            halves.append(torch.gather(m, 2, pos.expand(katoms, 64, E)).permute(1, 0, 2).reshape(64, katoms * E))
+        hi, lo = halves
+        assert float(hi[:, K:].abs().sum()) == 0 and float(lo[:, K:].abs().sum()) == 0
+        if f16:
+            assert torch.equal(hi[:, :K], w.half().float())
+            assert float((hi[:, :K].double() + lo[:, :K].double() - w.double()).abs().max()) <= 2.0 ** -21 * float(w.abs().max())
+        else:
+            assert torch.equal(hi[:, :K] + lo[:, :K], w)
+    vec = img[81920 // 4:]
+    assert torch.equal(vec[:64], sd["head.0.bias"]) and torch.equal(vec[192:256], sd["head.6.weight"].flatten(1)[0])
 
 
 def test_raw_raster_validation_and_no_cpu_path():

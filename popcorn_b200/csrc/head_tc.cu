@@ -55,6 +55,10 @@ constexpr int TC_SMEM_BYTES = OFF_PART + 512 + 1024;   // + slack to align the b
 
 // one hidden layer's UMMAs: D[128x64] = A[128xK] * W[64xK]^T, K in steps of 8 (TF32) or 16 (fp16) = 8 TMEM columns of A and 32 bytes
 // of a B row either way, three split terms per step
+// fp16 build: the layer's bias rides in the UMMAs — the A operand carries a constant column pair (1, 0) behind its K columns and the
+// weight image the bias (hi | lo) as K row Kpad — instead of 32 FADDs per thread and layer in epilogues that are bound by instruction
+// issue (the tensor pipe has the headroom: 12 -> 14 UMMAs per hidden layer)
+constexpr bool BIAS_MMA = PC_TC_F16 != 0;
 template <int K>
 __device__ __forceinline__ void issue_layer(uint32_t tD, uint32_t tAhi, uint32_t tAlo, uint32_t sWhi, uint32_t sWlo,
                                             uint32_t mbar) {
@@ -65,6 +69,12 @@ __device__ __forceinline__ void issue_layer(uint32_t tD, uint32_t tAhi, uint32_t
         umma_ts(tD, tAhi + 8 * j, bhi, IDESC, j > 0 ? 1u : 0u);
         umma_ts(tD, tAlo + 8 * j, bhi, IDESC, 1u);
         umma_ts(tD, tAhi + 8 * j, blo, IDESC, 1u);
+    }
+    if (BIAS_MMA) {
+        constexpr int j = (K + 15) / 16;                                    // the k-step behind the layer's own K: (1, 0 | zeros) x bias row
+        const uint32_t koff = (uint32_t)((j >> 2) * 8192 + (j & 3) * 32);
+        umma_ts(tD, tAhi + 8 * j, make_bdesc(sWhi + koff), IDESC, 1u);
+        umma_ts(tD, tAhi + 8 * j, make_bdesc(sWlo + koff), IDESC, 1u);
     }
     umma_commit(mbar);
 }
@@ -83,8 +93,7 @@ __device__ __forceinline__ void epilogue_hidden(uint32_t tD, uint32_t tAhi, uint
         uint32_t hi[8], lo[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-            split_f16x2(fmaxf(__uint_as_float(v[2 * i]) + bias[16 * q + 2 * i], 0.f), fmaxf(__uint_as_float(v[2 * i + 1]) + bias[16 * q + 2 * i + 1], 0.f),
-                        hi[i], lo[i]);
+            split_f16x2(fmaxf(__uint_as_float(v[2 * i]), 0.f), fmaxf(__uint_as_float(v[2 * i + 1]), 0.f), hi[i], lo[i]);   // bias: BIAS_MMA
         tmem_st8(tAhi + 8 * q, hi);
         tmem_st8(tAlo + 8 * q, lo);
 #else
@@ -109,9 +118,10 @@ constexpr int HWORK = 256;                       // worker threads per context
 constexpr int NCTX = PC_HEAD_NCTX;
 constexpr int HTHREADS = NCTX * HWORK + 32;
 // tensor-memory columns of one context: accumulator D | A_hi | A_lo of the hidden layers | A1_hi | A1_lo (layer-1 features of the next tile)
-constexpr uint32_t A_COLS = PC_TC_F16 ? 32 : 64, A1_COLS = PC_TC_F16 ? 8 : 16;
-constexpr uint32_t C_AHI = 64, C_ALO = C_AHI + A_COLS, C_A1HI = C_ALO + A_COLS, C_A1LO = C_A1HI + A1_COLS;
-constexpr uint32_t CTX_COLS = (C_A1LO + A1_COLS + 31) / 32 * 32;
+// (fp16 build: the hi halves end with the 8 columns of the constant bias k-step)
+constexpr uint32_t AHI_COLS = PC_TC_F16 ? 32 + 8 : 64, ALO_COLS = PC_TC_F16 ? 32 : 64, A1HI_COLS = PC_TC_F16 ? 8 + 8 : 16, A1LO_COLS = PC_TC_F16 ? 8 : 16;
+constexpr uint32_t C_AHI = 64, C_ALO = C_AHI + AHI_COLS, C_A1HI = C_ALO + ALO_COLS, C_A1LO = C_A1HI + A1HI_COLS;
+constexpr uint32_t CTX_COLS = (C_A1LO + A1LO_COLS + 31) / 32 * 32;
 static_assert(NCTX * CTX_COLS <= 512 && NCTX >= 2 && NCTX <= 4, "tensor-memory budget of the tile contexts");
 constexpr int OFF_BARS2 = OFF_MBAR;              // a_ready[2], d_ready[2]
 constexpr int OFF_TMEM2 = OFF_BARS2 + 64;
@@ -167,35 +177,68 @@ __global__ void __launch_bounds__(HTHREADS, 1) head_tc_kernel(const __grid_const
         const uint32_t acol_off = PC_TC_F16 ? col_off / 2 : col_off;    // ... and where they go in the next layer's A operand
         float* part = reinterpret_cast<float*>(sm + OFF_PART2) + 128 * c;
         uint32_t ph = 0;                                 // phase counter of both barriers of this context
+        if (BIAS_MMA && half == 0) {                     // the constant k-step of both A operands: K element Kpad = 1.0, the rest zero
+            const uint32_t one[8] = {0x00003C00u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};      // fp16 pair (1.0, 0.0)
+            tmem_st8(tAhi + lane_off + 32, one);
+            tmem_st8(tA1hi + lane_off + 8, one);
+            tc_wait_st();
+        }
 
-        // Between the phases of a tile only the pixel's linear index travels in registers; (image, row, column) and the tensor offsets
-        // are re-derived where they are used.  32-bit divisions whenever the batch has fewer than 2^31 pixels (always, for the sparse
-        // index list): the 64-bit software division costs ~150 instructions and registers the epilogues need.
-        // SMALL (chosen by the host: fewer than 2^31 pixels in the batch — always, for the sparse index list) selects 32-bit divisions
-        // at compile time: as a run-time select the compiler evaluated BOTH sides, i.e. two ~150-instruction 64-bit software
-        // divisions per call and three calls per tile and thread.
-        struct Pos { int b, y, x; long long r; };
-        auto decompose = [&](long long p) {
-            Pos q;
-            if (SMALL) { q.b = (int)((uint32_t)p / (uint32_t)HW); q.r = (long long)((uint32_t)p - (uint32_t)q.b * (uint32_t)HW); }
-            else { q.b = (int)(p / HW); q.r = p - (long long)q.b * HW; }
-            q.y = 0; q.x = 0;
-            if (!SPARSE) {
-                if (SMALL) q.y = (int)((uint32_t)q.r / (uint32_t)a.W);
-                else q.y = (int)(q.r / a.W);
-                q.x = (int)(q.r - (long long)q.y * a.W);
+        // Where a thread's pixel is: (image, row, column) for the dense map, (image, pixel inside the image) for the sparse index list.
+        // The dense position ADVANCES by a constant number of pixels per tile (stride * 128), so it is updated with two compare-and-wrap
+        // steps instead of being re-derived from a linear index: the divisions (three uses x two divisions per tile and thread, ~100
+        // instructions of a loop that is bound by instruction issue) happen once per thread.  The sparse position comes from the index
+        // list and costs one 32-bit division per tile (the host picks SMALL whenever the batch has fewer than 2^31 pixels — always for
+        // the int32 index list; the 64-bit software division costs ~150 instructions).
+        struct Pos { int b, y, x; };
+        int step_b = 0, step_y = 0, step_x = 0;
+        if (!SPARSE) {
+            const long long S = stride * TM;
+            step_b = (int)(S / HW);
+            const long long r = S - (long long)step_b * HW;
+            step_y = (int)(r / a.W);
+            step_x = (int)(r - (long long)step_y * a.W);
+        }
+        auto advance = [&](Pos q) {                      // dense: the same lane's pixel of the context's next tile
+            q.x += step_x; if (q.x >= a.W) { q.x -= a.W; ++q.y; }
+            q.y += step_y; if (q.y >= a.H) { q.y -= a.H; ++q.b; }
+            q.b += step_b;
+            return q;
+        };
+        auto locate_first = [&](long long tile, bool& valid) {
+            Pos q{0, 0, 0};
+            const long long i = tile * TM + px;
+            if (SPARSE) {
+                valid = tile < ntiles && i < total;
+                if (valid) {
+                    const uint32_t p = (uint32_t)__ldg(a.idx + i);
+                    q.b = (int)(p / (uint32_t)HW);
+                    q.x = (int)(p - (uint32_t)q.b * (uint32_t)HW);
+                }
+            } else {
+                if (SMALL) {
+                    q.b = (int)((uint32_t)i / (uint32_t)HW);
+                    const uint32_t r = (uint32_t)i - (uint32_t)q.b * (uint32_t)HW;
+                    q.y = (int)(r / (uint32_t)a.W);
+                    q.x = (int)(r - (uint32_t)q.y * (uint32_t)a.W);
+                } else {
+                    const long long b = i / HW, r = i - b * HW;
+                    q.b = b > a.B ? a.B : (int)b;
+                    q.y = (int)(r / a.W);
+                    q.x = (int)(r - (long long)q.y * a.W);
+                }
+                valid = q.b < a.B;
             }
             return q;
         };
-        auto pixel_of = [&](long long tile, bool& valid) -> long long {     // linear pixel index (dense) / compacted position's pixel (sparse)
-            const long long i = tile * TM + px;
-            valid = tile < ntiles && i < total;
-            if (!valid) return 0;
-            return SPARSE ? (long long)__ldg(a.idx + i) : i;
+        auto locate_next = [&](const Pos& cur, long long tile, bool& valid) {
+            if (SPARSE) return locate_first(tile, valid);
+            const Pos q = advance(cur);
+            valid = q.b < a.B;                           // p < B * H * W  <=>  image index < B
+            return q;
         };
-        auto feat_offset = [&](long long p) -> long long {
-            const Pos q = decompose(p);
-            return SPARSE ? q.b * a.f_bs + q.r : q.b * a.f_bs + (long long)q.y * a.f_rs + q.x;
+        auto feat_offset = [&](const Pos& q) -> long long {
+            return SPARSE ? q.b * a.f_bs + q.x : q.b * a.f_bs + (long long)q.y * a.f_rs + q.x;
         };
         auto hand_over = [&]() {                         // TMEM writes of this warp are done -> one arrival on a_ready[c]
             tc_wait_st();
@@ -212,9 +255,9 @@ __global__ void __launch_bounds__(HTHREADS, 1) head_tc_kernel(const __grid_const
                                // MOV of a register an outstanding load still has to fill would wait for DRAM
         long long tile = (long long)NCTX * blockIdx.x + c;
         bool valid;
-        long long p_cur = pixel_of(tile, valid);
+        Pos cur = locate_first(tile, valid);
         {
-            const long long foff0 = valid ? feat_offset(p_cur) : 0;
+            const long long foff0 = valid ? feat_offset(cur) : 0;
 #pragma unroll
             for (int k = 0; k < CH; ++k) fcur[k] = (valid && stager) ? __ldg(a.feats + foff0 + (long long)(c_lo + k) * a.f_cs) : 0.f;
         }
@@ -263,9 +306,9 @@ __global__ void __launch_bounds__(HTHREADS, 1) head_tc_kernel(const __grid_const
             // ---- while layer 2's UMMAs run (this warp would only wait): locate the next tile, start loading its features, and fetch
             //      THIS tile's builtup score, so that neither the address arithmetic nor a DRAM round trip sits between two UMMA phases
             bool valid_n;
-            const long long p_nxt = pixel_of(tile + stride, valid_n);
+            const Pos nxt = locate_next(cur, tile + stride, valid_n);
             {
-                const long long foffn = valid_n ? feat_offset(p_nxt) : 0;
+                const long long foffn = valid_n ? feat_offset(nxt) : 0;
 #pragma unroll
                 for (int k = 0; k < CH; ++k) fcur[k] = (valid_n && stager) ? ((PC_HEAD_EXP & 1) ? (float)(foffn & 7) : __ldg(a.feats + foffn + (long long)(c_lo + k) * a.f_cs)) : 0.f;
             }
@@ -273,8 +316,8 @@ __global__ void __launch_bounds__(HTHREADS, 1) head_tc_kernel(const __grid_const
             HP_ADD(10, g1, g2);
             float bu_cur = 1.f;
             if (half == 0 && valid && a.builtup) {
-                const Pos q = decompose(p_cur);
-                bu_cur = (PC_HEAD_EXP & 4) ? (float)q.x : __ldg(a.builtup + (SPARSE ? p_cur : q.b * a.bu_bs + (long long)q.y * a.bu_rs + q.x));
+                const Pos& q = cur;
+                bu_cur = (PC_HEAD_EXP & 4) ? (float)q.x : __ldg(a.builtup + (SPARSE ? q.b * HW + q.x : q.b * a.bu_bs + (long long)q.y * a.bu_rs + q.x));
             }
             HP_T(h3);
             wait_d();
@@ -300,7 +343,7 @@ __global__ void __launch_bounds__(HTHREADS, 1) head_tc_kernel(const __grid_const
                     tc_wait_ld();
 #pragma unroll
                     for (int k = 0; k < 16; ++k)
-                        o = fmaf(fmaxf(__uint_as_float(v[k]) + b3[col_off + 16 * q + k], 0.f), w4[col_off + 16 * q + k], o);
+                        o = fmaf(fmaxf(BIAS_MMA ? __uint_as_float(v[k]) : __uint_as_float(v[k]) + b3[col_off + 16 * q + k], 0.f), w4[col_off + 16 * q + k], o);
                 }
             }
             // D has been read and the next tile's A1 is staged: layer 1 of the next tile may run NOW, under this tile's combine + stores
@@ -314,8 +357,8 @@ __global__ void __launch_bounds__(HTHREADS, 1) head_tc_kernel(const __grid_const
                 const float s = fmaxf(b4[0] + o + part[px], 0.f);
                 float d = 0.f; int bin = -1;
                 if (valid) {
-                    const Pos q = decompose(p_cur);
-                    const long long ooff = SPARSE ? p_cur : q.b * a.o_bs + (long long)q.y * a.o_rs + q.x;
+                    const Pos& q = cur;
+                    const long long ooff = SPARSE ? q.b * HW + q.x : q.b * a.o_bs + (long long)q.y * a.o_rs + q.x;
                     d = a.builtup ? s * bu_cur : s;
                     if (!(PC_HEAD_EXP & 2) || d == 123.456f) {
                     a.dens[ooff] = d;
@@ -336,7 +379,7 @@ __global__ void __launch_bounds__(HTHREADS, 1) head_tc_kernel(const __grid_const
             asm volatile("bar.sync %0, %1;" ::"r"(1 + c), "r"(HWORK) : "memory");      // part[] may be rewritten by the next tile
             HP_T(f3);
             HP_ADD(13, f1, f2); HP_ADD(14, f2, f3);
-            p_cur = p_nxt;
+            cur = nxt;
             valid = valid_n;
             HP_T(h7);
             HP_ADD(6, h6, h7);

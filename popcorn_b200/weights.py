@@ -159,16 +159,17 @@ def _split_f16(w: torch.Tensor):
 
 
 def _swizzle_k_major_128b_f16(h: torch.Tensor, slot_floats: int) -> torch.Tensor:
-    """[64, K <= 64] fp16 -> one 128-byte-row atom [64 rows][64 halves], 16-byte chunks (8 halves) XOR-swizzled with (n % 8), returned
-    as a float32 view padded with zeros to the matrix's slot in the image (the slots keep their TF32 sizes)."""
+    """[64, K] fp16 -> atoms of [64 rows][64 halves] (128-byte rows, 16-byte chunks = 8 halves XOR-swizzled with n % 8, one atom per 64
+    K elements), returned as a float32 view padded with zeros to the matrix's slot in the image (the slots keep their TF32 sizes)."""
     N, K = h.shape
-    assert N == 64 and K <= 64
+    assert N == 64 and (K + 63) // 64 * 2048 <= slot_floats
     key = ("f16", K, str(h.device))
     dst = _SWIZZLE_DST.get(key)
     if dst is None:
         n = torch.arange(N, device=h.device).view(N, 1)
         k = torch.arange(K, device=h.device).view(1, -1)
-        dst = (n * 64 + ((k // 8) ^ (n % 8)) * 8 + k % 8).reshape(-1)
+        kk = k % 64
+        dst = ((k // 64) * (N * 64) + n * 64 + ((kk // 8) ^ (n % 8)) * 8 + kk % 8).reshape(-1)
         _SWIZZLE_DST[key] = dst
     out = torch.zeros(2 * slot_floats, dtype=torch.float16, device=h.device)
     out[dst] = h.reshape(-1)
@@ -184,13 +185,20 @@ def tc_operand_format() -> int:
 def pack_head_tc(sd: Dict[str, torch.Tensor]) -> torch.Tensor:
     """Weight image of csrc/head_tc.cu (byte offsets OFF_* there): W1hi W1lo (8 KB each, K padded to 32), W2hi W2lo
     W3hi W3lo (16 KB each), then b1 b2 b3 w4 (64 floats each) and b4 (+3 pad).  float32 tensor of 20 740 elements.
-    The matrices hold TF32 or fp16 halves, whichever the library was built for (tc_operand_format)."""
+    The matrices hold TF32 or fp16 halves, whichever the library was built for (tc_operand_format); the fp16 matrices carry the layer's
+    bias as K column Kpad (16 | 64)."""
     parts = []
     f16 = tc_operand_format() == 1
     for i in (0, 2, 4):
         w = sd[f"head.{i}.weight"].detach().float().flatten(1)             # [64 out, K in]  == UMMA B operand, K-major
         if f16:
-            hi, lo = _split_f16(w)
+            # K padded to the 16 of a kind::f16 UMMA, then the bias as one more K column: it rides in the UMMAs against a constant
+            # (1, 0, ...) k-step of the A operand (csrc/head_tc.cu BIAS_MMA)
+            kpad = (w.shape[1] + 15) // 16 * 16
+            wb = torch.zeros(64, kpad + 1, dtype=w.dtype, device=w.device)
+            wb[:, :w.shape[1]] = w
+            wb[:, kpad] = sd[f"head.{i}.bias"].detach().float()
+            hi, lo = _split_f16(wb)
             slot = 2048 if i == 0 else 4096
             parts += [_swizzle_k_major_128b_f16(hi, slot), _swizzle_k_major_128b_f16(lo, slot)]
             continue

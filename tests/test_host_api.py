@@ -202,18 +202,22 @@ def test_head_tc_weight_image_layout():
     for i, off_hi, off_lo in ((0, 0, 8192), (2, 16384, 32768), (4, 49152, 65536)):
         w = sd[f"head.{i}.weight"].flatten(1)
         K = w.shape[1]
-        katoms = (K + E - 1) // E
+        katoms = (K + (1 if f16 else 0) + E - 1) // E
         halves = []
         for off in (off_hi, off_lo):
             raw = img[off // 4: off // 4 + katoms * 2048]                       # one atom = 64 rows x 128 B
             m = (raw.view(torch.float16).float() if f16 else raw).view(katoms, 64, E)
             halves.append(torch.gather(m, 2, pos.expand(katoms, 64, E)).permute(1, 0, 2).reshape(64, katoms * E))
         hi, lo = halves
-        assert float(hi[:, K:].abs().sum()) == 0 and float(lo[:, K:].abs().sum()) == 0
-        if f16:
-            assert torch.equal(hi[:, :K], w.half().float())
-            assert float((hi[:, :K].double() + lo[:, :K].double() - w.double()).abs().max()) <= 2.0 ** -21 * float(w.abs().max())
+        if f16:     # [w | zero padding to a multiple of 16 | bias] : the bias is K column Kpad (it rides in the UMMAs)
+            kpad = (K + 15) // 16 * 16
+            want = torch.zeros(64, katoms * E)
+            want[:, :K] = w
+            want[:, kpad] = sd[f"head.{i}.bias"]
+            assert torch.equal(hi, want.half().float())
+            assert float((hi.double() + lo.double() - want.double()).abs().max()) <= 2.0 ** -21 * float(want.abs().max())
         else:
+            assert float(hi[:, K:].abs().sum()) == 0 and float(lo[:, K:].abs().sum()) == 0
             assert torch.equal(hi[:, :K] + lo[:, :K], w)
     vec = img[81920 // 4:]
     assert torch.equal(vec[:64], sd["head.0.bias"]) and torch.equal(vec[192:256], sd["head.6.weight"].flatten(1)[0])

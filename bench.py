@@ -666,7 +666,7 @@ def main():
         eng.wait_download()
         barrier()
         t0 = time.perf_counter()
-        k_e2e = max(3, min(args.steps, 5))
+        k_e2e = max(3, min(args.steps, 20))         # the un-overlapped first upload and last download are inside the region: ~80 ms / k_e2e per step
         if pipelined:
             eng.prefetch(host_raster, i0)
         for k_ in range(k_e2e):

@@ -463,7 +463,9 @@ class CountryEngine:
         cur = self._slabs[k]
         if cur is None or cur[0].dtype != raster.s2.dtype or cur[0].shape != (4, rows, W):
             self._slabs[k] = (torch.empty(4, rows, W, dtype=raster.s2.dtype, device=dev), torch.empty(2, rows, W, dtype=torch.float32, device=dev))
-            self._slab_free[k] = None
+            # fresh memory from the caching allocator may still be read by work queued on the current stream: the first upload waits for it
+            self._slab_free[k] = torch.cuda.Event()
+            self._slab_free[k].record(torch.cuda.current_stream(dev))
         return self._slabs[k]
 
     def _upload_slabs(self, k: int, raster: "RawRaster", row_offset: int, dev, chunk_rows: int):
@@ -478,13 +480,13 @@ class CountryEngine:
         if i0 - row_offset < 0 or i1 - row_offset > raster.shape[1] or raster.shape[2] != W:
             raise ValueError("raster does not hold this rank's input rows")
         d2, d1 = self._slab_set(k, raster, dev)
-        start = torch.cuda.Event()
-        start.record(main)                         # first use: the slabs' memory may still be read by earlier work of this stream
         landed = []
         with torch.cuda.stream(cs):
-            cs.wait_event(start)
+            # The upload waits ONLY for the last ingest kernel that read this slab set (or, for fresh slabs, for what was queued when they
+            # were allocated) — not for the run in flight, which reads the other set: prefetch() called right after run() must overlap it.
+            # (Waiting for "everything queued so far" serialised the next raster's upload behind the current run: 20 ms per step.)
             if self._slab_free[k] is not None:
-                cs.wait_event(self._slab_free[k])  # the previous run on this set has consumed it
+                cs.wait_event(self._slab_free[k])
             for a in range(0, rows, chunk_rows):
                 b = min(rows, a + chunk_rows)
                 h0 = i0 - row_offset + a

@@ -113,6 +113,13 @@ def kernel_table(prof, ms_total, hbm_peak, tensor_peak, fp32_peak=None, frac_mul
     """prof = {name: (ms, launches, units)} from ops.profile_results().  `bound`: "hbm" | "tensor" as in the contract, plus "fp32" for the
     kernels whose ceiling is the FP32 FFMA2 pipe (measured by pc_test_fma_peak), which is neither."""
     traffic_px = ncu_traffic_per_px()
+    from popcorn_b200 import weights as _w
+    f16 = _w.tc_operand_format() == 1
+    # fp32-accurate tensor-core arithmetic = three split products per algorithmic MAC: fp16 halves (kind::f16) run at the bf16 rate the
+    # peak was measured with, TF32 halves (kind::tf32) at half of it
+    slots = 3 if f16 else 6
+    split = ("3 x fp16-half products (kind::f16, x = hi + lo with 11 + 11 significand bits)" if f16
+             else "3xTF32 (kind::tf32 at half the bf16 rate)")
     rows = []
     for name, (ms, n, units) in prof.items():
         if ms <= 0:
@@ -120,8 +127,8 @@ def kernel_table(prof, ms_total, hbm_peak, tensor_peak, fp32_peak=None, frac_mul
         if name.startswith("conv3x3_tc<"):
             flop, byts = _conv_work(name)
             bound = "hbm"
-            note = ("tcgen05 implicit GEMM, 3xTF32 (3 MMAs per algorithmic MAC at half the bf16 rate -> tensor ceiling = peak/6 = "
-                    f"{tensor_peak / 6:.0f} TFLOP/s): the layer moves (Cin+Cout)*4 B per pixel and is HBM-bound")
+            note = (f"tcgen05 implicit GEMM, {split}: tensor ceiling = peak/{slots} = {tensor_peak / slots:.0f} TFLOP/s; "
+                    "the layer moves (Cin+Cout)*4 B per pixel and is HBM-bound")
         elif name.startswith("conv3x3<"):
             flop, byts = _conv_work(name)
             bound, note = "hbm", "fp32 FFMA2 stencil (first layer: reflect padding + channel remap, Cin 2|4): 12-48 B and 144-288 MAC per pixel"
@@ -130,7 +137,7 @@ def kernel_table(prof, ms_total, hbm_peak, tensor_peak, fp32_peak=None, frac_mul
             flop, byts, bound, note = 8 * c * c, 5 * c * 4, "hbm", "units = low-res pixels"
         elif name.startswith("head_tc"):
             flop, byts, bound = FLOP_PER_PX_HEAD, BYTES_PER_PX_HEAD, "tensor"
-            note = "tcgen05 kind::tf32 with 3xTF32 splitting: 3 MMAs per algorithmic MAC at half the bf16 rate -> ceiling = peak/6"
+            note = f"tcgen05, activations in TMEM, {split}: ceiling = peak/{slots}"
         elif name.startswith("head_forward_simt"):
             flop, byts, bound, note = FLOP_PER_PX_HEAD, BYTES_PER_PX_HEAD, "fp32", "fp32 SIMT head"
         elif name == "head_backward":
@@ -163,9 +170,10 @@ def kernel_table(prof, ms_total, hbm_peak, tensor_peak, fp32_peak=None, frac_mul
                      "tflops": tfl, "gbs": gbs, "bound": bound, "achieved": ach, "peak": peak, "unit": unit,
                      "frac": ach / peak if peak else None, "algorithmic_bytes": byts * units / n,
                      "traffic": None if tpp is None else tpp * units / n, "note": note})
-        if name.startswith("head_tc"):   # fp32-accurate tensor-core arithmetic costs 3 tf32 MMAs (= 6 bf16-rate slots) per MAC
-            rows[-1]["ceiling_3xtf32"] = tensor_peak / 6
-            rows[-1]["frac_of_3xtf32_ceiling"] = tfl / (tensor_peak / 6) if tensor_peak else None
+        if name.startswith("head_tc"):
+            rows[-1]["ceiling_split3"] = tensor_peak / slots
+            rows[-1]["frac_of_split3_ceiling"] = tfl / (tensor_peak / slots) if tensor_peak else None
+            rows[-1]["operands"] = "fp16 hi/lo" if f16 else "tf32 hi/lo"
     rows.sort(key=lambda r: -r["ms"])
     return rows
 
@@ -179,7 +187,7 @@ def roofline_of(kernels, peak_src):
          "traffic_source": "ncu --set full capture of this command's launches (profiles/r2_ncu_bench_traffic.json)" if dom.get("traffic") else None,
          "launches": dom["launches"], "avg_launch_ms": dom["ms"] / dom["launches"], "share_of_step": dom["share_of_step"],
          "note": dom["note"], "peak_source": peak_src}
-    for k in ("ceiling_3xtf32", "frac_of_3xtf32_ceiling"):
+    for k in ("ceiling_split3", "frac_of_split3_ceiling", "operands"):
         if k in dom:
             r[k] = dom[k]
     return r
@@ -886,7 +894,11 @@ def main():
                            "windows": "merged_row_strips" if not args.no_merge else "reference_tiles",
                            "rows_per_strip": args.rows_per_strip, "sharding": "balanced_256_row_units" if (balance and world > 1) else "strips", "ensemble": 1, "head": "dense",
                            "l2": "inputs (>=6 GB per GPU) far larger than the 126 MB L2; no flush needed",
-                           "weights": weights_name},
+                           "weights": weights_name,
+                           "arithmetic": ("fp32 results: 3x3 convs and head as tensor-core products of "
+                                          + ("fp16" if pb.weights.tc_operand_format() == 1 else "tf32")
+                                          + " hi/lo operand halves (3 products per MAC, 22 significand bits, fp32 accumulation in TMEM); "
+                                            "first conv layer, ConvT, epilogues, census sums (fp64) on the CUDA cores")},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kernels,
                 "fp32_simt": fp32,
                 "cpu_baseline": cpu_base, "gpu_baseline": gpu_base, "train_step": train, "ensemble5": ens, "time_series": tseries,

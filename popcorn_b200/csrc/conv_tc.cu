@@ -62,7 +62,7 @@ __device__ long long g_tc_trace[4096];   // [role 0..7][batch 0..63][event 0..7]
 constexpr int TCM = 128;           // pixels per UMMA
 constexpr int TCN = 16;            // UMMA N (output channels, zero-padded)
 // timing experiments of the probe build (results are then WRONG on purpose): 1 = no UMMAs, 2 = no tcgen05.st in the stagers,
-// 4 = stagers read no shared memory, 8 = epilogue skips tcgen05.ld / re-zeroing
+// 4 = stagers read no shared memory, 8 = epilogue skips tcgen05.ld / re-zeroing, 16 = no full-resolution stores, 32 = no pooled stores
 #ifndef PC_TC_EXP
 #define PC_TC_EXP 0
 #endif
@@ -255,7 +255,8 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
                     return (k < 3 * CIN) ? ((PC_TC_EXP & 4) ? (float)(k + px) : st[(k % CIN) * TC_BOXW + k / CIN]) : 0.f;
                 };
                 auto load_split = [&](int col, uint32_t& hi, uint32_t& lo) {
-                    if (PC_TC_F16) split_f16x2(a_elem(2 * col), a_elem(2 * col + 1), hi, lo);
+                    if (PC_TC_F16 && 2 * col >= 3 * CIN) { hi = 0u; lo = 0u; }                // K padding (the asm split is opaque to constant folding)
+                    else if (PC_TC_F16) split_f16x2(a_elem(2 * col), a_elem(2 * col + 1), hi, lo);
                     else split_tf32(a_elem(col), hi, lo);
                 };
 #if PC_TC_ST16
@@ -381,7 +382,7 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
                             }
                             job.dot_out[(long long)yy * job.dot_out_rs + xx] = sacc;
                         }
-                    } else if (job.out && inside) {
+                    } else if (job.out && inside && !(PC_TC_EXP & 16)) {
                         float* dst = job.out + (long long)yy * job.out_rs + xx;
 #pragma unroll
                         for (int o = 0; o < COUT; ++o) dst[(long long)o * job.out_cs] = acc[h][o];
@@ -438,7 +439,7 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
                     for (int o = 0; o < COUT; ++o) {
                         const float vm = fmaxf(acc[0][o], acc[1][o]);
                         const float hm = fmaxf(vm, __shfl_xor_sync(FULL, vm, 1));
-                        if (stp) job.pool[(long long)o * job.pool_cs + (long long)py * job.pool_rs + pxl] = hm;
+                        if (stp && !(PC_TC_EXP & 32)) job.pool[(long long)o * job.pool_cs + (long long)py * job.pool_rs + pxl] = hm;
                     }
                 }
             }

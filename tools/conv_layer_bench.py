@@ -25,13 +25,14 @@ for cin, cout in cases:
     _lib.check(L.pc_conv_tc_pack_layer(flat.data_ptr(), cin, cout, img.data_ptr()))
     flat_d, img_d = flat.cuda(), img.cuda()
     out = torch.empty(cout, H, W, device="cuda")
+    pool = torch.empty(cout, H // 2, W // 2, device="cuda") if os.environ.get("KB_POOL") else None      # EPI_POOL variant of the layer
     res = {}
     for name, wtc in (("simt", None), ("tc", img_d)):
         if only and only != name:
             continue
         def run():
             _lib.check(L.pc_test_conv3x3(x.data_ptr(), cin, H, W, 0, 0, 0, None, 0, 0, 0, 0, 0, flat_d.data_ptr(), cout, H, W,
-                                         out.data_ptr(), None, None if wtc is None else wtc.data_ptr(), st))
+                                         out.data_ptr(), None if pool is None else pool.data_ptr(), None if wtc is None else wtc.data_ptr(), st))
         for _ in range(2):
             run()
         a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -200,14 +200,17 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
 }
 
 // (x0, x1) = hi + lo with fp16 halves packed as f16x2 (x0 in the low half): 11 + 11 significand bits like the TF32 split, in half the
-// operand bytes.  fp16 keeps 5 exponent bits: lo parts below 6e-5 are subnormal (absolute error <= 3e-8, tools/precision_split_study.py)
-// and |x| > 65504 saturates instead of overflowing to inf (hi = 65504, lo = the rest, up to 131008).
+// operand bytes.  fp16 keeps 5 exponent bits:
+//   * lo parts below 6e-5 are subnormal: absolute error <= 3e-8 (tools/precision_split_study.py);
+//   * 65504 < |x| <= 131008: hi saturates at 65504 and lo carries the rest (relative error <= 2^-12 (|x| - 65504) / |x|);
+//   * |x| > 131008: lo overflows to inf ON PURPOSE (plain cvt.rn, not .satfinite) — the pixel comes out inf / NaN instead of silently
+//     clipped.  Such activations need the TF32 build (-DPC_TC_F16=0); BN-normalised networks stay orders of magnitude below.
 __device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
     float h0, h1;
     asm("{\n\t.reg .b16 a, b;\n\tmov.b32 {a, b}, %2;\n\tcvt.f32.f16 %0, a;\n\tcvt.f32.f16 %1, b;\n\t}" : "=f"(h0), "=f"(h1) : "r"(hi));
     const float r0 = x0 - h0, r1 = x1 - h1;
-    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
 }
 
 }  // namespace pc

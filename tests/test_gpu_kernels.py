@@ -54,6 +54,46 @@ def test_conv3x3_bias_relu(cin, cout, H, W, tc):
     assert torch.allclose(out.cpu(), ref, rtol=1e-4, atol=1e-4), float((out.cpu() - ref).abs().max())
 
 
+@pytest.mark.parametrize("scale,rel", [(1e-4, 1e-3), (1.0, 5e-6), (2e4, 5e-6), (1e5, 3e-4)])
+def test_conv3x3_tc_operand_range(scale, rel):
+    """Split-operand range of the tensor-core convs (csrc/tc_common.cuh split_f16x2): fp32-like accuracy for O(1) .. O(1e4) activations,
+    graceful for tiny ones (fp16 halves: lo parts go subnormal, absolute error ~3e-8 per element) and inside the saturating window
+    65504 < |x| <= 131008; the TF32 build (pc_tc_operand_format() == 0) has no such window and meets the tight bar everywhere."""
+    g = torch.Generator().manual_seed(11)
+    x = (torch.rand(8, 40, 160, generator=g) * scale).cuda()           # non-negative like post-ReLU activations, max = scale
+    w = (torch.randn(8, 8, 3, 3, generator=g) * 0.3).cuda()
+    b = torch.zeros(8).cuda()
+    out = torch.full((8, 40, 160), float("nan"), device="cuda")
+    wtc = _pack_conv_tc(w, b, True)
+    _lib.check(_lib.lib().pc_test_conv3x3(x.data_ptr(), 8, 40, 160, 0, 0, 0, None, 0, 0, 0, 0, 0, _pack_conv(w, b).data_ptr(), 8, 40, 160,
+                                          out.data_ptr(), None, _p(wtc), _st()))
+    ref = F.conv2d(x[None].double().cpu(), w.double().cpu(), None, padding=1)[0].clamp_(min=0)
+    err = float((out.double().cpu() - ref).abs().max() / ref.abs().max())
+    bar = rel if _lib.lib().pc_tc_operand_format() == 1 else 5e-6
+    assert torch.isfinite(out).all() and err < bar, err
+
+
+def test_conv3x3_tc_overflow_is_loud():
+    """fp16 halves: an activation beyond 2 x 65504 cannot be represented by hi + lo; the lo half overflows to inf on purpose, so the pixels
+    that see it come out non-finite instead of silently clipped (fp32 / the TF32 build compute them)."""
+    x = torch.ones(8, 32, 128, device="cuda")
+    x[3, 10, 40] = 3.0e5
+    w = torch.full((8, 8, 3, 3), 0.1, device="cuda")
+    b = torch.zeros(8, device="cuda")
+    out = torch.zeros(8, 32, 128, device="cuda")
+    wtc = _pack_conv_tc(w, b, True)
+    _lib.check(_lib.lib().pc_test_conv3x3(x.data_ptr(), 8, 32, 128, 0, 0, 0, None, 0, 0, 0, 0, 0, _pack_conv(w, b).data_ptr(), 8, 32, 128,
+                                          out.data_ptr(), None, _p(wtc), _st()))
+    hit = out[:, 9:12, 39:42]
+    if _lib.lib().pc_tc_operand_format() == 1:
+        assert not torch.isfinite(hit).any()
+        keep = torch.ones_like(out, dtype=torch.bool)
+        keep[:, 9:12, 39:42] = False
+        assert torch.isfinite(out[keep]).all()
+    else:
+        assert torch.isfinite(out).all() and abs(float(hit[0, 1, 1]) - (7.1 + 3.0e4)) < 0.1
+
+
 @pytest.mark.parametrize("c", [8, 16])
 @pytest.mark.parametrize("H,W", [(64, 64), (37, 52), (50, 36), (66, 260)])
 @TC

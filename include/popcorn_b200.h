@@ -67,8 +67,9 @@ int pc_dda_pack_offset(int stream, int layer);
 
 /* Tensor-core weight section (csrc/conv_tc.cu): the ten 3x3 conv layers of each stream again, as tcgen05 B
  * operands — per layer [hi|lo] matrices with rows [W_ky2 | W_ky1 | W_ky0] (3*Cout rows: row Cout*(2-ky) + co, k = kx*cin + ci,
- * K padded to 32-float atoms) in the UMMA K-major SWIZZLE_128B layout, each weight split w = hi + lo (hi = top 19 bits: exact
- * TF32) for 3xTF32, then bias[16].
+ * K padded to 128-byte atoms) in the UMMA K-major SWIZZLE_128B layout, each weight split w = hi + lo for the three-product scheme
+ * D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo — fp16 halves (64 per 128-byte row; default build) or TF32 halves (hi = top 19 bits, 32 per
+ * row; build with TC_OPERANDS=tf32), see pc_tc_operand_format() — then bias[16].
  * It is appended to the fp32 pack at float offset pc_dda_tc_pack_base() (the fp32 pack rounded up to 256 B) and is
  * pc_dda_tc_pack_floats() long; pc_dda_tc_pack converts a HOST fp32 pack into a HOST image (pure host code).
  * pc_dda_forward uses the tensor-core kernels when the pack it is given is long enough to hold the section. */
@@ -92,7 +93,7 @@ int pc_head_pack_floats(int head_in);
  *              the pad-to-64 amounts for the feature pass, 0 otherwise); nothing is materialised
  *   mode       PC_DDA_FEATURES -> out[B,F,H,W] ; PC_DDA_BUILTUP -> out[B,1,H,W]; cropped back to HxW
  *   wpack      device pack of wpack_floats floats: the fp32 section, optionally followed by the tensor-core
- *              section (then the 3x3 convs run on tcgen05, 3xTF32; otherwise the fp32 SIMT stencils run)
+ *              section (then the 3x3 convs run on tcgen05 with split operands; otherwise the fp32 SIMT stencils run)
  * --------------------------------------------------------------------------------------------- */
 size_t pc_dda_workspace_bytes(int B, int C, int Hv, int Wv);
 int pc_dda_forward(const float* wpack, long long wpack_floats, const float* x, int B, int C, int H, int W, long long x_bstride,
@@ -118,7 +119,7 @@ int pc_head_dense_forward(const float* hpack, int head_in, const float* feats, l
                           int o_rstride, const int32_t* ids, long long id_bstride, int id_rstride,
                           const int32_t* census_idx, double* sums, int R, pc_stream_t stream);
 
-/* Tensor-core variants of the two head forwards (tcgen05.mma kind::tf32 with 3xTF32 operand splitting, activations
+/* Tensor-core variants of the two head forwards (tcgen05.mma with hi/lo operand splitting — three products per MAC, activations
  * as the A operand in TMEM; csrc/head_tc.cu).  Same contract and arguments as pc_head_dense_forward /
  * pc_head_sparse_forward, except that `tcpack` is the pc_head_tc_pack_bytes()-byte weight image built by
  * popcorn_b200.weights.pack_head_tc (hi/lo split, K-major SWIZZLE_128B). */

@@ -1,9 +1,11 @@
-// 3x3 convolutions of the DDA UNet as implicit GEMMs on the 5th-gen tensor cores (tcgen05 + TMEM), 3xTF32.
+// 3x3 convolutions of the DDA UNet as implicit GEMMs on the 5th-gen tensor cores (tcgen05 + TMEM), split operands
+// (x = hi + lo, three products per MAC; fp16 halves by default — two K elements per TMEM column, K = 16 per UMMA — or TF32 halves with
+// -DPC_TC_F16=0; the text below counts K in TF32 elements, halve the columns and k-steps for fp16).
 //
 // Mapping (one persistent CTA per SM walks tiles of 128 columns x TR rows of one (image, stream) job):
 //   * UMMA M = 128 = the 128 pixels of one image row segment; pixel x0+t == TMEM lane t;
 //   * K of one input row = (kx, ci): the row is written to TMEM THREE times, shifted by -1/0/+1 pixel, each value
-//     split x = hi + lo (hi = top 19 bits = exact TF32) -> A operand [128 x 3*Cin] hi and lo, in TMEM;
+//     split x = hi + lo -> A operand [128 x 3*Cin] hi and lo, in TMEM;
 //   * the ky shift is NOT a lane shift: input row r feeds output rows r+1 (ky=0), r (ky=1), r-1 (ky=2), i.e. three
 //     different fp32 accumulators D[128 x 16] that live in an 8-slot TMEM ring (slot = running output row % 8);
 //   * B operand = the folded weights [W_ky2 | W_ky1 | W_ky0][co][(kx,ci)] (48 rows: 3 x Cout 16, or Cout 8 zero-padded),

@@ -1,17 +1,18 @@
-// Occupancy head on the 5th-gen tensor cores (tcgen05 + TMEM), error-compensated 3xTF32.
+// Occupancy head on the 5th-gen tensor cores (tcgen05 + TMEM), error-compensated split operands (x = hi + lo, three products per MAC).
 //
-// Per 128-pixel tile (UMMA M = 128, N = 64, cta_group::1), 256 threads:
+// Per 128-pixel tile (UMMA M = 128, N = 64, cta_group::1), 256 worker threads:
 //   * a pixel = one TMEM lane; TWO warps share each 32-lane quarter (warp w and w+4) and split the per-pixel work by
 //     columns (features 0-7 | 8-15, hidden units 0-31 | 32-63), which halves every epilogue between two layers' UMMAs;
-//   * activations are the A operand and LIVE IN TMEM: the epilogue reads the fp32 accumulator D with
-//     tcgen05.ld, applies bias + ReLU, splits x = hi + lo (hi = top 19 bits, exactly a TF32 number) and
-//     writes both halves back with tcgen05.st — they never touch shared or global memory;
+//   * activations are the A operand and LIVE IN TMEM: the epilogue reads the fp32 accumulator D with tcgen05.ld, applies ReLU,
+//     splits x = hi + lo into fp16 pairs (PC_TC_F16, default; two K elements per TMEM column) or TF32 halves and writes both
+//     halves back with tcgen05.st — they never touch shared or global memory;
 //   * weights are the B operand in shared memory, pre-split (hi/lo) and pre-swizzled on the host into the
 //     canonical K-major SWIZZLE_128B layout, copied in verbatim once per CTA;
-//   * every 8-wide k-step issues three tcgen05.mma.kind::tf32 (hi*hi + lo*hi + hi*lo) into the same fp32
-//     accumulator: ~21-bit operands, which is what the per-pixel 1e-2 bar needs;
+//   * every k-step (16 fp16 / 8 tf32 elements) issues three tcgen05.mma (hi*hi + lo*hi + hi*lo) into the same fp32
+//     accumulator: 22-bit operands, which is what the per-pixel 1e-2 bar needs (tools/precision_split_study.py);
+//     fp16 build: the layer's bias is one more k-step (constant (1, 0, ..) columns of A x the bias row of the weight image);
 //   * the 64->1 output layer, ReLU, x builtup, stores and the census partial sums run in the last epilogue.
-// Two CTAs per SM (256 TMEM columns, 85 KB smem each) overlap one tile's epilogue with the other's MMAs.
+// One persistent CTA per SM with three (fp16) or two (tf32) tile contexts and one UMMA-issuing warp: see "Kernel structure" below.
 // Replaces model/popcorn.py:79-88, 160-190, 195-228 (same contract as head.cu's SIMT kernel).
 #include "head_common.cuh"
 #include "tc_common.cuh"
@@ -106,10 +107,10 @@ __device__ __forceinline__ void epilogue_hidden(uint32_t tD, uint32_t tAhi, uint
     }
 }
 
-// Kernel structure: ONE persistent CTA per SM, 17 warps.  Two tile contexts (each: accumulator D, A_hi, A_lo = 192 TMEM
-// columns) are worked on by their own 8 worker warps; warp 16 is the only UMMA issuer and serves the contexts in strict
-// alternation (ctx0 layer 1, ctx1 layer 1, ctx0 layer 2, ...), so one context's epilogue always runs under the other
-// context's UMMAs instead of the two drifting into the same phase.  Hand-offs are mbarriers: workers -> issuer a_ready[c]
+// Kernel structure: ONE persistent CTA per SM, 8 * NCTX + 1 warps.  NCTX tile contexts (each: accumulator D, A_hi, A_lo, next tile's
+// layer-1 operand = 160 TMEM columns with fp16 halves, 224 with TF32) are worked on by their own 8 worker warps; the last warp is the
+// only UMMA issuer and serves the contexts in strict rotation (ctx0 layer 1, ctx1 layer 1, ctx2 layer 1, ctx0 layer 2, ...), so one
+// context's epilogue always runs under the other contexts' UMMAs instead of all drifting into the same phase.  Hand-offs are mbarriers: workers -> issuer a_ready[c]
 // (8 warp arrivals), issuer -> workers d_ready[c] (tcgen05.commit).
 constexpr int HWORK = 256;                       // worker threads per context
 #ifndef PC_HEAD_NCTX

@@ -18,7 +18,7 @@ from .. import ops, weights
 from . import unet_train
 from .dda import STAGE1_FEATS, load_checkpoint
 
-# forward head on tcgen05 (3xTF32, csrc/head_tc.cu) unless POPCORN_HEAD_TC=0 selects the fp32 SIMT kernel (csrc/head.cu)
+# forward head on tcgen05 (split operands, csrc/head_tc.cu) unless POPCORN_HEAD_TC=0 selects the fp32 SIMT kernel (csrc/head.cu)
 USE_TENSOR_CORE_HEAD = os.environ.get("POPCORN_HEAD_TC", "1") != "0"
 _CHECK_IDS = os.environ.get("POPCORN_CHECK_IDS", "0") == "1"
 FUSED_EVAL = os.environ.get("POPCORN_FUSED_EVAL", "1") != "0"      # eval forward through pc_infer_tile_fused (one library call)

@@ -51,7 +51,7 @@ def _pad4(t: torch.Tensor) -> torch.Tensor:
 def pack_dda(sd: Dict[str, torch.Tensor], copy: str, tc: bool = True) -> torch.Tensor:
     """One DualStreamUNet copy ('unetmodel' | 'building_extractor') -> flat fp32 CPU tensor.
     tc=True appends the tensor-core section (include/popcorn_b200.h "Tensor-core weight section": the 3x3 conv weights
-    pre-split for 3xTF32 and pre-swizzled for tcgen05), which makes pc_dda_forward run its convs on the tensor cores."""
+    pre-split into hi/lo halves and pre-swizzled for tcgen05), which makes pc_dda_forward run its convs on the tensor cores."""
     flat = _pack_dda_fp32(sd, copy)
     if not tc:
         return flat
@@ -107,7 +107,7 @@ def unpack_head_grad(gpack: torch.Tensor, head_in: int) -> Dict[str, torch.Tenso
 
 
 # ---------------------------------------------------------------------------------------------------
-# tcgen05 head: weights pre-split (3xTF32) and pre-swizzled into the UMMA K-major SWIZZLE_128B layout
+# tcgen05 head: weights pre-split (hi/lo halves, fp16 or TF32: tc_operand_format) and pre-swizzled into the UMMA K-major SWIZZLE_128B layout
 # ---------------------------------------------------------------------------------------------------
 def _split_tf32(w: torch.Tensor):
     """w = hi + lo, hi exactly representable in TF32 (low 13 mantissa bits cleared), lo = w - hi (exact in fp32)."""

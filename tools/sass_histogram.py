@@ -25,7 +25,7 @@ for ln in out.splitlines():
 dem = subprocess.run(["c++filt"], input="\n".join(names), capture_output=True, text=True).stdout.splitlines()
 print(f"# SASS opcode histogram of popcorn_b200/libpopcorn_b200.so (cuobjdump -sass, sm_100a)\n")
 print("UTCHMMA = tcgen05.mma, STTM / LDTM = tcgen05.st / tcgen05.ld, UTMALDG = TMA tensor load, UTCBAR = tcgen05.commit, SYNCS = mbarrier ops;")
-print("LD = generic loads (the conv stagers read the TMA-filled shared-memory ring through generic addresses).\n")
+print("LD = generic loads (none left: every shared-memory access of the library is an LDS / STS since the base pointers keep their address space).\n")
 print("| kernel | " + " | ".join(COLS) + " | instructions |")
 print("|---|" + "---|" * (len(COLS) + 1))
 tot = collections.Counter()

@@ -82,6 +82,9 @@ constexpr int TCN = 16;            // UMMA N (output channels, zero-padded)
 #ifndef PC_TC_OCC2
 #define PC_TC_OCC2 1
 #endif
+#ifndef PC_TC_POOL_SPLIT
+#define PC_TC_POOL_SPLIT 1         // pooling epilogue: the two lanes of a pooled pixel split the channels
+#endif
 #ifndef PC_TC_PAIRS16
 #define PC_TC_PAIRS16 1            // <8,8,8> (Cin 16, Cout 8): 1 = two issuers with pair ownership, 0 = one issuer with 3-row windows
 #endif
@@ -436,6 +439,20 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
                 }
                 if (EPI == EPI_POOL) {                               // 2x2 max over (rows 2m, 2m+1) x (lanes 2k, 2k+1)
                     const int py = (y0 >> 1) + m, pxl = vx >> 1;
+#if PC_TC_POOL_SPLIT
+                    // the two lanes of a pooled pixel share the channels: the even lane finishes and stores channels [0, COUT/2), the odd
+                    // lane [COUT/2, COUT) — half the shuffles and stores of "every lane reduces all channels, even lanes store"
+                    const bool stp = py < (H >> 1) && pxl < (W >> 1);
+                    const bool odd = lane & 1;
+                    float* pdst = job.pool + (long long)(odd ? COUT / 2 : 0) * job.pool_cs + (long long)py * job.pool_rs + pxl;
+#pragma unroll
+                    for (int o = 0; o < COUT / 2; ++o) {
+                        const float va = fmaxf(acc[0][o], acc[1][o]), vb = fmaxf(acc[0][o + COUT / 2], acc[1][o + COUT / 2]);
+                        const float other = __shfl_xor_sync(FULL, odd ? va : vb, 1);      // the partner's half of MY channels
+                        const float hm = fmaxf(odd ? vb : va, other);
+                        if (stp && !(PC_TC_EXP & 32)) pdst[(long long)o * job.pool_cs] = hm;
+                    }
+#else
                     const bool stp = !(lane & 1) && py < (H >> 1) && pxl < (W >> 1);
 #pragma unroll
                     for (int o = 0; o < COUT; ++o) {
@@ -443,6 +460,7 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
                         const float hm = fmaxf(vm, __shfl_xor_sync(FULL, vm, 1));
                         if (stp && !(PC_TC_EXP & 32)) job.pool[(long long)o * job.pool_cs + (long long)py * job.pool_rs + pxl] = hm;
                     }
+#endif
                 }
             }
             P0 += npairs;

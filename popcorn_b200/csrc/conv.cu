@@ -110,17 +110,25 @@ conv3x3_kernel(const __grid_constant__ ConvParams p) {
         const float* sp; long long cs; int rs, sH, sW, oy, ox, refl, ch0;
         if (fromA) { sp = job.a; cs = job.a_cs; rs = job.a_rs; sH = job.a_H; sW = job.a_W; oy = job.a_oy; ox = job.a_ox; refl = job.a_reflect; ch0 = chunk * CC; }
         else       { sp = job.b; cs = job.b_cs; rs = job.b_rs; sH = job.b_H; sW = job.b_W; oy = job.b_oy; ox = job.b_ox; refl = 0; ch0 = chunk * CC - CIN_A; }
-        int sxv[2]; bool okv[2];
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int c = lane + 32 * k;
+        // source column / validity of a staged column c (image column x0 - 1 + c), source row offset / validity of a staged row r
+        auto col_of = [&](int c, int& sx, bool& ok) {
             const int vx = x0 - 1 + c;
-            bool ok = (c < SROWS) && vx >= 0 && vx < W;
-            int sx = vx - ox;
+            ok = (c < SROWS) && vx >= 0 && vx < W;
+            sx = vx - ox;
             if (refl) { sx = sx < 0 ? -sx : sx; sx = sx >= sW ? 2 * (sW - 1) - sx : sx; }
             else ok = ok && sx >= 0 && sx < sW;
-            sxv[k] = ok ? sx : 0; okv[k] = ok;
-        }
+            sx = ok ? sx : 0;
+        };
+        auto row_of = [&](int r, long long& roff, bool& rok) {
+            const int vy = y0 - 1 + r;
+            rok = r < SROWS && vy >= 0 && vy < H;
+            int sy = vy - oy;
+            if (refl) { sy = sy < 0 ? -sy : sy; sy = sy >= sH ? 2 * (sH - 1) - sy : sy; }
+            else rok = rok && sy >= 0 && sy < sH;
+            roff = rok ? (long long)sy * rs : 0;
+        };
+        int sx0; bool ok0;
+        col_of(lane, sx0, ok0);
         const float* planes[CC];
 #pragma unroll
         for (int c = 0; c < CC; ++c) {
@@ -128,19 +136,28 @@ conv3x3_kernel(const __grid_constant__ ConvParams p) {
             if (CIN_A <= 4 && fromA) plane = (job.a_chmap >> (8 * plane)) & 0xff;
             planes[c] = sp + plane * cs;
         }
+        // columns 0..31 of every row: one full-warp copy per (row, channel)
 #pragma unroll 3
         for (int r = warp; r < SROWS; r += NWARP) {
-            const int vy = y0 - 1 + r;
-            bool rok = vy >= 0 && vy < H;
-            int sy = vy - oy;
-            if (refl) { sy = sy < 0 ? -sy : sy; sy = sy >= sH ? 2 * (sH - 1) - sy : sy; }
-            else rok = rok && sy >= 0 && sy < sH;
-            const long long roff = rok ? (long long)sy * rs : 0;
+            long long roff; bool rok;
+            row_of(r, roff, rok);
 #pragma unroll
-            for (int c = 0; c < CC; ++c) {
-                float* d = dst + (c * SROWS + r) * SPITCH + XOFF + lane;
-                cp_async4(d, planes[c] + roff + sxv[0], rok && okv[0]);
-                if (lane < SROWS - 32) cp_async4(d + 32, planes[c] + roff + sxv[1], rok && okv[1]);
+            for (int c = 0; c < CC; ++c)
+                cp_async4(dst + (c * SROWS + r) * SPITCH + XOFF + lane, planes[c] + roff + sx0, rok && ok0);
+        }
+        // the last two columns (32, 33) of 16 rows per copy: lane = (row within the group, column) — instead of one copy per row with
+        // two active lanes (half of the kernel's copy instructions were 94 % empty)
+        static_assert(SROWS - 32 == 2, "halo column copy assumes two extra columns");
+        for (int g = warp; g * 16 < SROWS; g += NWARP) {
+            const int r = g * 16 + (lane >> 1), cx = 32 + (lane & 1);
+            long long roff; bool rok;
+            int sx1; bool ok1;
+            row_of(r, roff, rok);
+            col_of(cx, sx1, ok1);
+            if (r < SROWS) {
+#pragma unroll
+                for (int c = 0; c < CC; ++c)
+                    cp_async4(dst + (c * SROWS + r) * SPITCH + XOFF + cx, planes[c] + roff + sx1, rok && ok1);
             }
         }
     };

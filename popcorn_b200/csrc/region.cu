@@ -260,25 +260,63 @@ __global__ void __launch_bounds__(256) compact_write_kernel(const __grid_constan
 // ---------------------------------------------------------------------------------------------------
 // country-map accumulation
 // ---------------------------------------------------------------------------------------------------
+// One thread = 4 consecutive pixels of a row (VEC: 16-byte loads / stores of the tile and the maps, 8-byte of the int16 counts; the host
+// checks the alignment) or 1 pixel.  Per element the arithmetic is the scalar one: separately rounded mul / add (no FMA contraction) —
+// the reference squares, then adds (run_eval.py:111,128).
+template <bool VEC>
 __global__ void __launch_bounds__(256) accumulate_kernel(const float* __restrict__ dens, const float* __restrict__ scale,
                                                          int t_rs, int r0, int r1, int c0, int c1, float* map,
                                                          float* map_sq, float* smap, float* smap_sq, int16_t* count,
                                                          int m_rs, int y0, int x0) {
-    const int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr int PX = VEC ? 4 : 1;
+    const int c = c0 + (blockIdx.x * blockDim.x + threadIdx.x) * PX;
     const int r = r0 + blockIdx.y;
     if (c >= c1 || r >= r1) return;
     const long long t = (long long)r * t_rs + c;
     const long long m = (long long)(y0 + r) * m_rs + (x0 + c);
-    // separately rounded mul / add (no FMA contraction): the reference squares, then adds (run_eval.py:111,128)
-    const float d = dens[t];
-    map[m] += d;
-    if (map_sq) map_sq[m] = __fadd_rn(map_sq[m], __fmul_rn(d, d));
-    if (scale) {
-        const float s = scale[t];
-        if (smap) smap[m] += s;
-        if (smap_sq) smap_sq[m] = __fadd_rn(smap_sq[m], __fmul_rn(s, s));
+    if (VEC && c + 3 < c1) {
+        const float4 d = *reinterpret_cast<const float4*>(dens + t);
+        float4 v = *reinterpret_cast<float4*>(map + m);
+        v.x += d.x; v.y += d.y; v.z += d.z; v.w += d.w;
+        *reinterpret_cast<float4*>(map + m) = v;
+        if (map_sq) {
+            float4 q = *reinterpret_cast<float4*>(map_sq + m);
+            q.x = __fadd_rn(q.x, __fmul_rn(d.x, d.x)); q.y = __fadd_rn(q.y, __fmul_rn(d.y, d.y));
+            q.z = __fadd_rn(q.z, __fmul_rn(d.z, d.z)); q.w = __fadd_rn(q.w, __fmul_rn(d.w, d.w));
+            *reinterpret_cast<float4*>(map_sq + m) = q;
+        }
+        if (scale) {
+            const float4 sc = *reinterpret_cast<const float4*>(scale + t);
+            if (smap) {
+                float4 u = *reinterpret_cast<float4*>(smap + m);
+                u.x += sc.x; u.y += sc.y; u.z += sc.z; u.w += sc.w;
+                *reinterpret_cast<float4*>(smap + m) = u;
+            }
+            if (smap_sq) {
+                float4 q = *reinterpret_cast<float4*>(smap_sq + m);
+                q.x = __fadd_rn(q.x, __fmul_rn(sc.x, sc.x)); q.y = __fadd_rn(q.y, __fmul_rn(sc.y, sc.y));
+                q.z = __fadd_rn(q.z, __fmul_rn(sc.z, sc.z)); q.w = __fadd_rn(q.w, __fmul_rn(sc.w, sc.w));
+                *reinterpret_cast<float4*>(smap_sq + m) = q;
+            }
+        }
+        if (count) {
+            short4 n = *reinterpret_cast<short4*>(count + m);
+            n.x += 1; n.y += 1; n.z += 1; n.w += 1;
+            *reinterpret_cast<short4*>(count + m) = n;
+        }
+        return;
     }
-    if (count) count[m] += 1;
+    for (int k = 0; k < PX && c + k < c1; ++k) {
+        const float d = dens[t + k];
+        map[m + k] += d;
+        if (map_sq) map_sq[m + k] = __fadd_rn(map_sq[m + k], __fmul_rn(d, d));
+        if (scale) {
+            const float sc = scale[t + k];
+            if (smap) smap[m + k] += sc;
+            if (smap_sq) smap_sq[m + k] = __fadd_rn(smap_sq[m + k], __fmul_rn(sc, sc));
+        }
+        if (count) count[m + k] += 1;
+    }
 }
 
 __global__ void __launch_bounds__(256) finalize_kernel(float* map, float* map_sq, float* smap, float* smap_sq,
@@ -392,11 +430,20 @@ extern "C" int pc_accumulate_tile(const float* dens, const float* scale, int t_r
                                   int y0, int x0, pc_stream_t stream) {
     PC_CHECK_ARG(dens && map, "null pointer");
     if (r1 <= r0 || c1 <= c0) return 0;
-    dim3 grid(cdiv(c1 - c0, 256), r1 - r0);
     static const int cat = prof_register("accumulate");
     ProfScope prof(cat, (cudaStream_t)stream, (double)(r1 - r0) * (c1 - c0));
-    accumulate_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dens, scale, t_rstride, r0, r1, c0, c1, map, map_sq, smap,
-                                                              smap_sq, count, m_rstride, y0, x0);
+    auto al = [](const void* p, int b) { return p == nullptr || (((uintptr_t)p) % b) == 0; };
+    const bool vec = (t_rstride % 4 == 0) && (m_rstride % 4 == 0) && (c0 % 4 == 0) && (x0 % 4 == 0) && al(dens, 16) && al(scale, 16) &&
+                     al(map, 16) && al(map_sq, 16) && al(smap, 16) && al(smap_sq, 16) && al(count, 8);
+    if (vec) {
+        dim3 grid(cdiv(cdiv(c1 - c0, 4), 256), r1 - r0);
+        accumulate_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(dens, scale, t_rstride, r0, r1, c0, c1, map, map_sq, smap,
+                                                                      smap_sq, count, m_rstride, y0, x0);
+    } else {
+        dim3 grid(cdiv(c1 - c0, 256), r1 - r0);
+        accumulate_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(dens, scale, t_rstride, r0, r1, c0, c1, map, map_sq, smap,
+                                                                       smap_sq, count, m_rstride, y0, x0);
+    }
     PC_LAUNCH_CHECK();
     return 0;
 }

@@ -319,24 +319,47 @@ __global__ void __launch_bounds__(256) accumulate_kernel(const float* __restrict
     }
 }
 
+// finalize one pixel: op-by-op IEEE arithmetic in the reference's order (run_eval.py:143-154): the variance formula cancels
+// catastrophically where tile results nearly coincide, so FMA contraction would change NaN / 0 outcomes
+__device__ __forceinline__ void finalize_pixel(float* map, float* map_sq, float* smap, float* smap_sq, long long p, int n) {
+    const float nf = (float)n;
+    const float mean = __fdiv_rn(map[p], nf);
+    map[p] = mean;
+    if (map_sq)
+        map_sq[p] = __fsqrt_rn(__fdiv_rn(__fsub_rn(map_sq[p], __fmul_rn(__fmul_rn(mean, mean), nf)), nf - 1.f));
+    if (smap) {
+        const float sm = __fdiv_rn(smap[p], nf);
+        smap[p] = sm;
+        if (smap_sq)
+            smap_sq[p] = __fsqrt_rn(__fdiv_rn(__fsub_rn(smap_sq[p], __fmul_rn(__fmul_rn(sm, sm), nf)), nf - 1.f));
+    }
+}
+
+// The visit counts are read 8 at a time (16 bytes; VEC: `count` 16-byte aligned): almost every pixel has count <= 1 and needs nothing else
+// (run_eval.py:140, div_mask = count > 1), so the kernel is a 2 B/px scan with rare read-modify-writes.
+template <bool VEC>
 __global__ void __launch_bounds__(256) finalize_kernel(float* map, float* map_sq, float* smap, float* smap_sq,
                                                        const int16_t* __restrict__ count, long long npix) {
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += stride) {
-        const int n = count[p];
-        if (n <= 1) continue;                                   // run_eval.py:140 (div_mask = count > 1)
-        const float nf = (float)n;
-        // op-by-op IEEE arithmetic in the reference's order (run_eval.py:143-154): the variance formula cancels
-        // catastrophically where tile results nearly coincide, so FMA contraction would change NaN / 0 outcomes
-        const float mean = __fdiv_rn(map[p], nf);
-        map[p] = mean;
-        if (map_sq)
-            map_sq[p] = __fsqrt_rn(__fdiv_rn(__fsub_rn(map_sq[p], __fmul_rn(__fmul_rn(mean, mean), nf)), nf - 1.f));
-        if (smap) {
-            const float sm = __fdiv_rn(smap[p], nf);
-            smap[p] = sm;
-            if (smap_sq)
-                smap_sq[p] = __fsqrt_rn(__fdiv_rn(__fsub_rn(smap_sq[p], __fmul_rn(__fmul_rn(sm, sm), nf)), nf - 1.f));
+    if (VEC) {
+        const long long nvec = npix / 8;
+        for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
+            const int4 w = __ldg(reinterpret_cast<const int4*>(count) + v);
+            const int words[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int n = (int)(short)((words[k >> 1] >> (16 * (k & 1))) & 0xffff);
+                if (n > 1) finalize_pixel(map, map_sq, smap, smap_sq, 8 * v + k, n);
+            }
+        }
+        for (long long p = nvec * 8 + (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += stride) {
+            const int n = count[p];
+            if (n > 1) finalize_pixel(map, map_sq, smap, smap_sq, p, n);
+        }
+    } else {
+        for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += stride) {
+            const int n = count[p];
+            if (n > 1) finalize_pixel(map, map_sq, smap, smap_sq, p, n);
         }
     }
 }
@@ -452,10 +475,13 @@ extern "C" int pc_finalize_map(float* map, float* map_sq, float* smap, float* sm
                                long long npix, pc_stream_t stream) {
     PC_CHECK_ARG(map && count, "null pointer");
     if (npix <= 0) return 0;
-    const int grid = (int)(cdiv(npix, 256) < num_sms() * 16 ? cdiv(npix, 256) : num_sms() * 16);
     static const int cat = prof_register("finalize");
     ProfScope prof(cat, (cudaStream_t)stream, (double)npix);
-    finalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(map, map_sq, smap, smap_sq, count, npix);
+    const bool vec = (((uintptr_t)count) % 16) == 0;
+    const long long work = vec ? cdiv(npix, 8) : npix;
+    const int grid = (int)(cdiv(work, 256) < num_sms() * 16 ? cdiv(work, 256) : num_sms() * 16);
+    if (vec) finalize_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(map, map_sq, smap, smap_sq, count, npix);
+    else finalize_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(map, map_sq, smap, smap_sq, count, npix);
     PC_LAUNCH_CHECK();
     return 0;
 }

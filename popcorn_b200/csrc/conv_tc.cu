@@ -404,27 +404,32 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
                     for (int cg = 0; cg < COUT; cg += 8) {
 #pragma unroll 1
                         for (int dy = 0; dy < 2; ++dy) {
-                            float u[2][2][8];                        // [row h][dx][co]
+                            // packed fp32 (fma.rn.f32x2): two adjacent output channels per instruction, weights read as 64-bit pairs
+                            unsigned long long u2[2][2][4];          // [row h][dx][co pair]
 #pragma unroll
-                            for (int o = 0; o < 8; ++o) {
-                                const float bo = ctb[cg + o];
-                                u[0][0][o] = bo; u[0][1][o] = bo; u[1][0][o] = bo; u[1][1][o] = bo;
+                            for (int o = 0; o < 4; ++o) {
+                                const unsigned long long bo = *reinterpret_cast<const unsigned long long*>(ctb + cg + 2 * o);
+                                u2[0][0][o] = bo; u2[0][1][o] = bo; u2[1][0][o] = bo; u2[1][1][o] = bo;
                             }
 #pragma unroll
                             for (int ci = 0; ci < COUT; ++ci) {
+                                const unsigned long long a0 = pack2(acc[0][ci], acc[0][ci]), a1 = pack2(acc[1][ci], acc[1][ci]);
 #pragma unroll
                                 for (int dx = 0; dx < 2; ++dx) {
                                     const float* wr = ctw + (ci * 4 + dy * 2 + dx) * COUT + cg;
-                                    const float4 wa = *reinterpret_cast<const float4*>(wr);
-                                    const float4 wb = *reinterpret_cast<const float4*>(wr + 4);
-                                    const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-#pragma unroll
-                                    for (int o = 0; o < 8; ++o) {
-                                        u[0][dx][o] = fmaf(acc[0][ci], wv[o], u[0][dx][o]);
-                                        u[1][dx][o] = fmaf(acc[1][ci], wv[o], u[1][dx][o]);
-                                    }
+                                    const ulonglong2 wa = *reinterpret_cast<const ulonglong2*>(wr);
+                                    const ulonglong2 wb = *reinterpret_cast<const ulonglong2*>(wr + 4);
+                                    fma2(u2[0][dx][0], a0, wa.x); fma2(u2[0][dx][1], a0, wa.y); fma2(u2[0][dx][2], a0, wb.x); fma2(u2[0][dx][3], a0, wb.y);
+                                    fma2(u2[1][dx][0], a1, wa.x); fma2(u2[1][dx][1], a1, wa.y); fma2(u2[1][dx][2], a1, wb.x); fma2(u2[1][dx][3], a1, wb.y);
                                 }
                             }
+                            float u[2][2][8];                        // [row h][dx][co]
+#pragma unroll
+                            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                                for (int dx = 0; dx < 2; ++dx)
+#pragma unroll
+                                    for (int o = 0; o < 4; ++o) unpack2(u2[h][dx][o], u[h][dx][2 * o], u[h][dx][2 * o + 1]);
 #pragma unroll
                             for (int h = 0; h < 2; ++h) {
                                 if (!row_ok[h]) continue;

@@ -337,6 +337,17 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
                 const int P = P0 + m, ps = P & (NDP - 1);
                 TCP_T(t0);
                 if (((warp - W_EPI0) & 3) == 0 && lane == 0) TCP_TRACE(4 + group, P, 0);
+                // EPI_DOT, second stream: the first stream's partial logits are fetched BEFORE the wait for the accumulators, so the DRAM round
+                // trip overlaps the UMMAs instead of sitting in the (single, at OCC 2) epilogue group's per-pair critical path
+                float din[2] = {0.f, 0.f};
+                if (EPI == EPI_DOT && job.dot_in) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int oy = y0 + 2 * m + h, yy = oy - p.crop_y, xx = vx - p.crop_x;
+                        if (in_x && oy < H && yy >= 0 && yy < p.crop_H && xx >= 0 && xx < p.crop_W)
+                            din[h] = __ldg(job.dot_in + (long long)yy * job.dot_in_rs + xx);
+                    }
+                }
                 mbar_wait_sleep(d_full(ps), (uint32_t)(P / NDP) & 1u);
                 tc_fence_after();
                 TCP_T(t1);
@@ -380,7 +391,7 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
                             float sacc = 0.f;
 #pragma unroll
                             for (int o = 0; o < 8; ++o) sacc = fmaf(acc[h][o], dotw[o], sacc);
-                            if (job.dot_in) sacc += job.dot_in[(long long)yy * job.dot_in_rs + xx];
+                            sacc += din[h];
                             if (job.dot_final) {
                                 sacc += dotb;
                                 sacc = 1.f / (1.f + expf(-sacc));

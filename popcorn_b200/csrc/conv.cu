@@ -36,10 +36,20 @@ __host__ __device__ constexpr int conv_cc() { return CIN < 4 ? CIN : 4; }       
 template <int CIN, int COUT>
 __host__ __device__ constexpr int conv_wfloats_padded() { return (CIN * 9 * COUT + COUT + 31) / 32 * 32; }   // 128-B multiple
 
+// The Cin = 2 first layer (SAR stream) walks PC_CONV_MT consecutive tiles of a row per CTA and stages tile t+1 while tile t is computed
+// (two buffers): the copies' DRAM latency, the weight load and the CTA launch are paid once per run instead of once per tile
+// (layer micro-benchmark 0.340 -> 0.308 ms per 33.5 Mpx).  Measured and NOT adopted for Cin = 4 (0.489 -> 0.527 ms: its tile already
+// carries twice the FFMA2 work to hide the copies behind).
+#ifndef PC_CONV_MT
+#define PC_CONV_MT 4
+#endif
+template <int CIN, bool TMA>
+__host__ __device__ constexpr int conv_mt() { return (CIN == 2 && !TMA) ? PC_CONV_MT : 1; }
+
 template <int CIN, int COUT, int EPI>
 constexpr int conv_smem_floats() {
     constexpr int CC = conv_cc<CIN>();
-    constexpr int NBUF = (CIN / CC) > 1 ? 2 : 1;
+    constexpr int NBUF = ((CIN / CC) > 1 || conv_mt<CIN, false>() > 1) ? 2 : 1;
     return conv_wfloats_padded<CIN, COUT>() + NBUF * CC * SROWS * SPITCH + 8 /* 2 mbarriers */ + 32 /* align slack */;
 }
 
@@ -81,7 +91,9 @@ conv3x3_kernel(const __grid_constant__ ConvParams p) {
     constexpr int CIN = CIN_A + CIN_B;
     constexpr int CC = conv_cc<CIN>();
     constexpr int NCHUNK = CIN / CC;
-    constexpr int NBUF = NCHUNK > 1 ? 2 : 1;
+    constexpr int MT = conv_mt<CIN, TMA>();               // tiles per CTA along x
+    constexpr int NBUF = (NCHUNK > 1 || MT > 1) ? 2 : 1;
+    static_assert(MT == 1 || EPI == EPI_STORE || EPI == EPI_POOL, "multi-tile CTAs: epilogues without an early return only");
     constexpr int NT = 128 * (COUT / 8);
     constexpr int NWARP = NT / 32;
     constexpr int WFLOATS = CIN * 9 * COUT + COUT;
@@ -100,7 +112,8 @@ conv3x3_kernel(const __grid_constant__ ConvParams p) {
     const int tx = threadIdx.x, ty = threadIdx.y, tz = threadIdx.z;
     const int tid = tx + 8 * ty + 128 * tz;
     const int lane = tid & 31, warp = tid >> 5;
-    const int x0 = blockIdx.x * TILE, y0 = blockIdx.y * TILE;
+    int x0 = blockIdx.x * (MT * TILE);                    // advances by TILE per tile of this CTA's run
+    const int y0 = blockIdx.y * TILE;
     const int H = p.H, W = p.W;
 
     // ---- stage CC channels of the (virtual) input tile with a 1-px halo: all copies are issued
@@ -188,6 +201,12 @@ conv3x3_kernel(const __grid_constant__ ConvParams p) {
     for (int i = tid; i < WFLOATS / 4; i += NT)
         reinterpret_cast<float4*>(ws)[i] = __ldg(reinterpret_cast<const float4*>(job.w) + i);
 
+#pragma unroll 1
+    for (int mt = 0; mt < MT; ++mt, x0 += TILE) {
+    if (MT > 1) {
+        if (x0 >= W) break;
+        if (mt > 0) __syncthreads();        // every thread is done with the buffer the next prefetch overwrites
+    }
     float acc[2][4][8];
     unsigned long long acc2[2][4][4];
 #pragma unroll
@@ -202,8 +221,19 @@ conv3x3_kernel(const __grid_constant__ ConvParams p) {
 
 #pragma unroll 1
     for (int chunk = 0; chunk < NCHUNK; ++chunk) {
-        float* cur = xs + (chunk & (NBUF - 1)) * XBUF;
-        if (TMA) {
+        float* cur = xs + ((MT > 1 ? mt : chunk) & (NBUF - 1)) * XBUF;
+        if (MT > 1) {
+            if (mt + 1 < MT && x0 + TILE < W) {         // stage the run's next tile into the other buffer, then wait for this one
+                x0 += TILE;
+                stage(0, xs + ((mt + 1) & 1) * XBUF);
+                x0 -= TILE;
+                cp_async_commit();
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncthreads();
+        } else if (TMA) {
             if (chunk == 0) __syncthreads();   // weights + barrier init visible to every thread
             if (chunk + 1 < NCHUNK && tid == 0) stage_tma(chunk + 1);   // prefetch into the other buffer
             mbar_wait_parity(bar0 + 8 * (chunk & (NBUF - 1)), (chunk / NBUF) & 1);
@@ -267,7 +297,7 @@ conv3x3_kernel(const __grid_constant__ ConvParams p) {
                     }
                 }
         }
-        if (NBUF > 1) __syncthreads();  // `cur` is refilled by the prefetch issued at the top of the next-but-one chunk
+        if (NBUF > 1 && MT == 1) __syncthreads();  // `cur` is refilled by the prefetch issued at the top of the next-but-one chunk
     }
 
     // ---------------- epilogue: bias + ReLU, then store / pool / logit dot ----------------
@@ -342,6 +372,7 @@ conv3x3_kernel(const __grid_constant__ ConvParams p) {
             }
         }
     }
+    }   // tiles of this CTA's run (MT)
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -506,7 +537,8 @@ static bool make_tmap(CUtensorMap* tm, const float* ptr, int C, int H, int W, in
 template <int CIN_A, int CIN_B, int COUT, int EPI, bool X2, bool TMA>
 static int launch_conv_impl(const ConvParams& p, int njobs, cudaStream_t st) {
     constexpr int smem = conv_smem_floats<CIN_A + CIN_B, COUT, EPI>() * 4;
-    dim3 grid(cdiv(p.W, TILE), cdiv(p.H, TILE), njobs), block(8, 16, COUT / 8);
+    constexpr int MT = conv_mt<CIN_A + CIN_B, TMA>();
+    dim3 grid(cdiv(cdiv(p.W, TILE), MT), cdiv(p.H, TILE), njobs), block(8, 16, COUT / 8);
     auto k = conv3x3_kernel<CIN_A, CIN_B, COUT, EPI, X2, TMA>;
     PC_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     k<<<grid, block, smem, st>>>(p);

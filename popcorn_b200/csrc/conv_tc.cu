@@ -13,7 +13,7 @@
 //     accumulators of rows r-1, r, r+1 are adjacent ring slots, so ONE N=48 UMMA per k-step and split term feeds all
 //     three (two UMMAs where the ring wraps; fewer rows at tile borders).  Accumulators are always accumulated into:
 //     the epilogue zeroes a slot after reading it;
-//   * per input row: 3*Cin/8 (k-steps) x 3 (hi*hi + lo*hi + hi*lo) tcgen05.mma kind::tf32, N/2 = 24 cycles each
+//   * per input row: 3*Cin/8 (TF32) | ceil(3*Cin/16) (fp16) k-steps x 3 (hi*hi + lo*hi + hi*lo) tcgen05.mma, N/2 = 24 cycles each
 //     (tools/probe/umma_probe.cu) -> 27*Cin cycles per 128 pixels.
 // Warp-specialised pipeline (576 threads), every hand-off is an mbarrier, nothing is block-synchronous:
 //   warp 17     TMA     : one lane streams input rows (all channels, 136 floats: 128 px + halo, zero-filled outside

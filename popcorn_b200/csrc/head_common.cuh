@@ -1,4 +1,4 @@
-// Shared declarations of the occupancy-head kernels (SIMT fp32 and tcgen05 3xTF32 variants).
+// Shared declarations of the occupancy-head kernels (SIMT fp32 and tcgen05 split-operand variants).
 #pragma once
 #include "common.cuh"
 

@@ -1,11 +1,11 @@
 // tcgen05 / TMEM / mbarrier primitives shared by the tensor-core kernels (head_tc.cu, conv_tc.cu), sm_100a only.
 //
 // Conventions used by both kernels:
-//   * UMMA M = 128 (one TMEM lane per pixel), cta_group::1, kind::tf32 with fp32 accumulation in TMEM;
+//   * UMMA M = 128 (one TMEM lane per pixel), cta_group::1, kind::f16 (default) or kind::tf32 with fp32 accumulation in TMEM;
 //   * the A operand (activations) lives in TMEM and is written with tcgen05.st by the thread that owns the lane;
 //   * the B operand (weights) lives in shared memory, pre-split (hi/lo) and pre-swizzled on the host into the
 //     canonical K-major SWIZZLE_128B layout: 32-float K-atoms, 128 B per row, 8-row groups 1024 B apart;
-//   * error-compensated 3xTF32: x = hi + lo (hi = top 19 bits), D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo.
+//   * error-compensated split operands: x = hi + lo (fp16 pairs, or TF32 with hi = top 19 bits), D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo.
 #pragma once
 #include "common.cuh"
 

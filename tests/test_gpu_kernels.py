@@ -20,7 +20,7 @@ def _pack_conv(w, b):
 
 
 def _pack_conv_tc(w, b, tc):
-    """tc=True: the layer's tcgen05 weight image (3xTF32 split, SWIZZLE_128B), built by the library's host packer."""
+    """tc=True: the layer's tcgen05 weight image (hi/lo split operands, SWIZZLE_128B), built by the library's host packer."""
     if not tc:
         return None
     L = _lib.lib()
@@ -213,8 +213,8 @@ def test_sparsity_mask_compaction_is_bit_exact(B, H, W, empty):
     assert torch.equal(idx[:n].long().cpu(), ref.reshape(-1).nonzero()[:, 0])    # row-major (b,h,w) order
 
 
-def test_accumulate_and_finalize_match_run_eval_arithmetic():
-    H, W, ps, ov = 200, 236, 96, 16
+@pytest.mark.parametrize("H,W,ps,ov", [(200, 236, 96, 16), (201, 237, 97, 15)], ids=["aligned_vector_path", "odd_scalar_path"])
+def test_accumulate_and_finalize_match_run_eval_arithmetic(H, W, ps, ov):
     g = torch.Generator().manual_seed(1)
     maps = [torch.zeros(H, W, device="cuda") for _ in range(4)] + [torch.zeros(H, W, dtype=torch.int16, device="cuda")]
     ref = [torch.zeros(H, W) for _ in range(4)] + [torch.zeros(H, W, dtype=torch.int16)]
@@ -238,10 +238,44 @@ def test_accumulate_and_finalize_match_run_eval_arithmetic():
         assert torch.allclose(a.cpu(), b, rtol=1e-5, atol=1e-5, equal_nan=True)
 
 
+@pytest.mark.parametrize("cols,origin", [((16, 78), (8, 12)), ((16, 80), (8, 12)), ((17, 80), (8, 12)), ((16, 80), (8, 13))],
+                         ids=["vector_with_tail", "vector", "odd_c0", "odd_x0"])
+def test_accumulate_vector_and_scalar_paths_agree_with_torch(cols, origin):
+    """pc_accumulate_tile takes 4 pixels per thread when tile, maps and column range are 16-byte aligned (with a scalar tail) and one pixel
+    per thread otherwise: every variant must give the element-wise result bit for bit; pc_finalize_map reads the counts 8 at a time when
+    its slice is 16-byte aligned (rows=(0, n)) and one at a time otherwise (rows=(1, n))."""
+    g = torch.Generator().manual_seed(5)
+    H, W, ps = 120, 140, 96            # 140 int16 = 280 B per count row: rows=(1, ..) is not 16-byte aligned
+    d, sc = torch.rand(ps, ps, generator=g), torch.rand(ps, ps, generator=g)
+    maps = [torch.rand(H, W, generator=g).cuda() for _ in range(4)] + [torch.ones(H, W, dtype=torch.int16, device="cuda")]
+    ref = [m.cpu().clone() for m in maps]
+    r0, r1, (c0, c1), (y0, x0) = 16, 80, cols, origin
+    ops.accumulate_tile(d.cuda(), sc.cuda(), (r0, r1), (c0, c1), maps, y0, x0)
+    sl = (slice(y0 + r0, y0 + r1), slice(x0 + c0, x0 + c1))
+    dd, ss = d[r0:r1, c0:c1], sc[r0:r1, c0:c1]
+    ref[0][sl] += dd; ref[1][sl] += dd * dd; ref[2][sl] += ss; ref[3][sl] += ss * ss; ref[4][sl] += 1
+    for a, b in zip(maps, ref):
+        assert torch.equal(a.cpu(), b)
+    for rows in ((0, H), (1, H - 1)):
+        fin = [m.clone() for m in maps]
+        ops.finalize_map(fin, rows=rows)
+        want = [m.clone() for m in ref]
+        blk = slice(rows[0], rows[1])
+        div = torch.zeros(H, W, dtype=torch.bool)
+        div[blk] = want[4][blk] > 1
+        cf = want[4][div].float()
+        want[0][div] = want[0][div] / cf
+        want[1][div] = torch.sqrt((want[1][div] - want[0][div] ** 2 * cf) / (cf - 1))
+        want[2][div] = want[2][div] / cf
+        want[3][div] = torch.sqrt((want[3][div] - want[2][div] ** 2 * cf) / (cf - 1))
+        for a, b in zip(fin[:4], want[:4]):
+            assert torch.allclose(a.cpu(), b, rtol=1e-6, atol=0, equal_nan=True)
+
+
 @pytest.mark.parametrize("head_in", [16, 8])
 @pytest.mark.parametrize("B,H,W", [(1, 64, 96), (2, 37, 53), (1, 300, 517)])
 def test_head_tensor_core_matches_simt_and_oracle(head_in, B, H, W):
-    """tcgen05 3xTF32 head (activations in TMEM) vs the fp32 SIMT head and the torch fp32 MLP."""
+    """tcgen05 split-operand head (activations in TMEM) vs the fp32 SIMT head and the torch fp32 MLP."""
     from popcorn_b200 import weights
     g = torch.Generator().manual_seed(H + head_in)
     sd = po.random_state_dict(seed=3, head_in=head_in)

@@ -43,8 +43,11 @@ __host__ __device__ constexpr int conv_wfloats_padded() { return (CIN * 9 * COUT
 #ifndef PC_CONV_MT
 #define PC_CONV_MT 4
 #endif
+#ifndef PC_CONV_MT4
+#define PC_CONV_MT4 1
+#endif
 template <int CIN, bool TMA>
-__host__ __device__ constexpr int conv_mt() { return (CIN == 2 && !TMA) ? PC_CONV_MT : 1; }
+__host__ __device__ constexpr int conv_mt() { return TMA ? 1 : CIN == 2 ? PC_CONV_MT : CIN == 4 ? PC_CONV_MT4 : 1; }
 
 template <int CIN, int COUT, int EPI>
 constexpr int conv_smem_floats() {

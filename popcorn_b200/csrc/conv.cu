@@ -435,6 +435,13 @@ __global__ void __launch_bounds__(128) convt2x2_kernel(const __grid_constant__ C
 // ---------------------------------------------------------------------------------------------------
 // Host side: packed-weight layout and the layer schedule
 // ---------------------------------------------------------------------------------------------------
+static bool first_layer_tc_enabled() {     // POPCORN_CONV_TC_L0=0: keep the first layer on the fp32 stencil even where the tensor-core kernel could run it
+    static const bool on = [] {
+        const char* e = getenv("POPCORN_CONV_TC_L0");
+        return e ? atoi(e) != 0 : true;
+    }();
+    return on;
+}
 constexpr int PC_NO_TC = -7001;   // launch_conv<..., EPI_CONVT>: no tensor-core launch was possible (internal, never returned to callers)
 struct LayerSpec { int cin, cout, is_t; };
 static const LayerSpec kLayers[12] = {
@@ -565,8 +572,21 @@ static int launch_conv(ConvParams& p, int njobs, cudaStream_t st) {
     }();
     // tensor-core path (conv_tc.cu): every job carries a pre-swizzled weight image and its sources can be read by TMA
     // (plain planes: not the reflect-padded, channel-remapped first layer, which stays on the fp32 stencil)
-    bool tc = conv_tc_enabled() && CIN_A >= 8;
-    for (int j = 0; tc && j < njobs; ++j) tc = p.jobs[j].wtc != nullptr && !p.jobs[j].a_reflect;
+    // The first layer (Cin 2 | 4, Cout 8, plain store) qualifies when its source needs no reflection and its channel map is a contiguous
+    // run of planes: (c0, c0 + 1) for the SAR stream, the optical stream's (c0 + 2, c0 + 1, c0, c0 + 3) — that permutation is folded into
+    // the layer's tensor-core weight image (pc_dda_tc_pack), so ONE TMA box of Cin planes starting at c0 feeds it.
+    constexpr bool first_layer = CIN_A < 8;
+    bool tc = conv_tc_enabled() && (CIN_A >= 8 || (CIN_B == 0 && COUT == 8 && EPI == EPI_STORE && first_layer_tc_enabled()));
+    int c0[MAX_JOBS] = {0};
+    for (int j = 0; tc && j < njobs; ++j) {
+        const ConvJob& J = p.jobs[j];
+        tc = J.wtc != nullptr && !J.a_reflect;
+        if (tc && first_layer) {
+            c0[j] = (CIN_A == 2) ? (int)(J.a_chmap & 0xff) : (int)((J.a_chmap >> 16) & 0xff);
+            const unsigned want = (CIN_A == 2) ? (0x00000100u + 0x00000101u * (unsigned)c0[j]) : (0x03000102u + 0x01010101u * (unsigned)c0[j]);
+            tc = J.a_chmap == want && (J.a_ox & 3) == 0;
+        }
+    }
     if (tc) {
         TcConvParams tp;
         memset(&tp, 0, sizeof(tp));
@@ -574,7 +594,7 @@ static int launch_conv(ConvParams& p, int njobs, cudaStream_t st) {
         for (int j = 0; tc && j < njobs; ++j) {
             const ConvJob& J = p.jobs[j];
             tp.jobs[j] = J;
-            tc = make_tmap3d(&tp.tmA[j], J.a, CIN_A, J.a_H, J.a_W, J.a_rs, J.a_cs, TC_BOXW, 1, CIN_A);
+            tc = make_tmap3d(&tp.tmA[j], J.a + (long long)c0[j] * J.a_cs, CIN_A, J.a_H, J.a_W, J.a_rs, J.a_cs, TC_BOXW, 1, CIN_A);
             if (tc && CIN_B > 0) tc = make_tmap3d(&tp.tmB[j], J.b, CIN_B, J.b_H, J.b_W, J.b_rs, J.b_cs, TC_BOXW, 1, CIN_B);
         }
         if (tc) return launch_conv_tc(CIN_A, CIN_B, COUT, EPI, tp, njobs, st);
@@ -633,7 +653,18 @@ extern "C" int pc_dda_tc_pack(const float* flat_host, float* img_host) {
         for (int l = 0; l < 12; ++l) {
             if (kLayers[l].is_t) continue;
             const int cin = kLayers[l].cin < 0 ? (s == 0 ? 2 : 4) : kLayers[l].cin;
-            conv_tc_pack_layer(flat_host + pack_offset(s, l), cin, kLayers[l].cout, img_host + tc_pack_offset(s, l));
+            const float* flat = flat_host + pack_offset(s, l);
+            float perm[4 * 9 * 8 + 8];
+            if (s == 1 && l == 0) {
+                // optical first layer: the tensor-core kernel reads the planes in MEMORY order (R, G, B, NIR) with one TMA box, the fp32 pack
+                // is in the network's channel order (B, G, R, NIR = planes 2, 1, 0, 3): plane q holds logical channel (2, 1, 0, 3)[q]
+                static const int logical_of_plane[4] = {2, 1, 0, 3};
+                const int per = 9 * kLayers[l].cout;
+                for (int q = 0; q < 4; ++q) memcpy(perm + q * per, flat + logical_of_plane[q] * per, sizeof(float) * per);
+                memcpy(perm + 4 * per, flat + 4 * per, sizeof(float) * kLayers[l].cout);
+                flat = perm;
+            }
+            conv_tc_pack_layer(flat, cin, kLayers[l].cout, img_host + tc_pack_offset(s, l));
         }
     return 0;
 }
@@ -696,7 +727,9 @@ extern "C" int pc_dda_forward(const float* wpack, long long wpack_floats, const 
             for (int k = 0; k < nb; ++k) {
                 ConvJob& j = p.jobs[k];
                 j.a = x + (long long)(b0 + k) * x_bstride; j.a_cs = x_cstride; j.a_rs = x_rstride;
-                j.a_H = H; j.a_W = W; j.a_oy = pad_top; j.a_ox = pad_left; j.a_reflect = 1;
+                j.a_H = H; j.a_W = W; j.a_oy = pad_top; j.a_ox = pad_left;
+                // without virtual padding the virtual image IS the source: "outside" = the conv's zero padding, which a plain (TMA) load gives too
+                j.a_reflect = (pad_top | pad_bottom | pad_left | pad_right) ? 1 : 0;
                 // [R,G,B,NIR,VV,VH] -> sar (VV,VH) | optical (B,G,R,NIR)   popcorn.py:130-134
                 if (C == 6) j.a_chmap = (s == 0) ? 0x00000504u : 0x03000102u;
                 else if (C == 2) j.a_chmap = 0x00000100u;

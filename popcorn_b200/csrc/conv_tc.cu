@@ -89,7 +89,7 @@ constexpr int TCN = 16;            // UMMA N (output channels, zero-padded)
 #define PC_TC_PAIRS16 1            // <8,8,8> (Cin 16, Cout 8): 1 = two issuers with pair ownership, 0 = one issuer with 3-row windows
 #endif
 __host__ __device__ constexpr int tc_occ(int cin_a, int cin_b, int cout, int epi) {
-    return (cin_a == 8 && cin_b == 0 && cout == 8 && (epi == EPI_STORE || epi == EPI_DOT) && (PC_TC_OCC2 & 1)) ? 2
+    return (cin_a <= 8 && cin_b == 0 && cout == 8 && (epi == EPI_STORE || epi == EPI_DOT) && (PC_TC_OCC2 & 1)) ? 2
          : (cin_a == 8 && cin_b == 0 && cout == 8 && epi == EPI_POOL && (PC_TC_OCC2 & 2)) ? 2
          : (cin_a == 8 && cin_b == 0 && cout == 16 && (PC_TC_OCC2 & 4)) ? 2
          : (cin_a == 8 && cin_b == 8 && cout == 8 && (PC_TC_OCC2 & 8)) ? 2 : 1;
@@ -122,9 +122,10 @@ struct TcGeom {
                                                                 // the stagers run ahead of the UMMAs of the two batches before), Cin 16 -> 4, Cin 32 -> 2
     static constexpr int D_COL0 = NA * A_COLS;                  // accumulator slots of 16 columns
     static constexpr int STAGE_BYTES = CIN * TC_BOXW * 4;       // one input row, all channels
+    static constexpr int STAGE_STRIDE = (STAGE_BYTES + 127) / 128 * 128;   // ring slot pitch: a TMA destination is 128-byte aligned (Cin 2: 1088 -> 1152)
     static constexpr int NS = CIN <= 8 ? 16 : CIN <= 16 ? 8 : 4;   // shared-memory ring depth (~70 KB in flight per SM)
     static constexpr int OFF_STAGE = (IMG_BYTES + 127) / 128 * 128;
-    static constexpr int OFF_BARS = OFF_STAGE + NS * STAGE_BYTES;   // s_full[NS] s_empty[NS] full_a[NA/2] empty_a[NA/2] d_full[ND/2] d_empty[ND/2]
+    static constexpr int OFF_BARS = OFF_STAGE + NS * STAGE_STRIDE;   // s_full[NS] s_empty[NS] full_a[NA/2] empty_a[NA/2] d_full[ND/2] d_empty[ND/2]
     static constexpr int NBARS = 2 * NS + 2 * NA + 2 * ND;
     static constexpr int OFF_TMEM = OFF_BARS + 8 * NBARS;
     static constexpr int OFF_CTW = (OFF_TMEM + 16 + 15) / 16 * 16;  // EPI_CONVT: [COUT][4][COUT] + bias[COUT] floats of the transposed conv
@@ -134,7 +135,7 @@ struct TcGeom {
     static constexpr int SMEM_BYTES = OCC == 2 ? SMEM_NEED : (SMEM_NEED > 116 * 1024 ? SMEM_NEED : 116 * 1024);
     static_assert(NA_FIT >= 2, "TMEM budget");
     static_assert(D_COL0 % 16 == 0 && D_COL0 + ND * SLOTW <= TMEM_COLS, "accumulator ring placement");
-    static_assert(STAGE_BYTES % 128 == 0 && SMEM_BYTES * OCC <= 226 * 1024, "shared memory layout");
+    static_assert(SMEM_BYTES * OCC <= 226 * 1024, "shared memory layout");
 };
 
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -254,7 +255,7 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
                 tc_fence_after();
                 TCP_T(t2);
                 if ((warp & 3) == 0 && lane == 0) TCP_TRACE(group, B, 3);
-                const float* st = stage0 + s * (G::STAGE_BYTES / 4);
+                const float* st = stage0 + s * (G::STAGE_STRIDE / 4);
                 const uint32_t tA = tbase + (uint32_t)(2 * pb + group) * G::A_COLS + lane_off;
                 auto a_elem = [&](int k) {                                                   // A element k = kx * CIN + ci
                     return (k < 3 * CIN) ? ((PC_TC_EXP & 4) ? (float)(k + px) : st[(k % CIN) * TC_BOXW + k / CIN]) : 0.f;
@@ -276,17 +277,16 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
                         tmem_st16(tA + 16 * j, hi);
                         tmem_st16(tA + G::KROW + 16 * j, lo);
                     }
-                } else {                                            // KROW = 24: [hi 0..23 | lo 0..23] = 48 contiguous columns, three stores
-                    static_assert(G::KROW % 16 == 0 || G::KROW == 24, "stager store shapes");
-                    uint32_t w[48];
+                } else {                                            // KROW = 24 | 8: [hi | lo] = 48 | 16 contiguous columns, three stores | one
+                    static_assert(G::KROW % 16 == 0 || G::KROW == 24 || G::KROW == 8, "stager store shapes");
+                    uint32_t w[2 * G::KROW];
 #pragma unroll
-                    for (int q = 0; q < 24; ++q) load_split(q, w[q], w[24 + q]);
+                    for (int q = 0; q < G::KROW; ++q) load_split(q, w[q], w[G::KROW + q]);
                     if (!(PC_TC_EXP & 2)) {
-                        tmem_st16(tA, reinterpret_cast<uint32_t(&)[16]>(w[0]));
-                        tmem_st16(tA + 16, reinterpret_cast<uint32_t(&)[16]>(w[16]));
-                        tmem_st16(tA + 32, reinterpret_cast<uint32_t(&)[16]>(w[32]));
+#pragma unroll
+                        for (int j = 0; j < 2 * G::KROW / 16; ++j) tmem_st16(tA + 16 * j, reinterpret_cast<uint32_t(&)[16]>(w[16 * j]));
                     } else {
-                        asm volatile("" ::"r"(w[0] ^ w[13] ^ w[24] ^ w[47]));
+                        asm volatile("" ::"r"(w[0] ^ w[G::KROW - 1] ^ w[G::KROW] ^ w[2 * G::KROW - 1]));
                     }
                 }
 #else
@@ -597,7 +597,7 @@ conv3x3_tc_kernel(const __grid_constant__ TcConvParams p) {
             for (int r = -1; r <= nrows; ++r, ++i) {
                 const int s = i % NS, n = i / NS;
                 if (n >= 1) mbar_wait_sleep(s_empty(s), (uint32_t)(n - 1) & 1u);
-                const uint32_t dst = stage_base + (uint32_t)s * G::STAGE_BYTES;
+                const uint32_t dst = stage_base + (uint32_t)s * G::STAGE_STRIDE;
                 mbar_expect_tx(s_full(s), G::STAGE_BYTES);
                 tma_load_3d(dst, tmA, x0 - 4 - job.a_ox, y0 + r - job.a_oy, 0, s_full(s));
                 if (CIN_B > 0) tma_load_3d(dst + CIN_A * TC_BOXW * 4, tmB, x0 - 4 - job.b_ox, y0 + r - job.b_oy, 0, s_full(s));
@@ -734,6 +734,8 @@ static int launch_tc_impl(TcConvParams& p, int njobs, cudaStream_t st) {
 int launch_conv_tc(int cin_a, int cin_b, int cout, int epi, TcConvParams& p, int njobs, cudaStream_t st) {
     const int key = ((cin_a * 100 + cin_b) * 100 + cout) * 10 + epi;
     switch (key) {
+        case ((2 * 100 + 0) * 100 + 8) * 10 + EPI_STORE: return launch_tc_impl<2, 0, 8, EPI_STORE>(p, njobs, st);   // first layer, SAR stream
+        case ((4 * 100 + 0) * 100 + 8) * 10 + EPI_STORE: return launch_tc_impl<4, 0, 8, EPI_STORE>(p, njobs, st);   // first layer, optical stream
         case ((8 * 100 + 0) * 100 + 8) * 10 + EPI_STORE: return launch_tc_impl<8, 0, 8, EPI_STORE>(p, njobs, st);
         case ((8 * 100 + 0) * 100 + 8) * 10 + EPI_POOL: return launch_tc_impl<8, 0, 8, EPI_POOL>(p, njobs, st);
         case ((8 * 100 + 0) * 100 + 8) * 10 + EPI_DOT: return launch_tc_impl<8, 0, 8, EPI_DOT>(p, njobs, st);

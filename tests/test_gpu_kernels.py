@@ -94,6 +94,40 @@ def test_conv3x3_tc_overflow_is_loud():
         assert torch.isfinite(out).all() and abs(float(hit[0, 1, 1]) - (7.1 + 3.0e4)) < 0.1
 
 
+@pytest.mark.parametrize("stream", ["sar", "optical"])
+@pytest.mark.parametrize("H,W,tc_path", [(64, 128, True), (70, 300, True), (37, 53, False)], ids=["64x128", "70x300", "odd_falls_back"])
+def test_first_layer_on_tensor_cores(stream, H, W, tc_path):
+    """The first conv layer of a stream on tcgen05 (csrc/conv.cu launch_conv, first_layer): an unpadded source whose channel map is a
+    contiguous run of planes — SAR = planes (4, 5) of a 6-plane tensor, optical = planes (2, 1, 0, 3) with the permutation folded into the
+    weight image — is read with ONE TMA box of Cin planes; anything else (odd strides here) falls back to the fp32 stencil.  Both paths
+    must agree with torch's conv on the reordered channels."""
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(H + W)
+    x = torch.randn(6, H, W, generator=g).cuda()
+    cin = 2 if stream == "sar" else 4
+    order = [4, 5] if stream == "sar" else [2, 1, 0, 3]
+    chmap = 0x00000504 if stream == "sar" else 0x03000102
+    w = (torch.randn(8, cin, 3, 3, generator=g) * 0.3)
+    b = torch.randn(8, generator=g)
+    flat = _pack_conv(w, b)                                   # network channel order (what the fp32 stencil multiplies)
+    w_mem = w if stream == "sar" else w[:, [2, 1, 0, 3]]      # memory plane order (what the tensor-core image holds): plane q = logical (2,1,0,3)[q]
+    img = torch.zeros(L.pc_conv_tc_layer_floats(cin, 8))
+    flat_mem = _pack_conv(w_mem, b)                           # named: the host packer reads it through a raw pointer
+    _lib.check(L.pc_conv_tc_pack_layer(flat_mem.data_ptr(), cin, 8, img.data_ptr()))
+    img, flat_d = img.cuda(), flat.cuda()
+    out = torch.full((8, H, W), float("nan"), device="cuda")
+    ops.profile_enable(True)
+    _lib.check(L.pc_conv3x3_layer(x.data_ptr(), cin, x.stride(0), x.stride(1), H, W, 0, 0, 0, chmap, None, 0, 0, 0, 0, 0, 0, 0,
+                                  flat_d.data_ptr(), img.data_ptr(), 8, 1, H, W, out.data_ptr(), out.stride(0), out.stride(1),
+                                  None, 0, 0, _st()), "pc_conv3x3_layer")
+    torch.cuda.synchronize()
+    ops.profile_enable(False)
+    ran = [k for k, v in ops.profile_results().items() if v[1] > 0]
+    assert any(k.startswith(f"conv3x3_tc<{cin},0,8") for k in ran) == tc_path, ran
+    ref = F.relu(F.conv2d(x[order][None].cpu(), w, b, padding=1))[0]
+    assert torch.allclose(out.cpu(), ref, rtol=1e-4, atol=1e-4), float((out.cpu() - ref).abs().max())
+
+
 @pytest.mark.parametrize("c", [8, 16])
 @pytest.mark.parametrize("H,W", [(64, 64), (37, 52), (50, 36), (66, 260)])
 @TC

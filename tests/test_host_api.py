@@ -184,6 +184,38 @@ def test_conv_tc_weight_image_layout(cin, cout):
     assert torch.equal(img[2 * mat: 2 * mat + cout], b) and float(img[2 * mat + cout: 2 * mat + 16].abs().sum()) == 0
 
 
+def test_dda_tc_pack_first_layers():
+    """pc_dda_tc_pack: every 3x3 layer's image equals pc_conv_tc_pack_layer of its fp32 block — except the optical stream's first layer,
+    whose input channels are permuted to MEMORY plane order (R, G, B, NIR = logical channels 2, 1, 0, 3 of the network's B, G, R, NIR
+    input), because the tensor-core first layer reads its planes with one TMA box (csrc/conv.cu launch_conv, first_layer)."""
+    L = _lib.lib()
+    n_fp32 = L.pc_dda_pack_floats()
+    g = torch.Generator().manual_seed(3)
+    flat = torch.randn(n_fp32, generator=g)
+    img = torch.zeros(L.pc_dda_tc_pack_floats())
+    _lib.check(L.pc_dda_tc_pack(flat.data_ptr(), img.data_ptr()))
+
+    def layer_image(block, cin):
+        out = torch.zeros(L.pc_conv_tc_layer_floats(cin, 8))
+        _lib.check(L.pc_conv_tc_pack_layer(block.contiguous().data_ptr(), cin, 8, out.data_ptr()))
+        return out
+
+    # stream 0 (SAR, Cin 2), layer 0: plain
+    b0 = flat[L.pc_dda_pack_offset(0, 0): L.pc_dda_pack_offset(0, 1)]
+    n0 = L.pc_conv_tc_layer_floats(2, 8)
+    assert torch.equal(img[:n0], layer_image(b0, 2))
+    # stream 1 (optical, Cin 4), layer 0: channels permuted (2, 1, 0, 3), bias unchanged; its image follows stream 0's ten conv layers
+    b1 = flat[L.pc_dda_pack_offset(1, 0): L.pc_dda_pack_offset(1, 1)]
+    w = b1[:4 * 72].view(4, 72)
+    perm = torch.cat([w[[2, 1, 0, 3]].reshape(-1), b1[4 * 72:]])
+    cins = (2, 8, 8, 16, 16, 16, 32, 8, 16, 8)
+    couts = (8, 8, 16, 16, 16, 16, 8, 8, 8, 8)
+    off1 = sum(L.pc_conv_tc_layer_floats(ci, co) for ci, co in zip(cins, couts))
+    n1 = L.pc_conv_tc_layer_floats(4, 8)
+    assert torch.equal(img[off1: off1 + n1], layer_image(perm, 4))
+    assert not torch.equal(img[off1: off1 + n1], layer_image(b1, 4))
+
+
 def test_head_tc_weight_image_layout():
     """weights.pack_head_tc: the three [64 x K] matrices sit at the byte offsets csrc/head_tc.cu names (W1hi 0, W1lo 8192, W2hi 16384,
     W2lo 32768, W3hi 49152, W3lo 65536, vectors at 81920) in the library's operand format, K-major SWIZZLE_128B, and hi + lo gives the

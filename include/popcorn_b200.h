@@ -72,7 +72,9 @@ int pc_dda_pack_offset(int stream, int layer);
  * row; build with TC_OPERANDS=tf32), see pc_tc_operand_format() — then bias[16].
  * It is appended to the fp32 pack at float offset pc_dda_tc_pack_base() (the fp32 pack rounded up to 256 B) and is
  * pc_dda_tc_pack_floats() long; pc_dda_tc_pack converts a HOST fp32 pack into a HOST image (pure host code).
- * pc_dda_forward uses the tensor-core kernels when the pack it is given is long enough to hold the section. */
+ * pc_dda_forward uses the tensor-core kernels when the pack it is given is long enough to hold the section.
+ * The image of the optical stream's FIRST layer holds its four input channels in memory plane order (R, G, B, NIR = network channels
+ * 2, 1, 0, 3): where the source needs no reflection that layer reads its planes with one TMA box (csrc/conv.cu launch_conv). */
 int pc_dda_tc_pack_base(void);
 int pc_dda_tc_pack_floats(void);
 int pc_dda_tc_pack(const float* flat_host, float* img_host);
